@@ -1,0 +1,153 @@
+/*
+ * dbnet_b200.h — C-ABI of the B200-native DBNet++ detection hot path.
+ *
+ * The reference (ZenHKD/ocr-vi-invoice) is pure Python and has no FFI of its own; every entry
+ * point below replaces one torch / torchvision / cv2 call site of the reference's detection path
+ * (file:line relative to the reference tree).  Plain pointers and sizes only, no torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; b200_last_error() gives the text.
+ *     Nothing throws or aborts (reference only has try/except around unclip, src/det/test.py:87-95).
+ *   - device pointers are owned by the caller; the library allocates nothing on the device.
+ *   - `stream` is a cudaStream_t passed as void*.  Entry points are re-entrant per stream.
+ *   - activations are NHWC bf16 unless stated; fp32 maps are NCHW as in the reference's dict.
+ */
+#ifndef DBNET_B200_H
+#define DBNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_ABI_VERSION 1
+
+/* ---- status ------------------------------------------------------------------------------- */
+int         b200_abi_version(void);
+const char* b200_last_error(void);
+/* 0 when device `dev` is an sm_100 part this library can run on. */
+int         b200_device_check(int dev);
+
+/* ---- implicit-GEMM convolution family (tcgen05 + TMEM + TMA) --------------------------------
+ * Replaces: nn.Conv2d + BatchNorm2d + ReLU chains of torchvision Bottleneck (resnet.py:143-163 via
+ * model/det/backbone.py:34-37), ConvBnRelu (model/det/layers.py:13-18), the lateral / smoothing
+ * convs (model/det/neck.py:16,21,31-39), offset_mask_conv (model/det/dcn.py:17-25,42),
+ * ConvTranspose2d 2x2 s2 (model/det/head.py:13,21) and, in B200_IGEMM_DCN mode,
+ * torchvision.ops.deform_conv2d (model/det/dcn.py:48-57).
+ */
+enum {
+    B200_IGEMM_CONV = 0, /* 1x1 / 3x3, stride 1 or 2, zero padding (k-1)/2; A operand by TMA     */
+    B200_IGEMM_STEM = 1, /* 7x7 s2 p3 conv on the space-to-depth buffer of b200_stem_pack; A rows
+                            (128 contiguous bytes each) copied by producer warps                 */
+    B200_IGEMM_DCN  = 2  /* modulated deformable conv v2, 3x3; A operand gathered + blended      */
+};
+
+enum {
+    B200_EPI_RELU       = 1,  /* max(v, 0)                                                        */
+    B200_EPI_RES        = 2,  /* v += residual[same pixel]               (Bottleneck identity)   */
+    B200_EPI_RES_UP2    = 4,  /* v += residual[(y>>1, x>>1)]             (neck.py:36-38 nearest) */
+    B200_EPI_OUT_F32    = 8,  /* store fp32 instead of bf16              (offset/mask conv)      */
+    B200_EPI_SHUFFLE2   = 16  /* N = 4*shuf_c, column (dy*2+dx)*shuf_c+co goes to pixel
+                                 (2y+dy, 2x+dx), channel co               (ConvTranspose2d 2x2) */
+};
+
+typedef struct b200_igemm_desc {
+    int32_t mode;          /* B200_IGEMM_*                                                        */
+    int32_t batch;
+    int32_t in_h, in_w;    /* input spatial size (STEM: the ORIGINAL image H, W)                  */
+    int32_t in_c;          /* input channels, multiple of 64 (STEM: ignored)                      */
+    int32_t out_c;         /* real output channels (GEMM N); weights are padded to n_pad rows     */
+    int32_t n_pad;         /* rows of the weight matrix, multiple of block_n                      */
+    int32_t ksize;         /* 1 or 3 (STEM: 7)                                                    */
+    int32_t stride;        /* 1 or 2                                                              */
+    int32_t flags;         /* B200_EPI_*                                                          */
+    int32_t out_ld;        /* elements between consecutive output pixels                          */
+    int32_t res_ld;        /* elements between consecutive residual pixels                        */
+    int32_t shuf_c;        /* channels per sub-pixel for B200_EPI_SHUFFLE2                        */
+    int32_t block_n;       /* 32, 64, 128 or 256; 0 = choose                                      */
+    int32_t reserved0;
+    int32_t reserved1;
+    const void*  x;        /* input activations, NHWC bf16                                        */
+    const void*  w;        /* weights [n_pad][taps*in_c] bf16, K order (tap, cin)                 */
+    const float* scale;    /* [n_pad] per-column multiplier (folded BN gamma/sqrt(var+eps)), or 1 */
+    const float* shift;    /* [n_pad] per-column addend (folded BN beta-mean*scale, or bias)      */
+    const void*  residual; /* NHWC bf16 or NULL                                                   */
+    void*        y;        /* output                                                              */
+    const float* offsets;  /* DCN: [batch*out_h*out_w][32] fp32 raw offset_mask_conv output:
+                              ch 2k = dy_k, 2k+1 = dx_k, 18+k = mask logit (dcn.py:44-46)         */
+} b200_igemm_desc;
+
+typedef struct b200_igemm b200_igemm; /* opaque: TMA descriptors + launch geometry */
+
+int b200_igemm_create(const b200_igemm_desc* desc, b200_igemm** out);
+int b200_igemm_launch(const b200_igemm* op, void* stream);
+int b200_igemm_destroy(b200_igemm* op);
+/* geometry a created op settled on (for tests / DESIGN tables) */
+int b200_igemm_info(const b200_igemm* op, int32_t* out_h, int32_t* out_w, int32_t* tile_w,
+                    int32_t* tile_h, int32_t* block_n, int32_t* num_tiles, int32_t* smem_bytes);
+
+/* ---- bandwidth-bound kernels ---------------------------------------------------------------- */
+/* fp32 NCHW (b,3,H,W) normalised image -> zero-padded space-to-depth bf16 buffer
+ * [b][H/2+3][W/2+3][16] (channel (dy*2+dx)*3+c of block (row-2, col-2); 12..15 zero) consumed by
+ * B200_IGEMM_STEM with weights [n_pad][4 rows][4 blocks][16] (replaces the layout half of
+ * torchvision conv1 7x7 s2, resnet.py:197 via model/det/backbone.py:34). */
+int b200_stem_pack(const float* img, void* packed, int batch, int h, int w, void* stream);
+/* MaxPool2d(3, stride 2, pad 1) on NHWC bf16 (torchvision resnet.py:200). */
+int b200_maxpool3x3s2(const void* x, void* y, int batch, int h, int w, int c, void* stream);
+/* ScaleFeatureSelection.forward (model/det/neck.py:57-79): bilinear(align_corners=True) upsample of
+ * p3,p4,p5 to p2's size, 1x1 conv 1024->4 (+bias), softmax over the 4 levels, weighted sum.
+ * p2..p5 NHWC bf16 with 256 channels; w_att [4][1024] fp32; b_att [4]; out NHWC bf16. */
+int b200_asf_fwd(const void* p2, const void* p3, const void* p4, const void* p5,
+                 const float* w_att, const float* b_att, void* out,
+                 int batch, int h2, int w2, int h3, int w3, int h4, int w4, int h5, int w5,
+                 void* stream);
+/* DBHead tail (model/det/head.py:15,23,28-48): last ConvTranspose2d(64->1, 2x2 s2) of both branches,
+ * sigmoid, differentiable-binarisation step.  t_bin/t_thr: NHWC bf16 (b, h, w, 64) (already
+ * BN+ReLU'd); w2_* [64][4] fp32 (ci, dy*2+dx); maps: fp32 (b,1,2h,2w) each; any map may be NULL. */
+int b200_db_head_fwd(const void* t_bin, const void* t_thr, const float* w2_bin, float b2_bin,
+                     const float* w2_thr, float b2_thr, float k,
+                     float* binary, float* thresh, float* thresh_binary,
+                     float* bin_logits, float* thresh_logits,
+                     int batch, int h, int w, void* stream);
+
+/* ---- post-processing (replaces DBPostProcessor.__call__, src/det/test.py:55-106) ------------
+ * threshold (test.py:57) -> 8-connected component labelling (replaces cv2.findContours, test.py:60)
+ * -> per-component bounding box, pixel count and fixed-point probability sum (replaces
+ * box_score_fast, test.py:20-34) -> box_thresh / min_area filters (test.py:77,81) -> closed-form
+ * un-clip of the bounding rectangle by d = area * ratio / perimeter (replaces unclip, test.py:37-43).
+ * All arithmetic after the threshold is integer or IEEE double without contraction, so the result
+ * is bit-exact against oracle/postproc_oracle.py. */
+typedef struct b200_box {
+    int32_t x0, y0, x1, y1;     /* un-clipped (expanded) rectangle, pixel-centre corners            */
+    int32_t bx0, by0, bx1, by1; /* tight bounding box of the component, inclusive                   */
+    int32_t label;              /* canonical label: rank (1-based) of the component's first pixel   */
+    int32_t npix;               /* pixels in the component                                          */
+    uint64_t qsum;              /* sum over pixels of (uint)(prob * 2^24 + 0.5): score = qsum/(npix*2^24) */
+} b200_box;
+
+/* bytes of device scratch b200_postproc needs for a batch of (h, w) maps; -1 on a bad shape */
+int64_t b200_postproc_workspace_bytes(int batch, int h, int w, int max_candidates);
+/* prob: fp32 (b, h, w) device.  labels: int32 (b, h, w) device, receives the canonical label map
+ * (0 = background; label L = the component whose first pixel in raster order is the L-th such).
+ * boxes: device array [batch][max_candidates]; counts: device int32 [batch] = boxes written per
+ * image (in label order); ncomp: device int32 [batch] = components found per image.
+ * Only the first max_candidates components (by label) are examined (test.py:66-67). */
+int b200_postproc(const float* prob, int32_t* labels, b200_box* boxes, int32_t* counts,
+                  int32_t* ncomp, void* workspace, int64_t workspace_bytes,
+                  int batch, int h, int w, double thresh, double box_thresh, double unclip_ratio,
+                  int min_area, int max_candidates, void* stream);
+
+/* ---- plain CUDA-core cross-check kernels (slow; used by the GPU tests, never by the engine) -- */
+int b200_ref_conv2d(const void* x, const void* w, const float* scale, const float* shift,
+                    const void* residual, void* y, int batch, int in_h, int in_w, int in_c,
+                    int out_c, int w_ld, int ksize, int stride, int flags, int out_ld, int res_ld,
+                    int shuf_c, void* stream);
+int b200_ref_dcn2d(const void* x, const float* offsets, const void* w, const float* scale,
+                   const float* shift, void* y, int batch, int in_h, int in_w, int in_c,
+                   int out_c, int stride, int flags, int out_ld, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DBNET_B200_H */

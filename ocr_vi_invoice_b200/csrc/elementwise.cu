@@ -1,0 +1,327 @@
+// Bandwidth-bound kernels of the DBNet++ path: stem packing, max-pool, the fused adaptive-scale-fusion
+// (ScaleFeatureSelection) and the DB head tail.  All activations NHWC bf16, 16-byte vector accesses.
+#include "common.cuh"
+#include "internal.h"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------ stem pack
+// fp32 NCHW image -> zero-padded 2x2 space-to-depth bf16 buffer [b][H/2+3][W/2+3][16];
+// channel (dy*2+dx)*3 + c holds img[c][2*br+dy][2*bc+dx] of block (br, bc) = (row-2, col-2); 12..15 = 0.
+// With this layout the 7x7 s2 p3 stem conv (torchvision resnet.py:197) is a 4x4 s1 conv whose A rows are
+// contiguous 128-byte runs (4 blocks x 16 channels).
+__global__ void stem_pack_kernel(const float* __restrict__ img, uint4* __restrict__ out, int batch, int h, int w) {
+    const int ph = h / 2 + 3, pw = w / 2 + 3;
+    const int64_t total = static_cast<int64_t>(batch) * ph * pw;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int px = static_cast<int>(i % pw);
+        int64_t r = i / pw;
+        const int py = static_cast<int>(r % ph);
+        const int n = static_cast<int>(r / ph);
+        const int br = py - 2, bc = px - 2;
+        float v[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) v[j] = 0.0f;
+        if (br >= 0 && br < h / 2 && bc >= 0 && bc < w / 2) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float* src = img + ((static_cast<int64_t>(n) * 3 + c) * h + 2 * br) * w + 2 * bc;
+                const float2 r0 = __ldg(reinterpret_cast<const float2*>(src));
+                const float2 r1 = __ldg(reinterpret_cast<const float2*>(src + w));
+                v[0 * 3 + c] = r0.x;
+                v[1 * 3 + c] = r0.y;
+                v[2 * 3 + c] = r1.x;
+                v[3 * 3 + c] = r1.y;
+            }
+        }
+        uint4 lo, hi;
+        lo.x = pack_bf16(v[0], v[1]);
+        lo.y = pack_bf16(v[2], v[3]);
+        lo.z = pack_bf16(v[4], v[5]);
+        lo.w = pack_bf16(v[6], v[7]);
+        hi.x = pack_bf16(v[8], v[9]);
+        hi.y = pack_bf16(v[10], v[11]);
+        hi.z = 0u;
+        hi.w = 0u;
+        out[2 * i] = lo;
+        out[2 * i + 1] = hi;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ max-pool
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+    __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&a);
+    __nv_bfloat162 y = *reinterpret_cast<__nv_bfloat162*>(&b);
+    __nv_bfloat162 m = __hmax2(x, y);
+    return *reinterpret_cast<uint32_t*>(&m);
+}
+
+// MaxPool2d(kernel 3, stride 2, padding 1), NHWC bf16; one thread per (output pixel, 8 channels).
+__global__ void maxpool_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int batch, int h,
+                               int w, int c) {
+    const int oh = h / 2, ow = w / 2, c8 = c / 8;
+    const int64_t total = static_cast<int64_t>(batch) * oh * ow * c8;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int cc = static_cast<int>(i % c8);
+        int64_t r = i / c8;
+        const int ox = static_cast<int>(r % ow);
+        r /= ow;
+        const int oy = static_cast<int>(r % oh);
+        const int n = static_cast<int>(r / oh);
+        const uint32_t ninf = 0xFF80FF80u;  // (-inf, -inf) bf16
+        uint4 m = make_uint4(ninf, ninf, ninf, ninf);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = 2 * oy - 1 + ky;
+            if (iy < 0 || iy >= h) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = 2 * ox - 1 + kx;
+                if (ix < 0 || ix >= w) continue;
+                const uint4 v = ldg128(x + ((static_cast<int64_t>(n) * h + iy) * w + ix) * c + cc * 8);
+                m.x = bf16x2_max(m.x, v.x);
+                m.y = bf16x2_max(m.y, v.y);
+                m.z = bf16x2_max(m.z, v.z);
+                m.w = bf16x2_max(m.w, v.w);
+            }
+        }
+        *reinterpret_cast<uint4*>(y + ((static_cast<int64_t>(n) * oh + oy) * ow + ox) * c + cc * 8) = m;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ ASF
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    f[0] = bf16lo(u.x); f[1] = bf16hi(u.x);
+    f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
+    f[4] = bf16lo(u.z); f[5] = bf16hi(u.z);
+    f[6] = bf16lo(u.w); f[7] = bf16hi(u.w);
+}
+
+// bilinear, align_corners=True (ATen upsample_bilinear2d: src = dst * (in-1)/(out-1), computed in fp32)
+__device__ __forceinline__ void bilinear_ac(const __nv_bfloat16* __restrict__ src, int n, int hin, int win, float sy,
+                                            float sx, int y, int x, int lane, float (&f)[8]) {
+    const float fy = sy * static_cast<float>(y), fx = sx * static_cast<float>(x);
+    const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+    const int y1 = y0 + ((y0 < hin - 1) ? 1 : 0), x1 = x0 + ((x0 < win - 1) ? 1 : 0);
+    const float ly = fy - static_cast<float>(y0), lx = fx - static_cast<float>(x0);
+    const float hy = 1.0f - ly, hx = 1.0f - lx;
+    const __nv_bfloat16* base = src + static_cast<int64_t>(n) * hin * win * 256 + lane * 8;
+    float a[8], b[8], c[8], d[8];
+    unpack8(ldg128(base + (static_cast<int64_t>(y0) * win + x0) * 256), a);
+    unpack8(ldg128(base + (static_cast<int64_t>(y0) * win + x1) * 256), b);
+    unpack8(ldg128(base + (static_cast<int64_t>(y1) * win + x0) * 256), c);
+    unpack8(ldg128(base + (static_cast<int64_t>(y1) * win + x1) * 256), d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = hy * (hx * a[j] + lx * b[j]) + ly * (hx * c[j] + lx * d[j]);
+}
+
+// ScaleFeatureSelection.forward (model/det/neck.py:57-79), one warp per output pixel, lane = 8 channels of
+// each of the 4 levels.  The 1024-channel concat is never materialised.
+__global__ void __launch_bounds__(256) asf_kernel(const __nv_bfloat16* __restrict__ p2, const __nv_bfloat16* __restrict__ p3,
+                                                  const __nv_bfloat16* __restrict__ p4, const __nv_bfloat16* __restrict__ p5,
+                                                  const float* __restrict__ w_att, const float* __restrict__ b_att,
+                                                  __nv_bfloat16* __restrict__ out, int batch, int h2, int w2, int h3, int w3,
+                                                  int h4, int w4, int h5, int w5) {
+    __shared__ float sw[4 * 4 * 8 * 32];  // [logit i][level l][j][lane]  (conflict-free per-lane reads)
+    for (int t = threadIdx.x; t < 4096; t += blockDim.x) {
+        const int i = t >> 10, k = t & 1023;  // w_att[i][k], k = l*256 + lane*8 + j
+        const int l = k >> 8, ln = (k >> 3) & 31, j = k & 7;
+        sw[((i * 4 + l) * 8 + j) * 32 + ln] = w_att[t];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const float sy3 = (h2 > 1) ? static_cast<float>(h3 - 1) / static_cast<float>(h2 - 1) : 0.0f;
+    const float sx3 = (w2 > 1) ? static_cast<float>(w3 - 1) / static_cast<float>(w2 - 1) : 0.0f;
+    const float sy4 = (h2 > 1) ? static_cast<float>(h4 - 1) / static_cast<float>(h2 - 1) : 0.0f;
+    const float sx4 = (w2 > 1) ? static_cast<float>(w4 - 1) / static_cast<float>(w2 - 1) : 0.0f;
+    const float sy5 = (h2 > 1) ? static_cast<float>(h5 - 1) / static_cast<float>(h2 - 1) : 0.0f;
+    const float sx5 = (w2 > 1) ? static_cast<float>(w5 - 1) / static_cast<float>(w2 - 1) : 0.0f;
+    const float b0 = b_att[0], b1 = b_att[1], b2 = b_att[2], b3 = b_att[3];
+    const int64_t total = static_cast<int64_t>(batch) * h2 * w2;
+    for (int64_t pix = static_cast<int64_t>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); pix < total;
+         pix += static_cast<int64_t>(gridDim.x) * warps_per_block) {
+        const int x = static_cast<int>(pix % w2);
+        int64_t r = pix / w2;
+        const int y = static_cast<int>(r % h2);
+        const int n = static_cast<int>(r / h2);
+        float f[4][8];
+        unpack8(ldg128(p2 + pix * 256 + lane * 8), f[0]);
+        bilinear_ac(p3, n, h3, w3, sy3, sx3, y, x, lane, f[1]);
+        bilinear_ac(p4, n, h4, w4, sy4, sx4, y, x, lane, f[2]);
+        bilinear_ac(p5, n, h5, w5, sy5, sx5, y, x, lane, f[3]);
+        float a[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int l = 0; l < 4; ++l)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[i] = fmaf(sw[((i * 4 + l) * 8 + j) * 32 + lane], f[l][j], a[i]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
+        }
+        a[0] += b0; a[1] += b1; a[2] += b2; a[3] += b3;
+        const float mx = fmaxf(fmaxf(a[0], a[1]), fmaxf(a[2], a[3]));
+        const float e0 = expf(a[0] - mx), e1 = expf(a[1] - mx), e2 = expf(a[2] - mx), e3 = expf(a[3] - mx);
+        const float inv = 1.0f / (e0 + e1 + e2 + e3);
+        const float s0 = e0 * inv, s1 = e1 * inv, s2 = e2 * inv, s3 = e3 * inv;
+        float o8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o8[j] = f[0][j] * s0 + f[1][j] * s1 + f[2][j] * s2 + f[3][j] * s3;
+        uint4 u;
+        u.x = pack_bf16(o8[0], o8[1]);
+        u.y = pack_bf16(o8[2], o8[3]);
+        u.z = pack_bf16(o8[4], o8[5]);
+        u.w = pack_bf16(o8[6], o8[7]);
+        *reinterpret_cast<uint4*>(out + pix * 256 + lane * 8) = u;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ DB head tail
+struct HeadParams {
+    const __nv_bfloat16* t_bin;
+    const __nv_bfloat16* t_thr;
+    const float* w2_bin;
+    const float* w2_thr;
+    float b2_bin, b2_thr, k;
+    float* binary;
+    float* thresh;
+    float* thresh_binary;
+    float* bin_logits;
+    float* thresh_logits;
+    int batch, h, w;
+};
+
+constexpr int kHeadPix = 128;       // pixels (threads) per block
+constexpr int kHeadRowBytes = 144;  // 128 B of channels + 16 B pad: conflict-free 16-byte row reads
+
+// Last ConvTranspose2d(64 -> 1, k2 s2) of both branches + sigmoid + DB step (model/det/head.py:15,23,28-48).
+// Stage 128 pixels x 64 channels of each branch into shared memory with coalesced 16-byte loads, then
+// one thread per input pixel produces its 2x2 output patch of all five maps (8-byte coalesced stores).
+__global__ void __launch_bounds__(kHeadPix) db_head_kernel(const HeadParams p) {
+    __shared__ __align__(16) uint8_t sb[2][kHeadPix * kHeadRowBytes];
+    __shared__ float sw[2][256];
+    for (int t = threadIdx.x; t < 256; t += kHeadPix) {
+        sw[0][t] = p.w2_bin[t];
+        sw[1][t] = p.w2_thr[t];
+    }
+    const int64_t total = static_cast<int64_t>(p.batch) * p.h * p.w;
+    const int64_t pix0 = static_cast<int64_t>(blockIdx.x) * kHeadPix;
+    const int npx = static_cast<int>(min(static_cast<int64_t>(kHeadPix), total - pix0));
+    // 128 pixels * 8 chunks of 16 B per branch
+    for (int t = threadIdx.x; t < kHeadPix * 8; t += kHeadPix) {
+        const int px = t >> 3, ch = t & 7;
+        if (px < npx) {
+            *reinterpret_cast<uint4*>(&sb[0][px * kHeadRowBytes + ch * 16]) = ldg128(p.t_bin + (pix0 + px) * 64 + ch * 8);
+            *reinterpret_cast<uint4*>(&sb[1][px * kHeadRowBytes + ch * 16]) = ldg128(p.t_thr + (pix0 + px) * 64 + ch * 8);
+        }
+    }
+    __syncthreads();
+    const int px = threadIdx.x;
+    if (px >= npx) return;
+    float acc[2][4];
+#pragma unroll
+    for (int br = 0; br < 2; ++br) {
+        acc[br][0] = acc[br][1] = acc[br][2] = acc[br][3] = 0.0f;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+            float f[8];
+            unpack8(*reinterpret_cast<const uint4*>(&sb[br][px * kHeadRowBytes + ch * 16]), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 wv = *reinterpret_cast<const float4*>(&sw[br][(ch * 8 + j) * 4]);
+                acc[br][0] = fmaf(f[j], wv.x, acc[br][0]);
+                acc[br][1] = fmaf(f[j], wv.y, acc[br][1]);
+                acc[br][2] = fmaf(f[j], wv.z, acc[br][2]);
+                acc[br][3] = fmaf(f[j], wv.w, acc[br][3]);
+            }
+        }
+    }
+    const int64_t pix = pix0 + px;
+    const int x = static_cast<int>(pix % p.w);
+    int64_t r = pix / p.w;
+    const int y = static_cast<int>(r % p.h);
+    const int n = static_cast<int>(r / p.h);
+    const int ow = 2 * p.w;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+        const float bl0 = acc[0][dy * 2 + 0] + p.b2_bin, bl1 = acc[0][dy * 2 + 1] + p.b2_bin;
+        const float tl0 = acc[1][dy * 2 + 0] + p.b2_thr, tl1 = acc[1][dy * 2 + 1] + p.b2_thr;
+        const float bp0 = 1.0f / (1.0f + expf(-bl0)), bp1 = 1.0f / (1.0f + expf(-bl1));
+        const float tp0 = 1.0f / (1.0f + expf(-tl0)), tp1 = 1.0f / (1.0f + expf(-tl1));
+        const float tb0 = 1.0f / (1.0f + expf(-p.k * (bp0 - tp0))), tb1 = 1.0f / (1.0f + expf(-p.k * (bp1 - tp1)));
+        const int64_t o = (static_cast<int64_t>(n) * (2 * p.h) + (2 * y + dy)) * ow + 2 * x;
+        if (p.binary) *reinterpret_cast<float2*>(p.binary + o) = make_float2(bp0, bp1);
+        if (p.thresh) *reinterpret_cast<float2*>(p.thresh + o) = make_float2(tp0, tp1);
+        if (p.thresh_binary) *reinterpret_cast<float2*>(p.thresh_binary + o) = make_float2(tb0, tb1);
+        if (p.bin_logits) *reinterpret_cast<float2*>(p.bin_logits + o) = make_float2(bl0, bl1);
+        if (p.thresh_logits) *reinterpret_cast<float2*>(p.thresh_logits + o) = make_float2(tl0, tl1);
+    }
+}
+
+static int grid_for(int64_t work_items, int threads) {
+    int64_t blocks = (work_items + threads - 1) / threads;
+    const int64_t cap = 148 * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return static_cast<int>(blocks);
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_stem_pack(const float* img, void* packed, int batch, int h, int w, void* stream) {
+    if (!img || !packed) return set_error("b200_stem_pack: null pointer");
+    if (batch <= 0 || h <= 0 || w <= 0 || (h & 1) || (w & 1)) return set_error("b200_stem_pack: H and W must be even");
+    const int64_t total = static_cast<int64_t>(batch) * (h / 2 + 3) * (w / 2 + 3);
+    stem_pack_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        img, reinterpret_cast<uint4*>(packed), batch, h, w);
+    return check_cuda(cudaGetLastError(), "b200_stem_pack launch");
+}
+
+extern "C" int b200_maxpool3x3s2(const void* x, void* y, int batch, int h, int w, int c, void* stream) {
+    if (!x || !y) return set_error("b200_maxpool3x3s2: null pointer");
+    if (batch <= 0 || (h & 1) || (w & 1) || (c % 8)) return set_error("b200_maxpool3x3s2: need even H, W and C %% 8 == 0");
+    const int64_t total = static_cast<int64_t>(batch) * (h / 2) * (w / 2) * (c / 8);
+    maxpool_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), batch, h, w, c);
+    return check_cuda(cudaGetLastError(), "b200_maxpool3x3s2 launch");
+}
+
+extern "C" int b200_asf_fwd(const void* p2, const void* p3, const void* p4, const void* p5, const float* w_att,
+                            const float* b_att, void* out, int batch, int h2, int w2, int h3, int w3, int h4, int w4,
+                            int h5, int w5, void* stream) {
+    if (!p2 || !p3 || !p4 || !p5 || !w_att || !b_att || !out) return set_error("b200_asf_fwd: null pointer");
+    if (batch <= 0 || h2 <= 0 || w2 <= 0) return set_error("b200_asf_fwd: bad shape");
+    const int64_t total = static_cast<int64_t>(batch) * h2 * w2;
+    asf_kernel<<<grid_for(total, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(p2), reinterpret_cast<const __nv_bfloat16*>(p3),
+        reinterpret_cast<const __nv_bfloat16*>(p4), reinterpret_cast<const __nv_bfloat16*>(p5), w_att, b_att,
+        reinterpret_cast<__nv_bfloat16*>(out), batch, h2, w2, h3, w3, h4, w4, h5, w5);
+    return check_cuda(cudaGetLastError(), "b200_asf_fwd launch");
+}
+
+extern "C" int b200_db_head_fwd(const void* t_bin, const void* t_thr, const float* w2_bin, float b2_bin,
+                                const float* w2_thr, float b2_thr, float k, float* binary, float* thresh,
+                                float* thresh_binary, float* bin_logits, float* thresh_logits, int batch, int h, int w,
+                                void* stream) {
+    if (!t_bin || !t_thr || !w2_bin || !w2_thr) return set_error("b200_db_head_fwd: null pointer");
+    if (batch <= 0 || h <= 0 || w <= 0) return set_error("b200_db_head_fwd: bad shape");
+    HeadParams p;
+    p.t_bin = reinterpret_cast<const __nv_bfloat16*>(t_bin);
+    p.t_thr = reinterpret_cast<const __nv_bfloat16*>(t_thr);
+    p.w2_bin = w2_bin; p.w2_thr = w2_thr; p.b2_bin = b2_bin; p.b2_thr = b2_thr; p.k = k;
+    p.binary = binary; p.thresh = thresh; p.thresh_binary = thresh_binary;
+    p.bin_logits = bin_logits; p.thresh_logits = thresh_logits;
+    p.batch = batch; p.h = h; p.w = w;
+    const int64_t total = static_cast<int64_t>(batch) * h * w;
+    const int64_t blocks = (total + kHeadPix - 1) / kHeadPix;
+    if (blocks > 0x7fffffff) return set_error("b200_db_head_fwd: too many pixels");
+    db_head_kernel<<<static_cast<int>(blocks), kHeadPix, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    return check_cuda(cudaGetLastError(), "b200_db_head_fwd launch");
+}

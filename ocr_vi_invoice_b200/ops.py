@@ -1,0 +1,189 @@
+"""Thin host wrappers over the C-ABI operators plus the weight re-layout they expect.
+
+Every function here either re-arranges parameters (pure torch tensor ops, run once at plan time) or
+launches a kernel of libdbnet_b200.so on the current CUDA stream.  Activations are NHWC bf16.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import (EPI_OUT_F32, EPI_RELU, EPI_RES, EPI_RES_UP2, EPI_SHUFFLE2, IGEMM_CONV, IGEMM_DCN,
+                   IGEMM_STEM)
+
+__all__ = [
+    "Igemm", "pack_conv_weight", "pack_stem_weight", "pack_convT_weight", "fold_bn", "pad_vec",
+    "stem_pack", "maxpool3x3s2", "asf_fwd", "db_head_fwd", "postproc", "ref_conv2d", "ref_dcn2d",
+    "EPI_RELU", "EPI_RES", "EPI_RES_UP2", "EPI_OUT_F32", "EPI_SHUFFLE2", "IGEMM_CONV", "IGEMM_STEM", "IGEMM_DCN",
+]
+
+
+# ----------------------------------------------------------------------------- parameter re-layout
+def _round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+def choose_n_pad(out_c: int) -> int:
+    """GEMM N padded to a block_n the kernel supports (32/64/128 or a multiple of 256)."""
+    for b in (32, 64, 128, 256):
+        if out_c <= b:
+            return b
+    return _round_up(out_c, 256)
+
+
+def pack_conv_weight(w: torch.Tensor, n_pad: Optional[int] = None) -> torch.Tensor:
+    """(O, I, kh, kw) fp32 -> [n_pad][kh*kw*I] bf16 with K ordered (tap, cin).
+
+    torchvision's deform_conv2d and nn.Conv2d flatten K as (cin, tap) (`weight.flatten(1)`); the NHWC
+    kernels walk K tap-major so a 64-channel slice of one tap is one contiguous 128-byte row.
+    """
+    o, i, kh, kw = w.shape
+    n_pad = n_pad or choose_n_pad(o)
+    out = torch.zeros(n_pad, kh * kw * i, dtype=torch.bfloat16, device=w.device)
+    out[:o] = w.permute(0, 2, 3, 1).reshape(o, kh * kw * i).to(torch.bfloat16)
+    return out.contiguous()
+
+
+def pack_stem_weight(w: torch.Tensor, n_pad: int = 64) -> torch.Tensor:
+    """(O, 3, 7, 7) -> [n_pad][4 block rows][4 blocks][16] bf16 for the space-to-depth stem.
+
+    Window position (wy, wx) of the 8x8 input window (block row ty = wy//2, dy = wy%2, ...) carries kernel
+    tap (ky, kx) = (wy-1, wx-1); the first window row/column has no tap and stays zero.
+    """
+    o, i, kh, kw = w.shape
+    assert (i, kh, kw) == (3, 7, 7), "stem is 7x7 on 3 channels"
+    full = torch.zeros(o, 3, 8, 8, dtype=torch.float32, device=w.device)
+    full[:, :, 1:, 1:] = w.float()
+    # (o, c, ty, dy, j, dx) -> (o, ty, j, dy, dx, c)
+    t = full.reshape(o, 3, 4, 2, 4, 2).permute(0, 2, 4, 3, 5, 1).reshape(o, 4, 4, 12)
+    out = torch.zeros(n_pad, 4, 4, 16, dtype=torch.bfloat16, device=w.device)
+    out[:o, :, :, :12] = t.to(torch.bfloat16)
+    return out.reshape(n_pad, 256).contiguous()
+
+
+def pack_convT_weight(w: torch.Tensor, n_pad: Optional[int] = None) -> torch.Tensor:
+    """ConvTranspose2d(k=2, s=2) weight (I, O, 2, 2) -> [4*O][I] bf16, row (dy*2+dx)*O + co."""
+    i, o, kh, kw = w.shape
+    assert (kh, kw) == (2, 2)
+    n = 4 * o
+    n_pad = n_pad or choose_n_pad(n)
+    out = torch.zeros(n_pad, i, dtype=torch.bfloat16, device=w.device)
+    out[:n] = w.permute(2, 3, 1, 0).reshape(n, i).to(torch.bfloat16)
+    return out.contiguous()
+
+
+def fold_bn(bn_weight, bn_bias, mean, var, eps: float = 1e-5, conv_bias=None):
+    """Eval-mode BatchNorm2d (+ optional preceding conv bias) -> per-channel (scale, shift) fp32."""
+    scale = bn_weight.float() / torch.sqrt(var.float() + eps)
+    shift = bn_bias.float() - mean.float() * scale
+    if conv_bias is not None:
+        shift = shift + conv_bias.float() * scale
+    return scale, shift
+
+
+def pad_vec(v: torch.Tensor, n_pad: int, fill: float = 0.0) -> torch.Tensor:
+    out = torch.full((n_pad,), fill, dtype=torch.float32, device=v.device)
+    out[: v.numel()] = v.float()
+    return out
+
+
+# ----------------------------------------------------------------------------- operators
+class Igemm:
+    """One planned implicit-GEMM launch (TMA descriptors baked at creation).  Keeps its tensors alive."""
+
+    def __init__(self, mode: int, x: torch.Tensor, w: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor,
+                 y: torch.Tensor, *, batch: int, in_h: int, in_w: int, in_c: int, out_c: int, ksize: int,
+                 stride: int, flags: int = 0, residual: Optional[torch.Tensor] = None,
+                 offsets: Optional[torch.Tensor] = None, out_ld: Optional[int] = None, res_ld: int = 0,
+                 shuf_c: int = 0, block_n: int = 0, name: str = ""):
+        lib = _lib.load()
+        self.name = name
+        self._keep = (x, w, scale, shift, y, residual, offsets)
+        n_pad = w.shape[0]
+        assert scale.numel() == n_pad and shift.numel() == n_pad, "scale/shift must be padded to n_pad"
+        assert w.dtype == torch.bfloat16 and w.is_contiguous()
+        if out_ld is None:
+            out_ld = shuf_c if (flags & EPI_SHUFFLE2) else out_c
+        d = _lib.IgemmDesc(
+            mode=mode, batch=batch, in_h=in_h, in_w=in_w, in_c=in_c, out_c=out_c, n_pad=n_pad, ksize=ksize,
+            stride=stride, flags=flags, out_ld=out_ld, res_ld=res_ld, shuf_c=shuf_c, block_n=block_n,
+            x=_lib.ptr(x), w=_lib.ptr(w), scale=_lib.ptr(scale), shift=_lib.ptr(shift),
+            residual=_lib.ptr(residual), y=_lib.ptr(y), offsets=_lib.ptr(offsets))
+        h = C.c_void_p()
+        _lib.check(lib.b200_igemm_create(C.byref(d), C.byref(h)), f"igemm_create({name})")
+        self._h = h
+        self._lib = lib
+        self.flops = 2.0 * batch * (in_h // stride) * (in_w // stride) * out_c * w.shape[1]
+
+    def info(self) -> dict:
+        vals = [C.c_int32() for _ in range(7)]
+        _lib.check(self._lib.b200_igemm_info(self._h, *[C.byref(v) for v in vals]))
+        keys = ("out_h", "out_w", "tile_w", "tile_h", "block_n", "num_tiles", "smem_bytes")
+        return {k: v.value for k, v in zip(keys, vals)}
+
+    def __call__(self, stream: Optional[int] = None) -> None:
+        st = _lib.current_stream() if stream is None else stream
+        _lib.check(self._lib.b200_igemm_launch(self._h, st), f"igemm_launch({self.name})")
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._lib.b200_igemm_destroy(h)
+            self._h = None
+
+
+def stem_pack(img: torch.Tensor, packed: torch.Tensor) -> None:
+    b, c, h, w = img.shape
+    assert c == 3 and img.dtype == torch.float32 and img.is_contiguous()
+    _lib.check(_lib.load().b200_stem_pack(_lib.ptr(img), _lib.ptr(packed), b, h, w, _lib.current_stream()), "stem_pack")
+
+
+def maxpool3x3s2(x: torch.Tensor, y: torch.Tensor, batch: int, h: int, w: int, c: int) -> None:
+    _lib.check(_lib.load().b200_maxpool3x3s2(_lib.ptr(x), _lib.ptr(y), batch, h, w, c, _lib.current_stream()), "maxpool")
+
+
+def asf_fwd(p2, p3, p4, p5, w_att, b_att, out, batch, sizes) -> None:
+    (h2, w2), (h3, w3), (h4, w4), (h5, w5) = sizes
+    _lib.check(_lib.load().b200_asf_fwd(_lib.ptr(p2), _lib.ptr(p3), _lib.ptr(p4), _lib.ptr(p5), _lib.ptr(w_att),
+                                        _lib.ptr(b_att), _lib.ptr(out), batch, h2, w2, h3, w3, h4, w4, h5, w5,
+                                        _lib.current_stream()), "asf_fwd")
+
+
+def db_head_fwd(t_bin, t_thr, w2_bin, b2_bin: float, w2_thr, b2_thr: float, k: float, maps: dict, batch: int,
+                h: int, w: int) -> None:
+    g = lambda n: _lib.ptr(maps.get(n))
+    _lib.check(_lib.load().b200_db_head_fwd(_lib.ptr(t_bin), _lib.ptr(t_thr), _lib.ptr(w2_bin), b2_bin,
+                                            _lib.ptr(w2_thr), b2_thr, k, g("binary"), g("thresh"), g("thresh_binary"),
+                                            g("bin_logits"), g("thresh_logits"), batch, h, w, _lib.current_stream()),
+               "db_head_fwd")
+
+
+def postproc_workspace_bytes(batch: int, h: int, w: int, max_candidates: int) -> int:
+    n = _lib.load().b200_postproc_workspace_bytes(batch, h, w, max_candidates)
+    if n < 0:
+        raise _lib.B200Error("postproc_workspace_bytes: bad shape")
+    return n
+
+
+def postproc(prob, labels, boxes, counts, ncomp, workspace, batch, h, w, thresh, box_thresh, unclip_ratio, min_area,
+             max_candidates) -> None:
+    _lib.check(_lib.load().b200_postproc(_lib.ptr(prob), _lib.ptr(labels), _lib.ptr(boxes), _lib.ptr(counts),
+                                         _lib.ptr(ncomp), _lib.ptr(workspace), workspace.numel() * workspace.element_size(),
+                                         batch, h, w, float(thresh), float(box_thresh), float(unclip_ratio),
+                                         int(min_area), int(max_candidates), _lib.current_stream()), "postproc")
+
+
+def ref_conv2d(x, w, scale, shift, residual, y, batch, in_h, in_w, in_c, out_c, ksize, stride, flags, out_ld,
+               res_ld=0, shuf_c=0) -> None:
+    _lib.check(_lib.load().b200_ref_conv2d(_lib.ptr(x), _lib.ptr(w), _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(residual),
+                                           _lib.ptr(y), batch, in_h, in_w, in_c, out_c, w.shape[1], ksize, stride, flags,
+                                           out_ld, res_ld, shuf_c, _lib.current_stream()), "ref_conv2d")
+
+
+def ref_dcn2d(x, offsets, w, scale, shift, y, batch, in_h, in_w, in_c, out_c, stride, flags, out_ld) -> None:
+    _lib.check(_lib.load().b200_ref_dcn2d(_lib.ptr(x), _lib.ptr(offsets), _lib.ptr(w), _lib.ptr(scale), _lib.ptr(shift),
+                                          _lib.ptr(y), batch, in_h, in_w, in_c, out_c, stride, flags, out_ld,
+                                          _lib.current_stream()), "ref_dcn2d")

@@ -1,0 +1,221 @@
+"""GPU parity of the tcgen05 implicit-GEMM family (conv / stem / convT / DCN) through the C-ABI.
+
+Each case is checked against (a) torch fp32 ops (TF32 off) on the same bf16-rounded operands and, for the
+conv/DCN cases, (b) the library's own CUDA-core cross-check kernels.  Tolerances: outputs are bf16
+(rel 2^-8) or fp32 with fp32 accumulation in a different order.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def nhwc(x):  # NCHW fp32 -> NHWC bf16
+    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def nchw(y):  # NHWC any -> NCHW fp32
+    return y.float().permute(0, 3, 1, 2).contiguous()
+
+
+def close(ours, ref, rel_rms=2e-2, rtol=1.6e-2):
+    rms = ref.float().pow(2).mean().sqrt().item() + 1e-12
+    err = (ours.float() - ref.float()).abs()
+    bound = rel_rms * rms + rtol * ref.float().abs()
+    bad = (err > bound)
+    assert not bad.any(), (
+        f"mismatch: {bad.sum().item()}/{bad.numel()} elements, max err {err.max().item():.4g}, rms {rms:.4g}, "
+        f"first bad index {bad.nonzero()[0].tolist()}")
+
+
+CONV_CASES = [
+    # (batch, H, W, Cin, Cout, k, stride, flags-tag)
+    (2, 32, 32, 64, 64, 1, 1, ""),
+    (1, 16, 128, 64, 256, 1, 1, "relu"),
+    (2, 20, 20, 256, 64, 1, 1, "relu"),
+    (1, 24, 40, 128, 128, 3, 1, "relu"),
+    (2, 16, 16, 256, 256, 3, 1, ""),
+    (1, 8, 8, 512, 512, 1, 1, "res+relu"),
+    (1, 30, 22, 64, 64, 3, 1, "res+relu"),
+    (1, 32, 32, 256, 512, 1, 2, ""),
+    (2, 20, 36, 128, 128, 3, 2, "relu"),
+    (1, 64, 64, 128, 27, 3, 1, "f32"),
+    (2, 40, 24, 256, 27, 3, 2, "f32"),
+    (1, 16, 16, 2048, 256, 1, 1, "bias"),
+    (1, 16, 16, 512, 256, 1, 1, "up2"),
+    (1, 64, 256, 64, 64, 3, 1, "relu"),
+    (3, 12, 12, 1024, 2048, 1, 1, ""),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "b%d_%dx%d_c%d_o%d_k%d_s%d_%s" % c)
+def test_conv_igemm(case):
+    from ocr_vi_invoice_b200 import ops
+    _setup()
+    b, h, w, ci, co, k, s, tag = case
+    g = torch.Generator(device="cuda").manual_seed(sum(int(v * 7) for v in case if not isinstance(v, str)) & 0xffff)
+    dev = "cuda"
+    x = torch.randn(b, ci, h, w, device=dev, generator=g)
+    wt = torch.randn(co, ci, k, k, device=dev, generator=g) / (ci * k * k) ** 0.5
+    scale = torch.rand(co, device=dev, generator=g) + 0.5
+    shift = torch.randn(co, device=dev, generator=g) * 0.1
+    xb, wb = x.to(torch.bfloat16).float(), wt.to(torch.bfloat16).float()
+    oh, ow = h // s, w // s
+    flags = 0
+    res = None
+    ref = F.conv2d(xb, wb, stride=s, padding=(k - 1) // 2) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    res_ld = 0
+    if "res" in tag:
+        r = torch.randn(b, co, oh, ow, device=dev, generator=g)
+        res = nhwc(r)
+        ref = ref + res.float().permute(0, 3, 1, 2)
+        flags |= ops.EPI_RES
+        res_ld = co
+    if "up2" in tag:
+        r = torch.randn(b, co, oh // 2, ow // 2, device=dev, generator=g)
+        res = nhwc(r)
+        ref = ref + F.interpolate(res.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+        flags |= ops.EPI_RES_UP2
+        res_ld = co
+    if "relu" in tag:
+        ref = ref.relu()
+        flags |= ops.EPI_RELU
+    out_c = co
+    n_pad = ops.choose_n_pad(co)
+    if "f32" in tag:
+        flags |= ops.EPI_OUT_F32
+        out_c = 32
+        y = torch.full((b, oh, ow, 32), float("nan"), device=dev, dtype=torch.float32)
+    else:
+        y = torch.full((b, oh, ow, co), float("nan"), device=dev, dtype=torch.bfloat16)
+    wp = ops.pack_conv_weight(wt, n_pad)
+    sc, sh = ops.pad_vec(scale, n_pad, 1.0), ops.pad_vec(shift, n_pad)
+    op = ops.Igemm(ops.IGEMM_CONV, nhwc(x), wp, sc, sh, y, batch=b, in_h=h, in_w=w, in_c=ci, out_c=out_c, ksize=k,
+                   stride=s, flags=flags, residual=res, res_ld=res_ld, name=str(case))
+    op()
+    torch.cuda.synchronize()
+    got = nchw(y)[:, :co]
+    if "f32" in tag:
+        close(got, ref, rel_rms=1e-3, rtol=1e-3)
+        assert (nchw(y)[:, co:] == 0).all()
+    else:
+        close(got, ref)
+    # cross-check kernel, same flags
+    y2 = torch.zeros_like(y)
+    ops.ref_conv2d(nhwc(x), wp, sc, sh, res, y2, b, h, w, ci, out_c, k, s, flags, y.shape[-1], res_ld)
+    torch.cuda.synchronize()
+    close(nchw(y2)[:, :co], ref, rel_rms=(1e-3 if "f32" in tag else 2e-2))
+
+
+@pytest.mark.parametrize("shape", [(1, 64, 64), (2, 96, 160), (1, 256, 224)])
+def test_stem_igemm(shape):
+    from ocr_vi_invoice_b200 import ops
+    _setup()
+    b, h, w = shape
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(7)
+    img = torch.randn(b, 3, h, w, device=dev, generator=g)
+    wt = torch.randn(64, 3, 7, 7, device=dev, generator=g) / 147 ** 0.5
+    scale = torch.rand(64, device=dev, generator=g) + 0.5
+    shift = torch.randn(64, device=dev, generator=g) * 0.1
+    packed = torch.empty(b, h // 2 + 3, w // 2 + 3, 16, device=dev, dtype=torch.bfloat16)
+    ops.stem_pack(img, packed)
+    y = torch.full((b, h // 2, w // 2, 64), float("nan"), device=dev, dtype=torch.bfloat16)
+    op = ops.Igemm(ops.IGEMM_STEM, packed, ops.pack_stem_weight(wt, 64), scale, shift, y, batch=b, in_h=h, in_w=w,
+                   in_c=3, out_c=64, ksize=7, stride=2, flags=ops.EPI_RELU, name="stem")
+    op()
+    torch.cuda.synchronize()
+    ref = F.conv2d(img.to(torch.bfloat16).float(), wt.to(torch.bfloat16).float(), stride=2, padding=3)
+    ref = (ref * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)).relu()
+    close(nchw(y), ref)
+    # max-pool on top
+    yp = torch.empty(b, h // 4, w // 4, 64, device=dev, dtype=torch.bfloat16)
+    ops.maxpool3x3s2(y, yp, b, h // 2, w // 2, 64)
+    torch.cuda.synchronize()
+    refp = F.max_pool2d(nchw(y), 3, 2, 1)
+    assert torch.equal(nchw(yp), refp)
+
+
+@pytest.mark.parametrize("shape", [(1, 16, 16), (2, 24, 40)])
+def test_convT_igemm(shape):
+    from ocr_vi_invoice_b200 import ops
+    _setup()
+    b, h, w = shape
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(11)
+    x = torch.randn(b, 64, h, w, device=dev, generator=g)
+    wt = torch.randn(64, 64, 2, 2, device=dev, generator=g) / 8
+    bias = torch.randn(64, device=dev, generator=g) * 0.1
+    scale = torch.rand(64, device=dev, generator=g) + 0.5
+    shift = torch.randn(64, device=dev, generator=g) * 0.1
+    ref = F.conv_transpose2d(x.to(torch.bfloat16).float(), wt.to(torch.bfloat16).float(), bias, stride=2)
+    ref = (ref * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)).relu()
+    sc4 = scale.repeat(4)
+    sh4 = (shift + bias * scale).repeat(4)
+    y = torch.full((b, 2 * h, 2 * w, 64), float("nan"), device=dev, dtype=torch.bfloat16)
+    op = ops.Igemm(ops.IGEMM_CONV, nhwc(x), ops.pack_convT_weight(wt, 256), sc4, sh4, y, batch=b, in_h=h, in_w=w,
+                   in_c=64, out_c=256, ksize=1, stride=1, flags=ops.EPI_RELU | ops.EPI_SHUFFLE2, shuf_c=64,
+                   name="convT")
+    op()
+    torch.cuda.synchronize()
+    close(nchw(y), ref)
+
+
+DCN_CASES = [
+    # (batch, Hin, Win, C, Cout, stride, offset sigma)
+    (1, 16, 16, 64, 64, 1, 0.0),
+    (1, 16, 16, 64, 64, 1, 2.0),
+    (2, 32, 24, 128, 128, 1, 2.0),
+    (1, 40, 48, 128, 128, 2, 2.0),
+    (2, 20, 20, 256, 256, 1, 3.0),
+    (1, 32, 32, 256, 256, 2, 3.0),
+    (1, 10, 14, 512, 512, 1, 4.0),
+]
+
+
+@pytest.mark.parametrize("case", DCN_CASES, ids=lambda c: "b%d_%dx%d_c%d_o%d_s%d_sig%g" % c)
+def test_dcn_igemm(case):
+    import torchvision.ops as tvops
+    from ocr_vi_invoice_b200 import ops
+    _setup()
+    b, h, w, ci, co, s, sig = case
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(sum(int(v * 7) for v in case if not isinstance(v, str)) & 0xffff)
+    x = torch.randn(b, ci, h, w, device=dev, generator=g)
+    wt = torch.randn(co, ci, 3, 3, device=dev, generator=g) / (9 * ci) ** 0.5
+    oh, ow = h // s, w // s
+    om = torch.zeros(b, oh, ow, 32, device=dev)
+    om[..., :18] = torch.randn(b, oh, ow, 18, device=dev, generator=g) * sig
+    om[..., 18:27] = torch.randn(b, oh, ow, 9, device=dev, generator=g)
+    # a few exact-integer and boundary offsets (bilinear edge cases: h == -1, h == H, integer coords)
+    om[:, 0, 0, 0:18] = -1.0
+    om[:, -1, -1, 0:18] = 1.0
+    om[:, oh // 2, ow // 2, 0:18] = 0.0
+    scale = torch.rand(co, device=dev, generator=g) + 0.5
+    shift = torch.randn(co, device=dev, generator=g) * 0.1
+    xb, wb = x.to(torch.bfloat16).float(), wt.to(torch.bfloat16).float()
+    offset = om[..., :18].permute(0, 3, 1, 2).contiguous()
+    mask = torch.sigmoid(om[..., 18:27]).permute(0, 3, 1, 2).contiguous()
+    ref = tvops.deform_conv2d(xb, offset, wb, None, stride=s, padding=1, mask=mask)
+    ref = (ref * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)).relu()
+    wp = ops.pack_conv_weight(wt, ops.choose_n_pad(co))
+    n_pad = wp.shape[0]
+    sc, sh = ops.pad_vec(scale, n_pad, 1.0), ops.pad_vec(shift, n_pad)
+    y = torch.full((b, oh, ow, co), float("nan"), device=dev, dtype=torch.bfloat16)
+    op = ops.Igemm(ops.IGEMM_DCN, nhwc(x), wp, sc, sh, y, batch=b, in_h=h, in_w=w, in_c=ci, out_c=co, ksize=3,
+                   stride=s, flags=ops.EPI_RELU, offsets=om, name=str(case))
+    op()
+    torch.cuda.synchronize()
+    close(nchw(y), ref, rel_rms=3e-2)
+    y2 = torch.zeros_like(y)
+    ops.ref_dcn2d(nhwc(x), om, wp, sc, sh, y2, b, h, w, ci, co, s, ops.EPI_RELU, co)
+    torch.cuda.synchronize()
+    close(nchw(y2), ref, rel_rms=3e-2)
+    # tensor-core path vs cross-check kernel: same rounding points, only accumulation order differs
+    close(nchw(y), nchw(y2), rel_rms=1e-2, rtol=1e-2)
