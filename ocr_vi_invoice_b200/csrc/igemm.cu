@@ -28,6 +28,7 @@ constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB per stage
 constexpr int kGatherWarps = 8;                 // producer warps of the gather (DCN / stem) variant
 constexpr int kBaseWarps = 6;                   // TMA, MMA, 4 epilogue
 constexpr int kMaxStages = 8;
+constexpr int kMaxSmem = 227 * 1024;
 
 struct IgemmParams {
     int mode, batch, in_h, in_w, in_c, out_h, out_w, out_c;
@@ -556,7 +557,7 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     op->gather = (d->mode != B200_IGEMM_CONV);
 
     const int b_bytes = block_n * 128;
-    const int budget = 227 * 1024 - 1024 /*alignment*/ - 256 /*barriers*/;
+    const int budget = kMaxSmem - 1024 /*alignment*/ - 256 /*barriers*/;
     int stages = budget / (kABytes + b_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) stages = 2;
@@ -599,11 +600,10 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
             }
         }
     }
-    cudaError_t e;
-    if (op->gather)
-        e = cudaFuncSetAttribute(igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, op->smem_bytes);
-    else
-        e = cudaFuncSetAttribute(igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, op->smem_bytes);
+    // the attribute is per kernel function, not per op: always raise it to the full 227 KB opt-in
+    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) {
         delete op;
         return set_error("igemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));

@@ -1,0 +1,234 @@
+"""Execution plan of the DBNet++ forward on one B200: weight preparation + a static list of kernel launches.
+
+The reference runs ~250 eager torch ops per forward.  Here a plan is built once per
+(batch, H, W): every convolution becomes one tcgen05 implicit-GEMM launch with BN / bias / ReLU / residual /
+nearest-upsample-add fused in its epilogue, activations live in NHWC bf16 buffers owned by the plan, and the
+launch list can be captured into a CUDA graph.  Layer order follows model/det/backbone.py:55-60,
+torchvision Bottleneck.forward (resnet.py:143-163), model/det/neck.py:26-46,57-79 and model/det/head.py:32-48.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from ... import ops
+
+LAYER_CFG = ((1, 3, 64), (2, 4, 128), (3, 6, 256), (4, 3, 512))
+MAP_NAMES = ("binary", "thresh", "thresh_binary", "bin_logits", "thresh_logits")
+
+
+def _bn_fold(bn, conv_bias=None):
+    return ops.fold_bn(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps, conv_bias)
+
+
+class PreparedWeights:
+    """bf16 K-major weight matrices + fp32 per-column scale/shift for every layer (built once per state)."""
+
+    def __init__(self, model, device):
+        bb = model.backbone.model
+        self.device = device
+        self.dcn = model.backbone.dcn
+        to = lambda t: t.detach().to(device=device, dtype=torch.float32)
+        P: Dict[str, tuple] = {}
+
+        def conv_bn(name, conv_w, bn, n_pad=None, conv_bias=None):
+            w = ops.pack_conv_weight(to(conv_w), n_pad)
+            s, t = _bn_fold(bn, None if conv_bias is None else to(conv_bias))
+            P[name] = (w, ops.pad_vec(to(s), w.shape[0], 1.0), ops.pad_vec(to(t), w.shape[0]))
+
+        # stem (torchvision resnet.py:197-199)
+        w = ops.pack_stem_weight(to(bb.conv1.weight), 64)
+        s, t = _bn_fold(bb.bn1)
+        P["stem"] = (w, ops.pad_vec(to(s), 64, 1.0), ops.pad_vec(to(t), 64))
+        for li, nblocks, _width in LAYER_CFG:
+            layer = getattr(bb, f"layer{li}")
+            for bi in range(nblocks):
+                blk = layer[bi]
+                p = f"layer{li}.{bi}"
+                conv_bn(p + ".conv1", blk.conv1.weight, blk.bn1)
+                if self.dcn and li >= 2:
+                    om = blk.conv2.offset_mask_conv
+                    w = ops.pack_conv_weight(to(om.weight), 32)
+                    P[p + ".offset"] = (w, torch.ones(32, device=device), ops.pad_vec(to(om.bias), 32))
+                conv_bn(p + ".conv2", blk.conv2.weight, blk.bn2)
+                conv_bn(p + ".conv3", blk.conv3.weight, blk.bn3)
+                if blk.downsample is not None:
+                    conv_bn(p + ".down", blk.downsample[0].weight, blk.downsample[1])
+        nk = model.neck
+        for i in range(4):
+            lc = nk.lateral_convs[i]
+            w = ops.pack_conv_weight(to(lc.weight))
+            P[f"lat{i}"] = (w, torch.ones(w.shape[0], device=device), ops.pad_vec(to(lc.bias), w.shape[0]))
+            conv_bn(f"smooth{i}", nk.fpn_convs[i].conv.weight, nk.fpn_convs[i].bn)
+        self.w_att = to(nk.asf.conv_atten.weight).reshape(4, 1024).contiguous()
+        self.b_att = to(nk.asf.conv_atten.bias).contiguous()
+        for br, seq in (("bin", model.head.bin_conv), ("thr", model.head.thresh_conv)):
+            conv_bn(f"head.{br}.0", seq[0].conv.weight, seq[0].bn)
+            w = ops.pack_convT_weight(to(seq[1].weight), 256)
+            s, t = _bn_fold(seq[2], to(seq[1].bias))
+            P[f"head.{br}.1"] = (w, to(s).repeat(4).contiguous(), to(t).repeat(4).contiguous())
+            # last ConvTranspose2d(64 -> 1): [ci][dy*2+dx] fp32, consumed by the head-tail kernel
+            P[f"head.{br}.4"] = (to(seq[4].weight).reshape(64, 4).contiguous(), float(seq[4].bias.detach().float().item()))
+        self.P = P
+        self.k = float(model.head.k)
+
+
+class Plan:
+    """Static launch list + activation buffers for one (batch, H, W)."""
+
+    def __init__(self, W: PreparedWeights, batch: int, H: int, Wd: int, keep_taps: bool = False):
+        if H % 32 or Wd % 32:
+            raise ValueError(f"DBNet++ input sizes must be multiples of 32 (got {H}x{Wd}); see pipeline2.py:33-40")
+        dev = W.device
+        self.W, self.batch, self.H, self.Wd = W, batch, H, Wd
+        self.steps: List = []
+        self.names: List[str] = []
+        self.taps: Dict[str, tuple] = {}  # name -> (NHWC tensor, channels)
+        self.flops = 0.0
+        self.n_igemm = 0
+        b = batch
+        bf = lambda *s: torch.empty(*s, device=dev, dtype=torch.bfloat16)
+        P = W.P
+
+        def igemm(name, mode, x, key, y, *, in_h, in_w, in_c, out_c, ksize, stride, flags=0, residual=None, res_ld=0,
+                  offsets=None, shuf_c=0, out_ld=None):
+            w, s, t = P[key]
+            op = ops.Igemm(mode, x, w, s, t, y, batch=b, in_h=in_h, in_w=in_w, in_c=in_c, out_c=out_c, ksize=ksize,
+                           stride=stride, flags=flags, residual=residual, res_ld=res_ld, offsets=offsets, shuf_c=shuf_c,
+                           out_ld=out_ld, name=name)
+            self.steps.append(op)
+            self.names.append(name)
+            self.flops += op.flops
+            self.n_igemm += 1
+            return op
+
+        # ---- stem: pack -> 7x7 s2 (+BN+ReLU) -> maxpool
+        self.x_in = torch.empty(b, 3, H, Wd, device=dev, dtype=torch.float32)
+        packed = bf(b, H // 2 + 3, Wd // 2 + 3, 16)
+        stem = bf(b, H // 2, Wd // 2, 64)
+        self.steps.append(lambda: ops.stem_pack(self.x_in, packed)); self.names.append("stem_pack")
+        igemm("stem", ops.IGEMM_STEM, packed, "stem", stem, in_h=H, in_w=Wd, in_c=3, out_c=64, ksize=7, stride=2,
+              flags=ops.EPI_RELU)
+        h, w = H // 4, Wd // 4
+        x = bf(b, h, w, 64)
+        self.steps.append(lambda s=stem, o=x: ops.maxpool3x3s2(s, o, b, H // 2, Wd // 2, 64)); self.names.append("maxpool")
+        cin = 64
+        feats = []
+        for li, nblocks, width in LAYER_CFG:
+            cout = width * 4
+            for bi in range(nblocks):
+                p = f"layer{li}.{bi}"
+                stride = 2 if (bi == 0 and li > 1) else 1
+                ho, wo = h // stride, w // stride
+                t1 = bf(b, h, w, width)
+                igemm(p + ".conv1", ops.IGEMM_CONV, x, p + ".conv1", t1, in_h=h, in_w=w, in_c=cin, out_c=width, ksize=1,
+                      stride=1, flags=ops.EPI_RELU)
+                t2 = bf(b, ho, wo, width)
+                if W.dcn and li >= 2:
+                    om = torch.empty(b, ho, wo, 32, device=dev, dtype=torch.float32)
+                    igemm(p + ".offset", ops.IGEMM_CONV, t1, p + ".offset", om, in_h=h, in_w=w, in_c=width, out_c=32,
+                          ksize=3, stride=stride, flags=ops.EPI_OUT_F32)
+                    igemm(p + ".dcn", ops.IGEMM_DCN, t1, p + ".conv2", t2, in_h=h, in_w=w, in_c=width, out_c=width,
+                          ksize=3, stride=stride, flags=ops.EPI_RELU, offsets=om)
+                else:
+                    igemm(p + ".conv2", ops.IGEMM_CONV, t1, p + ".conv2", t2, in_h=h, in_w=w, in_c=width, out_c=width,
+                          ksize=3, stride=stride, flags=ops.EPI_RELU)
+                if bi == 0:
+                    idn = bf(b, ho, wo, cout)
+                    igemm(p + ".down", ops.IGEMM_CONV, x, p + ".down", idn, in_h=h, in_w=w, in_c=cin, out_c=cout,
+                          ksize=1, stride=stride)
+                else:
+                    idn = x
+                y = bf(b, ho, wo, cout)
+                igemm(p + ".conv3", ops.IGEMM_CONV, t2, p + ".conv3", y, in_h=ho, in_w=wo, in_c=width, out_c=cout,
+                      ksize=1, stride=1, flags=ops.EPI_RES | ops.EPI_RELU, residual=idn, res_ld=cout)
+                if keep_taps and W.dcn and li >= 2:
+                    self.taps[f"backbone.model.{p}.bn2"] = (t2, width)
+                x, cin, h, w = y, cout, ho, wo
+            feats.append((x, cin, h, w))
+            if keep_taps:
+                self.taps[f"c{li + 1}"] = (x, cin)
+        # ---- neck: lateral 1x1 (+bias) with the top-down nearest-upsample add fused, then 3x3 smoothing
+        inner = [None] * 4
+        ps = [None] * 4
+        for i in (3, 2, 1, 0):
+            f, c, fh, fw = feats[i]
+            inner[i] = bf(b, fh, fw, 256)
+            if i == 3:
+                igemm(f"lat{i}", ops.IGEMM_CONV, f, f"lat{i}", inner[i], in_h=fh, in_w=fw, in_c=c, out_c=256, ksize=1,
+                      stride=1)
+            else:
+                igemm(f"lat{i}", ops.IGEMM_CONV, f, f"lat{i}", inner[i], in_h=fh, in_w=fw, in_c=c, out_c=256, ksize=1,
+                      stride=1, flags=ops.EPI_RES_UP2, residual=inner[i + 1], res_ld=256)
+            ps[i] = bf(b, fh, fw, 256)
+            igemm(f"smooth{i}", ops.IGEMM_CONV, inner[i], f"smooth{i}", ps[i], in_h=fh, in_w=fw, in_c=256, out_c=256,
+                  ksize=3, stride=1, flags=ops.EPI_RELU)
+            if keep_taps:
+                self.taps[f"p{i + 2}"] = (ps[i], 256)
+        sizes = [(feats[i][2], feats[i][3]) for i in range(4)]
+        fused = bf(b, sizes[0][0], sizes[0][1], 256)
+        self.steps.append(lambda: ops.asf_fwd(ps[0], ps[1], ps[2], ps[3], W.w_att, W.b_att, fused, b, sizes))
+        self.names.append("asf")
+        if keep_taps:
+            self.taps["asf"] = (fused, 256)
+        # ---- head
+        h4, w4 = sizes[0]
+        tails = {}
+        for br in ("bin", "thr"):
+            t = bf(b, h4, w4, 64)
+            igemm(f"head.{br}.0", ops.IGEMM_CONV, fused, f"head.{br}.0", t, in_h=h4, in_w=w4, in_c=256, out_c=64, ksize=3,
+                  stride=1, flags=ops.EPI_RELU)
+            u = bf(b, 2 * h4, 2 * w4, 64)
+            igemm(f"head.{br}.1", ops.IGEMM_CONV, t, f"head.{br}.1", u, in_h=h4, in_w=w4, in_c=64, out_c=256, ksize=1,
+                  stride=1, flags=ops.EPI_RELU | ops.EPI_SHUFFLE2, shuf_c=64)
+            tails[br] = u
+            if keep_taps:
+                self.taps[f"head.{'bin_conv' if br == 'bin' else 'thresh_conv'}.3"] = (u, 64)
+        self.tails = tails
+        self.maps: Optional[Dict[str, torch.Tensor]] = None
+        self.want = MAP_NAMES
+        self.graph = None
+
+        def head_tail():
+            (wb, bb_), (wt, bt) = P["head.bin.4"], P["head.thr.4"]
+            ops.db_head_fwd(tails["bin"], tails["thr"], wb, bb_, wt, bt, W.k, self.maps, b, 2 * h4, 2 * w4)
+
+        self.steps.append(head_tail)
+        self.names.append("db_head")
+        self.n_launches = len(self.steps)
+
+    def _alloc_maps(self):
+        dev = self.W.device
+        self.maps = {n: torch.empty(self.batch, 1, self.H, self.Wd, device=dev, dtype=torch.float32) for n in self.want}
+
+    def run(self, x: torch.Tensor, want=MAP_NAMES, use_graph: bool = False) -> Dict[str, torch.Tensor]:
+        """One forward.  Fresh output tensors per call unless `use_graph` (then the plan's static buffers are
+        returned and overwritten by the next call)."""
+        self.x_in.copy_(x, non_blocking=True)
+        if use_graph:
+            if self.graph is None or tuple(want) != tuple(self.want):
+                self.want = tuple(want)
+                self._alloc_maps()
+                self._launch_all()  # warm-up outside capture
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._launch_all()
+                self.graph = g
+            self.graph.replay()
+            return dict(self.maps)
+        self.want = tuple(want)
+        self.graph = None
+        self._alloc_maps()
+        self._launch_all()
+        return dict(self.maps)
+
+    def _launch_all(self):
+        for s in self.steps:
+            s()
+
+    def tap(self, name: str) -> torch.Tensor:
+        """NCHW fp32 copy of a recorded stage tensor (tests only)."""
+        t, c = self.taps[name]
+        return t[..., :c].float().permute(0, 3, 1, 2).contiguous()

@@ -1,0 +1,243 @@
+"""GPU parity of the fused bandwidth kernels and of the whole DBNetPP forward, through the drop-in module.
+
+Oracle = oracle/dbnet_oracle.py (fp32 CPU restatement, pinned to the reference by tests/golden/dbnet_small.npz).
+The CUDA path computes in bf16 with fp32 accumulation, so tolerances are stated per stage as a fraction of the
+stage's RMS (bf16 has 8 bits of mantissa: 2^-9 relative rounding per stored activation, compounding over ~55
+layers); logits are compared before the sigmoid, the probability maps with an absolute bound.
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden"
+torch.backends.cudnn.allow_tf32 = False        # the torch fp32 references below must be real fp32
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def nchw(y):
+    return y.float().permute(0, 3, 1, 2).contiguous()
+
+
+def rel_rms(a, b):
+    return ((a.float() - b.float()).pow(2).mean().sqrt() / (b.float().pow(2).mean().sqrt() + 1e-12)).item()
+
+
+@pytest.mark.parametrize("size", [(1, 16, 24), (2, 40, 56)])
+def test_asf_kernel(size):
+    from ocr_vi_invoice_b200 import ops
+    b, h2, w2 = size
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(3)
+    sizes = [(h2, w2), (h2 // 2, w2 // 2), (h2 // 4, w2 // 4), (h2 // 8, w2 // 8)]
+    ps = [torch.randn(b, 256, h, w, device=dev, generator=g).to(torch.bfloat16) for h, w in sizes]
+    w_att = torch.randn(4, 1024, device=dev, generator=g) * 0.05
+    b_att = torch.randn(4, device=dev, generator=g) * 0.1
+    out = torch.empty(b, h2, w2, 256, device=dev, dtype=torch.bfloat16)
+    ops.asf_fwd(*[nhwc(p.float()) for p in ps], w_att, b_att, out, b, sizes)
+    torch.cuda.synchronize()
+    ups = [ps[0].float()] + [F.interpolate(p.float(), size=(h2, w2), mode="bilinear", align_corners=True) for p in ps[1:]]
+    score = F.softmax(F.conv2d(torch.cat(ups, 1), w_att.view(4, 1024, 1, 1), b_att), dim=1)
+    ref = sum(u * score[:, i:i + 1] for i, u in enumerate(ups))
+    got = nchw(out)
+    assert rel_rms(got, ref) < 4e-3
+    torch.testing.assert_close(got, ref, rtol=1.6e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("size", [(1, 32, 48), (2, 70, 36)])
+def test_db_head_kernel(size):
+    from ocr_vi_invoice_b200 import ops
+    b, h, w = size
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(4)
+    tb = torch.randn(b, 64, h, w, device=dev, generator=g).relu().to(torch.bfloat16)
+    tt = torch.randn(b, 64, h, w, device=dev, generator=g).relu().to(torch.bfloat16)
+    wb = torch.randn(64, 1, 2, 2, device=dev, generator=g) * 0.3
+    wt = torch.randn(64, 1, 2, 2, device=dev, generator=g) * 0.3
+    bb, bt = 0.17, -0.4
+    maps = {n: torch.full((b, 1, 2 * h, 2 * w), float("nan"), device=dev) for n in
+            ("binary", "thresh", "thresh_binary", "bin_logits", "thresh_logits")}
+    ops.db_head_fwd(nhwc(tb.float()), nhwc(tt.float()), wb.reshape(64, 4).contiguous(), bb, wt.reshape(64, 4).contiguous(),
+                    bt, 50.0, maps, b, h, w)
+    torch.cuda.synchronize()
+    bl = F.conv_transpose2d(tb.float(), wb, torch.tensor([bb], device=dev), stride=2)
+    tl = F.conv_transpose2d(tt.float(), wt, torch.tensor([bt], device=dev), stride=2)
+    torch.testing.assert_close(maps["bin_logits"], bl, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(maps["thresh_logits"], tl, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(maps["binary"], torch.sigmoid(bl), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(maps["thresh"], torch.sigmoid(tl), rtol=1e-4, atol=1e-4)
+    ref_tb = torch.reciprocal(1 + torch.exp(-50.0 * (torch.sigmoid(bl) - torch.sigmoid(tl))))
+    torch.testing.assert_close(maps["thresh_binary"], ref_tb, rtol=1e-3, atol=5e-3)
+    # NULL maps are skipped
+    only = {"binary": torch.empty_like(maps["binary"])}
+    ops.db_head_fwd(nhwc(tb.float()), nhwc(tt.float()), wb.reshape(64, 4).contiguous(), bb, wt.reshape(64, 4).contiguous(),
+                    bt, 50.0, only, b, h, w)
+    torch.cuda.synchronize()
+    assert torch.equal(only["binary"], maps["binary"])
+
+
+def _model(seed, offset_px=1.5):
+    from ocr_vi_invoice_b200.model.det.dbnet import DBNetPP
+    from oracle.weights import make_state_dict
+    sd = make_state_dict(seed, offset_px=offset_px)
+    m = DBNetPP(pretrained=False)
+    m.load_state_dict(sd, strict=True)
+    return m.cuda().eval(), sd
+
+
+# Tolerances, stated per stage as (rms error / rms of the stage).  bf16 storage of ~55 chained activations plus
+# bf16 weights costs this much by itself: the fp32 oracle with bf16 rounding emulated at the same points
+# (dbnet_forward(emulate_bf16=True)) sits 0.005 (c2) .. 0.08 (c5) away from the fp32 oracle on these inputs.
+# The seeded test weights are a worst case: features are spatially white, so every DCN layer turns input noise
+# into sampling-position noise (offset error ~ 1.5 px x relative input error) and amplifies it ~3x on its branch;
+# that is why the DCN rows are loose here.  The kernel itself is pinned tightly in tests/test_gpu_igemm.py
+# (same inputs -> torchvision.ops.deform_conv2d), and `test_dbnet_small_offsets_tight` below runs the whole net
+# with 0.25 px offsets, where that amplification is absent.
+# TOL_FP32 bounds CUDA vs the reference-pinned fp32 oracle; TOL_EMU bounds CUDA vs the bf16-emulating oracle,
+# where only accumulation order and rounding flips (amplified the same way) remain.
+TOL_FP32 = {"c2": 0.02, "c3": 0.04, "c4": 0.09, "c5": 0.15, "p2": 0.12, "p3": 0.12, "p4": 0.13, "p5": 0.15, "asf": 0.10,
+            "dcn": 0.40, "head3": 0.10, "logits": 0.12}
+TOL_EMU = {"c2": 0.004, "c3": 0.015, "c4": 0.06, "c5": 0.10, "p2": 0.08, "p3": 0.08, "p4": 0.09, "p5": 0.10, "asf": 0.07,
+           "dcn": 0.30, "head3": 0.07, "logits": 0.09}
+TOL_TIGHT = {"c2": 0.012, "c3": 0.02, "c4": 0.03, "c5": 0.04, "p2": 0.04, "p3": 0.04, "p4": 0.04, "p5": 0.04, "asf": 0.04,
+             "dcn": 0.05, "head3": 0.04, "logits": 0.04}
+
+
+def _check_against(out, taps, ref_out, ref_taps, sd, tol, prob_mean=0.03, prob_max=1.01):
+    from oracle import dbnet_oracle as dbo
+    report = {}
+    fails = []
+
+    def chk(name, r, bound):
+        report[name] = round(r, 4)
+        if not r < bound:
+            fails.append(f"{name}: {r:.4f} >= {bound}")
+
+    for name in ("c2", "c3", "c4", "c5", "p2", "p3", "p4", "p5", "asf"):
+        chk(name, rel_rms(taps[name].cpu(), ref_taps[name]), tol[name])
+    for k in [k for k in taps if k.endswith(".bn2")]:
+        p = k[:-4]
+        ref = F.relu(dbo.bn(ref_taps[p + ".conv2"], sd, p + ".bn2"))
+        chk(k.replace("backbone.model.", ""), rel_rms(taps[k].cpu(), ref), tol["dcn"])
+    for k in ("head.bin_conv.3", "head.thresh_conv.3"):
+        chk(k, rel_rms(taps[k].cpu(), ref_taps[k]), tol["head3"])
+    for k in ("bin_logits", "thresh_logits"):
+        chk(k, rel_rms(out[k].cpu(), ref_out[k]), tol["logits"])
+        report[k + ".maxabs"] = round((out[k].cpu() - ref_out[k]).abs().max().item(), 4)
+    for k in ("binary", "thresh", "thresh_binary"):
+        err = (out[k].cpu() - ref_out[k]).abs()
+        report[k + ".mean"] = round(err.mean().item(), 5)
+        report[k + ".maxabs"] = round(err.max().item(), 4)
+        if k != "thresh_binary":  # k=50 amplifies differences near the decision boundary: reported, mean-bounded
+            if not (err.mean().item() < prob_mean and err.max().item() < prob_max):
+                fails.append(f"{k}: mean {err.mean():.4f} max {err.max():.4f}")
+        elif not err.mean().item() < 3 * prob_mean:
+            fails.append(f"{k}: mean {err.mean():.4f}")
+    print(report)
+    return fails
+
+
+def test_dbnet_vs_reference_golden():
+    """Reference's own outputs (golden, generated from /root/reference) on a 64x96 input."""
+    g = np.load(GOLD / "dbnet_small.npz")
+    m, sd = _model(int(g["seed"]))
+    x = torch.from_numpy(g["x"]).cuda()
+    out, taps = m.forward_with_taps(x)
+    torch.cuda.synchronize()
+    ref_out = {k[4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("out.")}
+    ref_taps = {k[4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("tap.")}
+    assert set(out) == set(ref_out)
+    for k in out:
+        assert out[k].shape == ref_out[k].shape and out[k].dtype == torch.float32
+    fails = _check_against(out, taps, ref_out, ref_taps, sd, TOL_FP32)
+    # and against the bf16-emulating oracle (computed here on the CPU; 64x96 is small)
+    from oracle import dbnet_oracle as dbo
+    emu_taps = {}
+    emu_out = dbo.dbnet_forward(sd, torch.from_numpy(g["x"]), taps=emu_taps, emulate_bf16=True)
+    fails += _check_against(out, taps, emu_out, emu_taps, sd, TOL_EMU, prob_mean=0.02)
+    assert not fails, fails
+
+
+def test_dbnet_vs_oracle_batch2_odd_tiles():
+    """Batch 2 at 160x224 (tile remainders at every stage) against the fp32 oracle."""
+    from oracle import dbnet_oracle as dbo
+    m, sd = _model(77)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 3, 160, 224, generator=g)
+    ref_taps = {}
+    ref_out = dbo.dbnet_forward(sd, x, taps=ref_taps)
+    out, taps = m.forward_with_taps(x.cuda())
+    torch.cuda.synchronize()
+    fails = _check_against(out, taps, ref_out, ref_taps, sd, TOL_FP32)
+    emu_taps = {}
+    emu_out = dbo.dbnet_forward(sd, x, taps=emu_taps, emulate_bf16=True)
+    fails += _check_against(out, taps, emu_out, emu_taps, sd, TOL_EMU, prob_mean=0.02)
+    assert not fails, fails
+    # plain forward (fresh outputs) and CUDA-graph replay give the same bits as the tapped run
+    out2 = m(x.cuda())
+    m.use_cuda_graph = True
+    out3 = m(x.cuda())
+    out4 = m(x.cuda())
+    torch.cuda.synchronize()
+    for k in out:
+        assert torch.equal(out[k], out2[k]) and torch.equal(out[k], out3[k]) and torch.equal(out[k], out4[k])
+    m.use_cuda_graph = False
+
+
+def test_dbnet_small_offsets_tight():
+    """Whole net with 0.25 px deformable offsets (no sampling-noise amplification): tight bf16-level bounds."""
+    from oracle import dbnet_oracle as dbo
+    m, sd = _model(31, offset_px=0.25)
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(1, 3, 128, 160, generator=g)
+    ref_taps = {}
+    ref_out = dbo.dbnet_forward(sd, x, taps=ref_taps)
+    out, taps = m.forward_with_taps(x.cuda())
+    torch.cuda.synchronize()
+    fails = _check_against(out, taps, ref_out, ref_taps, sd, TOL_TIGHT, prob_mean=0.01, prob_max=0.3)
+    assert not fails, fails
+
+
+def test_reference_api_conformance():
+    """The reference's own det tests (tests/test_model.py:102-183): shapes, ranges, keys, attributes."""
+    m, _ = _model(1)
+    x = torch.randn(2, 3, 640, 640, device="cuda")
+    preds = m(x)
+    for k in ("binary", "thresh", "thresh_binary"):
+        assert preds[k].shape == (2, 1, 640, 640)
+        assert preds[k].min() >= 0 and preds[k].max() <= 1
+    assert "bin_logits" in preds and "thresh_logits" in preds
+    assert isinstance(preds, dict) and preds["binary"][0].cpu().numpy().shape == (1, 640, 640)  # pipeline2.py:318-320
+    info = m.plan_info(2, 640, 640)
+    assert abs(info["flops"] / 2 - 341.26e9 * (640 * 640) / (1024 * 1024)) / 133.3e9 < 0.08
+    # changing weights invalidates the prepared copies
+    with torch.no_grad():
+        m.head.bin_conv[4].bias.add_(3.0)
+    preds2 = m(x)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(preds2["bin_logits"], preds["bin_logits"] + 3.0, rtol=0, atol=1e-4)
+
+
+def test_dcn_false_variant_runs():
+    from ocr_vi_invoice_b200.model.det.dbnet import DBNetPP
+    from oracle import dbnet_oracle as dbo
+    torch.manual_seed(0)
+    m = DBNetPP(pretrained=False, dcn=False)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_var.uniform_(0.5, 1.5)
+            mod.running_mean.normal_(0, 0.1)
+    m = m.cuda().eval()
+    x = torch.randn(1, 3, 96, 64)
+    out = m(x.cuda())
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    ref = dbo.dbnet_forward(sd, x, dcn=False)
+    torch.cuda.synchronize()
+    assert rel_rms(out["bin_logits"].cpu(), ref["bin_logits"]) < 0.06

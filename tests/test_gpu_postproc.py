@@ -1,0 +1,111 @@
+"""GPU parity of the post-processing (threshold -> CCL -> boxes): bit-exact against oracle/postproc_oracle.py."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden"
+
+
+def _run(prob_np, **kw):
+    from ocr_vi_invoice_b200.postprocess import DBPostProcessor
+    pp = DBPostProcessor(thresh=kw.get("thresh", 0.3), box_thresh=kw.get("box_thresh", 0.6),
+                         max_candidates=kw.get("max_candidates", 1000), unclip_ratio=kw.get("unclip_ratio", 1.5))
+    pp.min_area = kw.get("min_area", 10)
+    prob = torch.from_numpy(prob_np).cuda()
+    if prob.dim() == 2:
+        prob = prob[None]
+    buf = pp.run_device(prob, want_labels=True)
+    recs, ncomp = pp.fetch(buf)
+    return buf["labels"].cpu().numpy(), ncomp, recs, pp
+
+
+def _assert_same(prob_np, **kw):
+    from oracle import postproc_oracle as ppo
+    labels, ncomp, recs, _ = _run(prob_np, **kw)
+    maps = prob_np if prob_np.ndim == 3 else prob_np[None]
+    for i, prob in enumerate(maps):
+        ref_lab, ref_n, ref_recs = ppo.postprocess(prob, kw.get("thresh", 0.3), kw.get("box_thresh", 0.6),
+                                                   kw.get("max_candidates", 1000), kw.get("unclip_ratio", 1.5),
+                                                   kw.get("min_area", 10))
+        assert ncomp[i] == ref_n
+        assert np.array_equal(labels[i], ref_lab), "label map differs"
+        assert len(recs[i]) == len(ref_recs)
+        for name in ref_recs.dtype.names:
+            assert np.array_equal(recs[i][name], ref_recs[name]), f"box field {name} differs"
+    return recs
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_rendered_maps_bit_exact(seed):
+    from oracle import postproc_oracle as ppo
+    prob = np.stack([ppo.render_prob_map(256, 320, seed=seed * 10 + i, n_boxes=20 + 5 * i) for i in range(3)])
+    recs = _assert_same(prob, thresh=0.3, box_thresh=0.5, unclip_ratio=1.6, min_area=10)
+    assert sum(len(r) for r in recs) > 30
+
+
+def test_edge_cases_bit_exact():
+    rng = np.random.default_rng(0)
+    _assert_same(np.zeros((64, 96), np.float32))                                   # empty map
+    _assert_same(np.full((64, 96), 0.9, np.float32))                               # one giant component
+    _assert_same(rng.random((128, 160), dtype=np.float32), thresh=0.5, min_area=1)  # noise: thousands of specks
+    _assert_same(rng.random((70, 45), dtype=np.float32), thresh=0.4, min_area=1)   # width not a multiple of 32
+    spiral = np.zeros((65, 65), np.float32)                                        # long thin snake, many merges
+    for k in range(0, 32, 2):
+        spiral[k, k:65 - k] = 0.9; spiral[64 - k, k:65 - k] = 0.9
+        spiral[k:65 - k, 64 - k] = 0.9; spiral[k + 2:65 - k, k] = 0.9
+    _assert_same(spiral, min_area=1)
+    checker = (np.indices((64, 64)).sum(0) % 2).astype(np.float32)                 # pure diagonal connectivity
+    _assert_same(checker, thresh=0.5, min_area=1)
+    dots = np.zeros((256, 256), np.float32)                                        # > max_candidates components
+    dots[::3, ::3] = 0.0
+    for y in range(0, 256, 6):
+        for x in range(0, 256, 6):
+            dots[y:y + 4, x:x + 4] = 0.8
+    _assert_same(dots, max_candidates=1000, min_area=4)
+    _assert_same(dots, max_candidates=37, min_area=4)
+
+
+def test_full_size_properties():
+    """1024x1024, batch 4 (BASELINE config-2 map size): oracle parity + size-independent properties."""
+    from oracle import postproc_oracle as ppo
+    prob = np.stack([ppo.render_prob_map(1024, 1024, seed=100 + i, n_boxes=180) for i in range(4)])
+    labels, ncomp, recs, pp = _run(prob, thresh=0.3, box_thresh=0.5, unclip_ratio=1.6, min_area=10)
+    fg = prob > np.float32(0.3)
+    for i in range(4):
+        assert np.array_equal(labels[i] > 0, fg[i])                                # foreground preserved
+        assert labels[i].max() == ncomp[i]
+        # idempotence: labelling the label map's foreground again gives the same labels
+    relab, _, _, _ = _run((labels > 0).astype(np.float32), thresh=0.5)
+    assert np.array_equal(relab, labels)
+    # npix of kept boxes sums to no more than the foreground; qsum/npix within [box_thresh, 1]
+    for i in range(4):
+        assert recs[i]["npix"].sum() <= fg[i].sum()
+        s = recs[i]["qsum"].astype(np.float64) / (recs[i]["npix"] * 16777216.0)
+        assert (s >= 0.5).all() and (s <= 1.0).all()
+    _assert_same(prob[:2], thresh=0.3, box_thresh=0.5, unclip_ratio=1.6, min_area=10)
+
+
+def test_reference_call_signature_and_cv2_agreement():
+    """DBPostProcessor(pred (1,H,W) numpy) -> (list[(K,2) int64 writable], list[float]); agreement with the cv2
+    half of the reference path (golden from tests/golden/make_golden.py) is reported as a match rate."""
+    from ocr_vi_invoice_b200.postprocess import DBPostProcessor
+    from oracle import postproc_oracle as ppo
+    p = np.load(GOLD / "postproc_cv2.npz")
+    pp = DBPostProcessor(thresh=0.3, box_thresh=0.5, unclip_ratio=1.6)
+    pp.min_area = 10
+    for i in range(3):
+        prob = p[f"{i}.prob"]
+        boxes, scores = pp(prob[None])
+        assert len(boxes) == len(scores) > 0
+        b0 = boxes[0]
+        assert b0.shape == (4, 2) and b0.dtype == np.int64 and b0.flags.writeable
+        b0[:, 0] = b0[:, 0] / 0.5                                                   # pipeline2.py:325-327
+        ours = [(b[:, 0].min(), b[:, 1].min(), b[:, 0].max(), b[:, 1].max()) for b in boxes[1:]]
+        theirs = [tuple(int(v) for v in r) for r in p[f"{i}.cv2_rects"]]
+        assert ppo.match_rate(ours, theirs, 0.8) >= 0.85
+        # torch CUDA input, batched API
+        res = pp.batch(torch.from_numpy(prob).cuda()[None, None])
+        assert len(res) == 1 and len(res[0][0]) == len(boxes)

@@ -1,0 +1,100 @@
+"""CPU: host-side mirror of the reference interface (constructor, state_dict, weight re-layout, error behaviour).
+Mirrors tests/test_model.py:57-183 of the reference where it does not need a device."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from ocr_vi_invoice_b200 import ops
+from ocr_vi_invoice_b200.model.det.dbnet import DBNetPP
+from oracle.weights import make_state_dict, state_dict_keys
+
+
+@pytest.fixture(scope="module")
+def model():
+    return DBNetPP(pretrained=False)
+
+
+def test_parameter_counts(model):
+    count = lambda m: sum(p.numel() for p in m.parameters() if p.requires_grad)
+    total = count(model)
+    assert count(model.backbone) + count(model.neck) + count(model.head) == total  # test_model.py:96
+    assert total == 30106637
+    assert model.backbone.out_channels == [256, 512, 1024, 2048]                    # test_model.py:162-169
+
+
+def test_state_dict_is_reference_compatible(model):
+    assert list(model.state_dict().keys()) == state_dict_keys()
+    sd = make_state_dict(5)
+    assert model.load_state_dict(sd, strict=True).missing_keys == []
+    prefixed = {"module." + k: v for k, v in sd.items()}                             # pipeline2.py:49-50
+    assert model.load_state_dict({k.replace("module.", "", 1): v for k, v in prefixed.items()}).unexpected_keys == []
+    torch.testing.assert_close(model.backbone.layer2[1].conv2.offset_mask_conv.bias,
+                               sd["backbone.model.layer2.1.conv2.offset_mask_conv.bias"])
+
+
+def test_offset_conv_zero_init():
+    m = DBNetPP(pretrained=False)
+    om = m.backbone.model.layer3[0].conv2.offset_mask_conv                          # dcn.py:28-29
+    assert om.weight.abs().sum() == 0 and om.bias.abs().sum() == 0 and om.stride == (2, 2)
+
+
+def test_rejections(model):
+    with pytest.raises(NotImplementedError):
+        DBNetPP(backbone="resnet18", pretrained=False)
+    with pytest.raises(NotImplementedError):
+        DBNetPP(backbone="resnet101", pretrained=False)                              # backbone.py:21 raises too
+    with pytest.raises(RuntimeError, match="no network"):
+        DBNetPP()                                                                    # pretrained=True default
+    model.eval()
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        model(torch.zeros(1, 3, 64, 64))
+    with pytest.raises(RuntimeError, match="no eager forward"):
+        model.backbone(torch.zeros(1, 3, 64, 64))
+
+
+def test_dcn_false_constructs():
+    m = DBNetPP(pretrained=False, dcn=False)
+    assert isinstance(m.backbone.model.layer2[0].conv2, torch.nn.Conv2d)
+    assert len(m.state_dict()) == 754 - 2 * 2 * 13
+
+
+def test_pack_conv_weight_is_tap_major():
+    w = torch.randn(5, 64, 3, 3)
+    p = ops.pack_conv_weight(w, 32).float()
+    assert p.shape == (32, 576) and p[5:].abs().sum() == 0
+    torch.testing.assert_close(p[2, 4 * 64 + 7], w[2, 7, 1, 1].to(torch.bfloat16).float())
+
+
+def test_pack_stem_weight_equals_conv7x7():
+    """The space-to-depth re-layout reproduces conv 7x7 s2 p3 exactly (fp32 emulation of pack + GEMM)."""
+    g = torch.Generator().manual_seed(0)
+    img = torch.randn(1, 3, 16, 24, generator=g).to(torch.bfloat16).float()
+    w = torch.randn(64, 3, 7, 7, generator=g).to(torch.bfloat16).float()
+    wp = ops.pack_stem_weight(w, 64).float()                       # [64][ty][j][16]
+    H, W = 16, 24
+    packed = torch.zeros(H // 2 + 3, W // 2 + 3, 16)
+    blocks = img[0].reshape(3, H // 2, 2, W // 2, 2).permute(1, 3, 2, 4, 0).reshape(H // 2, W // 2, 12)
+    packed[2:2 + H // 2, 2:2 + W // 2, :12] = blocks
+    out = torch.zeros(64, H // 2, W // 2)
+    for oy in range(H // 2):
+        for ox in range(W // 2):
+            a = packed[oy:oy + 4, ox:ox + 4, :].reshape(256)
+            out[:, oy, ox] = wp @ a
+    ref = F.conv2d(img, w, stride=2, padding=3)[0]
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-4)
+
+
+def test_pack_convT_weight():
+    w = torch.randn(64, 64, 2, 2)
+    p = ops.pack_convT_weight(w, 256).float()
+    torch.testing.assert_close(p[(1 * 2 + 0) * 64 + 9, 17], w[17, 9, 1, 0].to(torch.bfloat16).float())
+
+
+def test_postprocessor_attributes():
+    from ocr_vi_invoice_b200.postprocess import DBPostProcessor
+    pp = DBPostProcessor(thresh=0.3, box_thresh=0.5, unclip_ratio=1.6)
+    pp.min_area = 10                                                                  # pipeline2.py:254-259
+    assert (pp.thresh, pp.box_thresh, pp.max_candidates, pp.unclip_ratio, pp.min_size) == (0.3, 0.5, 1000, 1.6, 3)
+    with pytest.raises(RuntimeError):
+        pp.run_device(torch.zeros(1, 8, 8))

@@ -1,0 +1,132 @@
+"""CPU: the oracle restatement against golden vectors produced by the reference itself
+(tests/golden/make_golden.py, run in the authoring container where /root/reference exists)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dbnet_oracle as dbo
+from oracle import postproc_oracle as ppo
+from oracle.weights import make_state_dict, state_dict_keys, unique_param_table
+
+GOLD = Path(__file__).parent / "golden"
+
+
+def test_state_dict_key_set():
+    keys = state_dict_keys()
+    assert len(keys) == 754 and len(set(keys)) == 754
+    assert len(unique_param_table()) == 410
+    sd = make_state_dict(3)
+    assert list(sd.keys()) == keys
+    assert len({id(v) for v in sd.values()}) == 410            # 344 alias pairs share storage
+    assert sd["backbone.layer1.0.weight"] is sd["backbone.model.conv1.weight"]
+    assert sd["backbone.layer3.2.conv2.offset_mask_conv.bias"].shape == (27,)
+    n_params = sum(v.numel() for k, v in {id(v): v for v in sd.values()}.items() if v.dtype.is_floating_point
+                   and v.dim() > 0) - sum(v.numel() for k, v in sd.items()
+                                          if k.startswith("backbone.model.") and "running_" in k) \
+        - sum(v.numel() for k, v in sd.items() if not k.startswith("backbone.") and "running_" in k)
+    assert n_params == 30106637                                 # reference parameter count
+
+
+def test_model_oracle_matches_reference_golden():
+    g = np.load(GOLD / "dbnet_small.npz")
+    sd = make_state_dict(int(g["seed"]))
+    taps = {}
+    out = dbo.dbnet_forward(sd, torch.from_numpy(g["x"]), taps=taps)
+    for k, v in out.items():
+        ref = torch.from_numpy(g["out." + k])
+        assert v.shape == ref.shape
+        torch.testing.assert_close(v, ref, rtol=1e-5, atol=1e-5)
+    tap_keys = [k[4:] for k in g.files if k.startswith("tap.")]
+    assert len(tap_keys) == 24
+    for k in tap_keys:
+        ref = torch.from_numpy(g["tap." + k])
+        torch.testing.assert_close(taps[k], ref, rtol=1e-5, atol=1e-5 * float(ref.abs().max()))
+
+
+def test_model_oracle_with_torchvision_op():
+    """Same forward, but through the installed third-party op the reference calls (dcn.py:48)."""
+    pytest.importorskip("torchvision")
+    g = np.load(GOLD / "dbnet_small.npz")
+    sd = make_state_dict(int(g["seed"]))
+    out = dbo.dbnet_forward(sd, torch.from_numpy(g["x"]), deform=dbo.torchvision_deform)
+    torch.testing.assert_close(out["bin_logits"], torch.from_numpy(g["out.bin_logits"]), rtol=1e-5, atol=1e-5)
+
+
+def test_deform_conv_restatement_matches_torchvision_golden():
+    d = np.load(GOLD / "dcn_torchvision.npz")
+    for i in range(3):
+        t = lambda k: torch.from_numpy(d[f"{i}.{k}"])
+        y = dbo.deform_conv2d_ref(t("x"), t("offset"), t("weight"), t("mask"), stride=int(d[f"{i}.stride"]))
+        torch.testing.assert_close(y, t("y"), rtol=1e-5, atol=1e-5)
+
+
+def test_deform_conv_float64_property():
+    """Zero offsets and unit mask reduce the op to a plain convolution."""
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 4, 7, 9, generator=g, dtype=torch.float64)
+    w = torch.randn(5, 4, 3, 3, generator=g, dtype=torch.float64)
+    for s in (1, 2):
+        ho, wo = (7 + 2 - 3) // s + 1, (9 + 2 - 3) // s + 1
+        y = dbo.deform_conv2d_ref(x, torch.zeros(1, 18, ho, wo, dtype=torch.float64), w,
+                                  torch.ones(1, 9, ho, wo, dtype=torch.float64), stride=s)
+        torch.testing.assert_close(y, torch.nn.functional.conv2d(x, w, stride=s, padding=1), rtol=1e-12, atol=1e-12)
+
+
+# ----------------------------------------------------------------------------- post-processing oracle
+def test_labels_scipy_vs_numpy_and_canonical_order():
+    for seed in range(4):
+        prob = ppo.render_prob_map(96, 128, seed=seed, n_boxes=10)
+        fg = ppo.foreground(prob, 0.3)
+        a, na = ppo.label_components(fg)
+        b, nb = ppo.label_components_numpy(fg)
+        assert na == nb and np.array_equal(a, b)
+        firsts = [np.flatnonzero(a.ravel() == l)[0] for l in range(1, na + 1)]
+        assert firsts == sorted(firsts)
+
+
+def test_postproc_edge_cases():
+    z = np.zeros((32, 64), np.float32)
+    lab, n, recs = ppo.postprocess(z)
+    assert n == 0 and len(recs) == 0 and not lab.any()
+    full = np.full((32, 64), 0.9, np.float32)
+    lab, n, recs = ppo.postprocess(full, unclip_ratio=1.5)
+    assert n == 1 and len(recs) == 1 and recs[0]["npix"] == 32 * 64
+    d = (63 * 31 * 1.5) / (2 * (63 + 31))
+    assert recs[0]["x0"] == -int(d + 0.5) and recs[0]["x1"] == int(63 + d + 0.5)
+    # diagonal touch is one component (8-connectivity); a one-row run is dropped (zero-area contour)
+    m = np.zeros((16, 16), np.float32)
+    m[2:6, 2:6] = 0.9
+    m[6:10, 6:10] = 0.9
+    m[12, 1:15] = 0.9
+    lab, n, recs = ppo.postprocess(m, min_area=1)
+    assert n == 2 and len(recs) == 1 and (recs[0]["bx0"], recs[0]["by0"], recs[0]["bx1"], recs[0]["by1"]) == (2, 2, 9, 9)
+    # max_candidates caps the examined components (test.py:66-67)
+    dots = np.zeros((64, 64), np.float32)
+    dots[::4, ::4] = 0.0
+    for y in range(0, 64, 8):
+        for x in range(0, 64, 8):
+            dots[y:y + 5, x:x + 5] = 0.95
+    lab, n, recs = ppo.postprocess(dots, max_candidates=10, min_area=4)
+    assert n == 64 and len(recs) == 10 and recs[-1]["label"] == 10
+    # box_thresh: exact integer comparison
+    faint = np.zeros((16, 32), np.float32)
+    faint[4:10, 4:20] = 0.5
+    assert len(ppo.postprocess(faint, box_thresh=0.5, min_area=1)[2]) == 1
+    assert len(ppo.postprocess(faint, box_thresh=0.5000001, min_area=1)[2]) == 0
+
+
+def test_boxes_agree_with_cv2_half_of_reference():
+    """Reported agreement (not bit-exact): bounding rectangles vs the reference's cv2 contour path."""
+    p = np.load(GOLD / "postproc_cv2.npz")
+    rates = []
+    for i in range(3):
+        _, _, recs = ppo.postprocess(p[f"{i}.prob"], 0.3, 0.5, 1000, 1.6, 10)
+        ours = [(r["x0"], r["y0"], r["x1"], r["y1"]) for r in recs]
+        theirs = [tuple(int(v) for v in r) for r in p[f"{i}.cv2_rects"]]
+        rates.append(ppo.match_rate(ours, theirs, 0.8))
+        boxes, scores = ppo.records_to_boxes(recs)
+        assert all(b.shape == (4, 2) and b.dtype == np.int64 and b.flags.writeable for b in boxes)
+        assert all(0.5 <= s <= 1.0 for s in scores)
+    assert min(rates) >= 0.9, rates
