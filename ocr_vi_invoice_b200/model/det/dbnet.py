@@ -77,6 +77,15 @@ class DBNetPP(nn.Module):
             out = plan.run(x.float().contiguous(), want=MAP_NAMES)
             return out, {n: plan.tap(n) for n in plan.taps}
 
+    @torch.no_grad()
+    def time_launches(self, x, iters: int = 3):
+        """Per-kernel-launch device times of the plan for `x` (see Plan.time_launches)."""
+        self._check_input(x)
+        with torch.cuda.device(x.device):
+            plan = self._get_plan(x)
+            plan.x_in.copy_(x.float())
+            return plan.time_launches(iters)
+
     def plan_info(self, batch, height, width, device="cuda"):
         """(#launches, #tcgen05 GEMM launches, conv FLOPs) of the plan for an input shape."""
         x = torch.empty(batch, 3, height, width, device=device)

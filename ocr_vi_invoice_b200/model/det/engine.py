@@ -87,6 +87,8 @@ class Plan:
         self.taps: Dict[str, tuple] = {}  # name -> (NHWC tensor, channels)
         self.flops = 0.0
         self.n_igemm = 0
+        self.step_flops: Dict[str, float] = {}
+        self.step_kind: Dict[str, str] = {}
         b = batch
         bf = lambda *s: torch.empty(*s, device=dev, dtype=torch.bfloat16)
         P = W.P
@@ -99,6 +101,8 @@ class Plan:
                            out_ld=out_ld, name=name)
             self.steps.append(op)
             self.names.append(name)
+            self.step_flops[name] = op.flops
+            self.step_kind[name] = {ops.IGEMM_CONV: "conv", ops.IGEMM_STEM: "stem", ops.IGEMM_DCN: "dcn"}[mode]
             self.flops += op.flops
             self.n_igemm += 1
             return op
@@ -227,6 +231,26 @@ class Plan:
     def _launch_all(self):
         for s in self.steps:
             s()
+
+    def time_launches(self, iters: int = 3):
+        """Per-launch device time with CUDA events on the current stream (a separate, instrumented pass: the
+        events serialise nothing but add a little launch overhead, so use it for SHARES and per-kernel rates,
+        not for the step time).  Returns [(name, kind, mean ms, algorithmic flops)]."""
+        if self.maps is None:
+            self._alloc_maps()
+        n = len(self.steps)
+        acc = [0.0] * n
+        for _ in range(iters):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+            ev[0].record()
+            for i, s in enumerate(self.steps):
+                s()
+                ev[i + 1].record()
+            torch.cuda.synchronize()
+            for i in range(n):
+                acc[i] += ev[i].elapsed_time(ev[i + 1])
+        return [(nm, self.step_kind.get(nm, "elementwise"), acc[i] / iters, self.step_flops.get(nm, 0.0))
+                for i, nm in enumerate(self.names)]
 
     def tap(self, name: str) -> torch.Tensor:
         """NCHW fp32 copy of a recorded stage tensor (tests only)."""
