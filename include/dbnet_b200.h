@@ -48,9 +48,20 @@ enum {
     B200_EPI_RES        = 2,  /* v += residual[same pixel]               (Bottleneck identity)   */
     B200_EPI_RES_UP2    = 4,  /* v += residual[(y>>1, x>>1)]             (neck.py:36-38 nearest) */
     B200_EPI_OUT_F32    = 8,  /* store fp32 instead of bf16              (offset/mask conv)      */
-    B200_EPI_SHUFFLE2   = 16  /* N = 4*shuf_c, column (dy*2+dx)*shuf_c+co goes to pixel
+    B200_EPI_SHUFFLE2   = 16, /* N = 4*shuf_c, column (dy*2+dx)*shuf_c+co goes to pixel
                                  (2y+dy, 2x+dx), channel co               (ConvTranspose2d 2x2) */
+    B200_EPI_DCN_COORDS = 32  /* offset_mask_conv only (out_c = 32): instead of the raw 27 channels, store
+                                 the b200_dcn_coord records of the 9 taps, y = [pixel][9] records, so
+                                 the DCN producers do no coordinate arithmetic (dcn.py:44-46 fused)    */
 };
+
+/* Sampling record of one (output pixel, tap) of the modulated deformable conv: the four bilinear corners as
+ * element offsets into the image ((h*W + w)*x_ld, 0 when the corner is outside) and their weights already
+ * multiplied by sigmoid(mask) (0 when outside).  torchvision deform_conv2d semantics. */
+typedef struct b200_dcn_coord {
+    int32_t off[4];
+    float   wgt[4];
+} b200_dcn_coord;
 
 typedef struct b200_igemm_desc {
     int32_t mode;          /* B200_IGEMM_*                                                        */
@@ -66,7 +77,7 @@ typedef struct b200_igemm_desc {
     int32_t res_ld;        /* elements between consecutive residual pixels                        */
     int32_t shuf_c;        /* channels per sub-pixel for B200_EPI_SHUFFLE2                        */
     int32_t block_n;       /* 32, 64, 128 or 256; 0 = choose                                      */
-    int32_t reserved0;
+    int32_t x_ld;          /* elements between consecutive input pixels; 0 = in_c (dense NHWC)    */
     int32_t reserved1;
     const void*  x;        /* input activations, NHWC bf16                                        */
     const void*  w;        /* weights [n_pad][taps*in_c] bf16, K order (tap, cin)                 */
@@ -74,8 +85,8 @@ typedef struct b200_igemm_desc {
     const float* shift;    /* [n_pad] per-column addend (folded BN beta-mean*scale, or bias)      */
     const void*  residual; /* NHWC bf16 or NULL                                                   */
     void*        y;        /* output                                                              */
-    const float* offsets;  /* DCN: [batch*out_h*out_w][32] fp32 raw offset_mask_conv output:
-                              ch 2k = dy_k, 2k+1 = dx_k, 18+k = mask logit (dcn.py:44-46)         */
+    const void*  offsets;  /* DCN: b200_dcn_coord [batch*out_h*out_w][9], written by an offset conv with
+                              B200_EPI_DCN_COORDS or by b200_dcn_coords() from raw offsets        */
 } b200_igemm_desc;
 
 typedef struct b200_igemm b200_igemm; /* opaque: TMA descriptors + launch geometry */
@@ -86,6 +97,13 @@ int b200_igemm_destroy(b200_igemm* op);
 /* geometry a created op settled on (for tests / DESIGN tables) */
 int b200_igemm_info(const b200_igemm* op, int32_t* out_h, int32_t* out_w, int32_t* tile_w,
                     int32_t* tile_h, int32_t* block_n, int32_t* num_tiles, int32_t* smem_bytes);
+
+/* raw offset_mask_conv output [batch*out_h*out_w][32] fp32 (ch 2k = dy_k, 2k+1 = dx_k, 18+k = mask logit,
+ * dcn.py:44-46) -> b200_dcn_coord [pixel][9] for a 3x3, pad 1 DCN over an (in_h, in_w) image with x_ld
+ * elements per pixel.  (The engine fuses this into the offset conv's epilogue; this entry point serves callers
+ * that bring their own offsets.) */
+int b200_dcn_coords(const float* raw, void* coords, int batch, int in_h, int in_w, int x_ld, int stride,
+                    void* stream);
 
 /* ---- bandwidth-bound kernels ---------------------------------------------------------------- */
 /* fp32 NCHW (b,3,H,W) normalised image -> zero-padded space-to-depth bf16 buffer
@@ -103,13 +121,15 @@ int b200_asf_fwd(const void* p2, const void* p3, const void* p4, const void* p5,
                  int batch, int h2, int w2, int h3, int w3, int h4, int w4, int h5, int w5,
                  void* stream);
 /* DBHead tail (model/det/head.py:15,23,28-48): last ConvTranspose2d(64->1, 2x2 s2) of both branches,
- * sigmoid, differentiable-binarisation step.  t_bin/t_thr: NHWC bf16 (b, h, w, 64) (already
- * BN+ReLU'd); w2_* [64][4] fp32 (ci, dy*2+dx); maps: fp32 (b,1,2h,2w) each; any map may be NULL. */
+ * sigmoid, differentiable-binarisation step.  t_bin/t_thr: NHWC bf16, 64 channels each (already
+ * BN+ReLU'd), `ld` elements between consecutive pixels (64 for two dense tensors, 128 when both branches
+ * are interleaved in one tensor); w2_* [64][4] fp32 (ci, dy*2+dx); maps: fp32 (b,1,2h,2w) each; any map
+ * may be NULL. */
 int b200_db_head_fwd(const void* t_bin, const void* t_thr, const float* w2_bin, float b2_bin,
                      const float* w2_thr, float b2_thr, float k,
                      float* binary, float* thresh, float* thresh_binary,
                      float* bin_logits, float* thresh_logits,
-                     int batch, int h, int w, void* stream);
+                     int batch, int h, int w, int ld, void* stream);
 
 /* ---- post-processing (replaces DBPostProcessor.__call__, src/det/test.py:55-106) ------------
  * threshold (test.py:57) -> 8-connected component labelling (replaces cv2.findContours, test.py:60)
@@ -143,6 +163,7 @@ int b200_ref_conv2d(const void* x, const void* w, const float* scale, const floa
                     const void* residual, void* y, int batch, int in_h, int in_w, int in_c,
                     int out_c, int w_ld, int ksize, int stride, int flags, int out_ld, int res_ld,
                     int shuf_c, void* stream);
+/* offsets here are the RAW [pixel][32] fp32 offset_mask_conv output */
 int b200_ref_dcn2d(const void* x, const float* offsets, const void* w, const float* scale,
                    const float* shift, void* y, int batch, int in_h, int in_w, int in_c,
                    int out_c, int stride, int flags, int out_ld, void* stream);

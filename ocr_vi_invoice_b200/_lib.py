@@ -13,7 +13,7 @@ from pathlib import Path
 _LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libdbnet_b200.so"
 
 IGEMM_CONV, IGEMM_STEM, IGEMM_DCN = 0, 1, 2
-EPI_RELU, EPI_RES, EPI_RES_UP2, EPI_OUT_F32, EPI_SHUFFLE2 = 1, 2, 4, 8, 16
+EPI_RELU, EPI_RES, EPI_RES_UP2, EPI_OUT_F32, EPI_SHUFFLE2, EPI_DCN_COORDS = 1, 2, 4, 8, 16, 32
 
 
 class B200Error(RuntimeError):
@@ -25,7 +25,7 @@ class IgemmDesc(C.Structure):
         ("mode", C.c_int32), ("batch", C.c_int32), ("in_h", C.c_int32), ("in_w", C.c_int32),
         ("in_c", C.c_int32), ("out_c", C.c_int32), ("n_pad", C.c_int32), ("ksize", C.c_int32),
         ("stride", C.c_int32), ("flags", C.c_int32), ("out_ld", C.c_int32), ("res_ld", C.c_int32),
-        ("shuf_c", C.c_int32), ("block_n", C.c_int32), ("reserved0", C.c_int32), ("reserved1", C.c_int32),
+        ("shuf_c", C.c_int32), ("block_n", C.c_int32), ("x_ld", C.c_int32), ("reserved1", C.c_int32),
         ("x", C.c_void_p), ("w", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
         ("residual", C.c_void_p), ("y", C.c_void_p), ("offsets", C.c_void_p),
     ]
@@ -52,7 +52,8 @@ SYMBOLS = {
     "b200_stem_pack": (_i, [_p, _p, _i, _i, _i, _p]),
     "b200_maxpool3x3s2": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "b200_asf_fwd": (_i, [_p] * 7 + [_i] * 9 + [_p]),
-    "b200_db_head_fwd": (_i, [_p, _p, _p, _f, _p, _f, _f, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "b200_db_head_fwd": (_i, [_p, _p, _p, _f, _p, _f, _f, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "b200_dcn_coords": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "b200_postproc_workspace_bytes": (_i64, [_i, _i, _i, _i]),
     "b200_postproc": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _d, _d, _d, _i, _i, _p]),
     "b200_ref_conv2d": (_i, [_p] * 6 + [_i] * 12 + [_p]),

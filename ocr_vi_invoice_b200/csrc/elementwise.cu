@@ -193,7 +193,7 @@ struct HeadParams {
     float* thresh_binary;
     float* bin_logits;
     float* thresh_logits;
-    int batch, h, w;
+    int batch, h, w, ld;
 };
 
 constexpr int kHeadPix = 128;       // pixels (threads) per block
@@ -216,8 +216,8 @@ __global__ void __launch_bounds__(kHeadPix) db_head_kernel(const HeadParams p) {
     for (int t = threadIdx.x; t < kHeadPix * 8; t += kHeadPix) {
         const int px = t >> 3, ch = t & 7;
         if (px < npx) {
-            *reinterpret_cast<uint4*>(&sb[0][px * kHeadRowBytes + ch * 16]) = ldg128(p.t_bin + (pix0 + px) * 64 + ch * 8);
-            *reinterpret_cast<uint4*>(&sb[1][px * kHeadRowBytes + ch * 16]) = ldg128(p.t_thr + (pix0 + px) * 64 + ch * 8);
+            *reinterpret_cast<uint4*>(&sb[0][px * kHeadRowBytes + ch * 16]) = ldg128(p.t_bin + (pix0 + px) * p.ld + ch * 8);
+            *reinterpret_cast<uint4*>(&sb[1][px * kHeadRowBytes + ch * 16]) = ldg128(p.t_thr + (pix0 + px) * p.ld + ch * 8);
         }
     }
     __syncthreads();
@@ -309,16 +309,16 @@ extern "C" int b200_asf_fwd(const void* p2, const void* p3, const void* p4, cons
 extern "C" int b200_db_head_fwd(const void* t_bin, const void* t_thr, const float* w2_bin, float b2_bin,
                                 const float* w2_thr, float b2_thr, float k, float* binary, float* thresh,
                                 float* thresh_binary, float* bin_logits, float* thresh_logits, int batch, int h, int w,
-                                void* stream) {
+                                int ld, void* stream) {
     if (!t_bin || !t_thr || !w2_bin || !w2_thr) return set_error("b200_db_head_fwd: null pointer");
-    if (batch <= 0 || h <= 0 || w <= 0) return set_error("b200_db_head_fwd: bad shape");
+    if (batch <= 0 || h <= 0 || w <= 0 || ld < 64 || (ld % 8)) return set_error("b200_db_head_fwd: bad shape");
     HeadParams p;
     p.t_bin = reinterpret_cast<const __nv_bfloat16*>(t_bin);
     p.t_thr = reinterpret_cast<const __nv_bfloat16*>(t_thr);
     p.w2_bin = w2_bin; p.w2_thr = w2_thr; p.b2_bin = b2_bin; p.b2_thr = b2_thr; p.k = k;
     p.binary = binary; p.thresh = thresh; p.thresh_binary = thresh_binary;
     p.bin_logits = bin_logits; p.thresh_logits = thresh_logits;
-    p.batch = batch; p.h = h; p.w = w;
+    p.batch = batch; p.h = h; p.w = w; p.ld = ld;
     const int64_t total = static_cast<int64_t>(batch) * h * w;
     const int64_t blocks = (total + kHeadPix - 1) / kHeadPix;
     if (blocks > 0x7fffffff) return set_error("b200_db_head_fwd: too many pixels");

@@ -2,12 +2,16 @@
 // warp-specialised persistent CTAs.  One kernel template covers
 //   * plain 1x1 / 3x3 convolutions, stride 1 or 2 (A operand = NHWC activations loaded by TMA boxes,
 //     one box per (tap, 64-channel slice); zero padding comes from TMA out-of-bounds fill),
-//   * the modulated deformable conv v2 (A operand gathered by producer warps: 4-corner bilinear blend,
-//     mask modulation, bf16 pack, written straight into the 128B-swizzled UMMA layout),
+//   * the modulated deformable conv v2 (A operand gathered by 16 producer warps from pre-computed
+//     b200_dcn_coord records: 4-corner bilinear blend with mask-modulated weights, bf16 pack, written
+//     straight into the 128B-swizzled UMMA layout; loads software-pipelined one unit ahead),
 //   * the 7x7 s2 stem on a space-to-depth buffer (A rows are contiguous 128 B runs, copied by the
 //     producer warps),
-// all with a fused epilogue (folded BN scale/shift or bias, residual add, ReLU, bf16 / fp32 store,
-// 2x2 pixel-shuffle store for ConvTranspose2d 2x2 s2).
+// all with a fused epilogue (folded BN scale/shift or bias, residual add, ReLU) that either
+//   * stages bf16 64-channel chunks in swizzled shared memory and writes them with TMA stores
+//     (pixel-shuffle for ConvTranspose2d 2x2 = four parity views of the output), the residual being
+//     prefetched by TMA loads two chunks ahead, or
+//   * stores directly from registers (fp32 outputs, DCN coordinate records, nearest-upsampled residual).
 //
 // GEMM view:  D[M = output pixels of one 128-pixel tile][N = out channels] =
 //             A[M][K = taps * Cin] * B[N][K]^T,   K ordered (tap, cin),  BLOCK_K = 64 (one SW128 atom).
@@ -24,11 +28,16 @@ namespace b200 {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
-constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB per stage
-constexpr int kGatherWarps = 8;                 // producer warps of the gather (DCN / stem) variant
-constexpr int kBaseWarps = 6;                   // TMA, MMA, 4 epilogue
+constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB per stage (= one 128 x 64 bf16 chunk)
+constexpr int kGatherWarps = 16;                // producer warps of the gather (DCN / stem) variant
 constexpr int kMaxStages = 8;
 constexpr int kMaxSmem = 227 * 1024;
+constexpr int kEpiThreads = 128;                // one epilogue group = 4 warps = the 4 TMEM lane quarters
+constexpr int kMaxResBufs = 8;
+// The TMA-fed conv kernel runs two epilogue groups (alternating 64-column chunks): its 1x1 layers are
+// epilogue-latency-bound with one warp per scheduler.  The gather kernel keeps one group (threads go to producers).
+__host__ __device__ constexpr int epi_groups(bool gather) { return gather ? 1 : 2; }
+__host__ __device__ constexpr int base_warps(bool gather) { return 2 + 4 * epi_groups(gather); }
 
 struct IgemmParams {
     int mode, batch, in_h, in_w, in_c, out_h, out_w, out_c;
@@ -36,40 +45,60 @@ struct IgemmParams {
     int tile_w, tile_h, tiles_x, tiles_y;
     int num_n_blocks, num_tiles, k_blocks, cchunks;
     int out_ld, res_ld, shuf_c, stages;
-    int pk_h, pk_w;  // STEM: rows / columns of the packed space-to-depth buffer
+    int pk_h, pk_w;        // STEM: rows / columns of the packed space-to-depth buffer
+    int x_ld;              // elements between consecutive input pixels
+    int epi_tma, res_tma;  // epilogue stores through TMA / residual prefetched through TMA
+    int epi_active;        // epilogue groups that take chunks (1 for compute-bound layers: frees staging smem)
+    int stg_bufs;          // output staging buffers per active group (2 when a single group must overlap its stores)
+    int res_bufs;          // residual ring depth per epilogue group
+    int res_bytes;         // bytes of one residual box (16 KB, or 4 KB for the half-resolution RES_UP2 box)
     const __nv_bfloat16* x;
     const float* scale;
     const float* shift;
     const __nv_bfloat16* residual;
     void* y;
-    const float* offsets;
+    const void* offsets;
 };
 
 struct TmapPack {
     CUtensorMap a[4];
     CUtensorMap b;
+    CUtensorMap out[4];
+    CUtensorMap res;
 };
 
 struct SmemLayout {
     uint8_t* a;
     uint8_t* b;
+    uint8_t* stg;  // one 16 KB output staging buffer per epilogue group
+    uint8_t* rsd;  // groups x res_bufs residual boxes (16 KB stride)
+    float* ss;     // per group: scale[256] then shift[256] of the current n-block
     uint64_t* full;
     uint64_t* empty;
     uint64_t* tfull;
     uint64_t* tempty;
+    uint64_t* resfull;  // [group][kMaxResBufs]
     uint32_t* tmem_slot;
 };
 
-__device__ __forceinline__ SmemLayout carve(uint8_t* raw, int stages, int b_bytes) {
+template <bool kGather>
+__device__ __forceinline__ SmemLayout carve(uint8_t* raw, const IgemmParams& p) {
+    constexpr int G = epi_groups(kGather);
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
     SmemLayout s;
     s.a = base;
-    s.b = base + stages * kABytes;
-    s.full = reinterpret_cast<uint64_t*>(s.b + stages * b_bytes);
+    s.b = s.a + p.stages * kABytes;
+    s.stg = s.b + p.stages * p.block_n * 128;
+    s.rsd = s.stg + (p.epi_tma ? p.epi_active * p.stg_bufs * kABytes : 0);
+    uint8_t* rest = s.rsd + (p.res_tma ? p.epi_active * p.res_bufs * kABytes : 0);
+    s.ss = reinterpret_cast<float*>(rest);
+    uint8_t* bars = rest + G * 2048;
+    s.full = reinterpret_cast<uint64_t*>(bars);
     s.empty = s.full + kMaxStages;
     s.tfull = s.empty + kMaxStages;
     s.tempty = s.tfull + 2;
-    s.tmem_slot = reinterpret_cast<uint32_t*>(s.tempty + 2);
+    s.resfull = s.tempty + 2;
+    s.tmem_slot = reinterpret_cast<uint32_t*>(s.resfull + 2 * kMaxResBufs);
     return s;
 }
 
@@ -88,11 +117,69 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile)
     t.x0 = (m - ty * p.tiles_x) * p.tile_w;
     return t;
 }
+// 64-column chunks the TMA-store epilogue writes for n-block nb
+__device__ __forceinline__ int chunks_of(const IgemmParams& p, int nb) {
+    return min(p.block_n, p.out_c - nb * p.block_n) >> 6;
+}
 
-// ------------------------------------------------------------------------------------------ epilogue
+// ------------------------------------------------------------------------------------------ DCN coordinates
+// torchvision deform_conv2d sampling of tap k at output pixel (oy, ox): see include/dbnet_b200.h b200_dcn_coord.
+__device__ __forceinline__ void dcn_make_coord(float dy, float dx, float mlogit, int oy, int ox, int tap, int stride,
+                                               int in_h, int in_w, int x_ld, int (&off)[4], float (&wgt)[4]) {
+    const int ky = tap / 3, kx = tap - ky * 3;
+    const float m = 1.0f / (1.0f + expf(-mlogit));
+    const float h = static_cast<float>(oy * stride - 1 + ky) + dy;
+    const float w = static_cast<float>(ox * stride - 1 + kx) + dx;
+    off[0] = off[1] = off[2] = off[3] = 0;
+    wgt[0] = wgt[1] = wgt[2] = wgt[3] = 0.0f;
+    if (h > -1.0f && w > -1.0f && h < static_cast<float>(in_h) && w < static_cast<float>(in_w)) {
+        const float hf = floorf(h), wf = floorf(w);
+        const int hl = static_cast<int>(hf), wl = static_cast<int>(wf);
+        const int hh = hl + 1, wh = wl + 1;
+        const float lh = h - hf, lw = w - wf;
+        const float uh = 1.0f - lh, uw = 1.0f - lw;
+        const bool t_ok = hl >= 0, b_ok = hh <= in_h - 1, l_ok = wl >= 0, r_ok = wh <= in_w - 1;
+        if (t_ok && l_ok) { off[0] = (hl * in_w + wl) * x_ld; wgt[0] = m * (uh * uw); }
+        if (t_ok && r_ok) { off[1] = (hl * in_w + wh) * x_ld; wgt[1] = m * (uh * lw); }
+        if (b_ok && l_ok) { off[2] = (hh * in_w + wl) * x_ld; wgt[2] = m * (lh * uw); }
+        if (b_ok && r_ok) { off[3] = (hh * in_w + wh) * x_ld; wgt[3] = m * (lh * lw); }
+    }
+}
+
+__device__ __forceinline__ void dcn_store_coords(uint4* dst, const float (&f)[32], int oy, int ox, int stride, int in_h,
+                                                 int in_w, int x_ld) {
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        int off[4];
+        float wgt[4];
+        dcn_make_coord(f[2 * tap], f[2 * tap + 1], f[18 + tap], oy, ox, tap, stride, in_h, in_w, x_ld, off, wgt);
+        dst[2 * tap] = make_uint4(off[0], off[1], off[2], off[3]);
+        dst[2 * tap + 1] = make_uint4(__float_as_uint(wgt[0]), __float_as_uint(wgt[1]), __float_as_uint(wgt[2]),
+                                      __float_as_uint(wgt[3]));
+    }
+}
+
+__global__ void dcn_coords_kernel(const float* __restrict__ raw, uint4* __restrict__ coords, int batch, int out_h,
+                                  int out_w, int in_h, int in_w, int x_ld, int stride) {
+    const int64_t total = static_cast<int64_t>(batch) * out_h * out_w;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int ox = static_cast<int>(i % out_w);
+        const int oy = static_cast<int>((i / out_w) % out_h);
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(raw + i * 32 + j));
+            f[j] = v.x; f[j + 1] = v.y; f[j + 2] = v.z; f[j + 3] = v.w;
+        }
+        dcn_store_coords(coords + i * 18, f, oy, ox, stride, in_h, in_w, x_ld);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ direct epilogue
 // v[32] = fp32 accumulators of one pixel (TMEM lane) for 32 consecutive GEMM columns starting at col0.
-__device__ __forceinline__ void epilogue_chunk(const IgemmParams& p, const uint32_t (&v)[32], int col0, int n, int oy,
-                                               int ox) {
+__device__ __forceinline__ void epilogue_direct32(const IgemmParams& p, const uint32_t (&v)[32], int col0, int n, int oy,
+                                                  int ox) {
     if (col0 >= p.out_c) return;
     float f[32];
 #pragma unroll
@@ -103,6 +190,11 @@ __device__ __forceinline__ void epilogue_chunk(const IgemmParams& p, const uint3
         f[i + 1] = fmaf(__uint_as_float(v[i + 1]), sc.y, sh.y);
         f[i + 2] = fmaf(__uint_as_float(v[i + 2]), sc.z, sh.z);
         f[i + 3] = fmaf(__uint_as_float(v[i + 3]), sc.w, sh.w);
+    }
+    if (p.flags & B200_EPI_DCN_COORDS) {
+        const int64_t opix = (static_cast<int64_t>(n) * p.out_h + oy) * p.out_w + ox;
+        dcn_store_coords(reinterpret_cast<uint4*>(p.y) + opix * 18, f, oy, ox, p.stride, p.in_h, p.in_w, p.x_ld);
+        return;
     }
     const int ncols = min(32, p.out_c - col0);  // multiple of 8
     int64_t opix;
@@ -159,13 +251,15 @@ __device__ __forceinline__ void epilogue_chunk(const IgemmParams& p, const uint3
 
 // ------------------------------------------------------------------------------------------ kernel
 template <bool kGather>
-__global__ void __launch_bounds__((kBaseWarps + (kGather ? kGatherWarps : 0)) * 32, 1)
+__global__ void __launch_bounds__((base_warps(kGather) + (kGather ? kGatherWarps : 0)) * 32, 1)
 igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
     extern __shared__ uint8_t smem_raw[];
+    constexpr int kBaseWarps = base_warps(kGather);
+    constexpr int G = epi_groups(kGather);
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int b_bytes = p.block_n * 128;
-    const SmemLayout sm = carve(smem_raw, p.stages, b_bytes);
+    const SmemLayout sm = carve<kGather>(smem_raw, p);
     const int stages = p.stages;
     const uint32_t tmem_cols = (2 * p.block_n < 32) ? 32u : static_cast<uint32_t>(2 * p.block_n);
 
@@ -179,6 +273,8 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                 tma_prefetch_desc(&tm.a[3]);
             }
         }
+        if (p.epi_tma) tma_prefetch_desc(&tm.out[0]);
+        if (p.res_tma) tma_prefetch_desc(&tm.res);
     }
     if (warp == 1) {
         if (lane == 0) {
@@ -188,8 +284,9 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
             }
             for (int a = 0; a < 2; ++a) {
                 mbar_init(&sm.tfull[a], 1);
-                mbar_init(&sm.tempty[a], 4);
+                mbar_init(&sm.tempty[a], 4 * G);
             }
+            for (int a = 0; a < 2 * kMaxResBufs; ++a) mbar_init(&sm.resfull[a], 1);
             fence_mbar_init();
         }
         __syncwarp();
@@ -265,12 +362,48 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
             }
         }
     } else if (warp < kBaseWarps) {
-        // ===================================================================== epilogue (4 warps)
-        const int quarter = warp & 3;  // TMEM lane quarter this warp may touch
+        // ===================================================================== epilogue (G groups of 4 warps)
+        const int eg = (warp - 2) >> 2;  // epilogue group
+        const int quarter = warp & 3;    // TMEM lane quarter this warp may touch
         const int row = quarter * 32 + lane;
+        const int et = ((warp - 2) & 3) * 32 + lane;  // thread index inside the group
         const int ty = row / p.tile_w;
         const int tx = row - ty * p.tile_w;
+        const bool issuer = (et == 0);
+        const uint32_t swz = static_cast<uint32_t>(row & 7);
+        const int GA = p.epi_active;  // groups that take work; the others only keep the TMEM hand-shake going
+        uint8_t* const rsd_base = sm.rsd + eg * p.res_bufs * kABytes;
+        uint64_t* const resfull = sm.resfull + eg * kMaxResBufs;
+        float* const ss = sm.ss + eg * 512;
+        // residual row this thread reads: its own pixel, or (y>>1, x>>1) of the half-resolution RES_UP2 box
+        const bool up2 = (p.flags & B200_EPI_RES_UP2) != 0;
+        const int rrow = up2 ? ((ty >> 1) * (p.tile_w >> 1) + (tx >> 1)) : row;
+        const uint32_t rswz = static_cast<uint32_t>(rrow & 7);
+        // residual prefetch cursor (issuer only): walks this group's (tile, chunk) sequence res_bufs chunks ahead
+        int pf_tile = blockIdx.x, pf_chunk = 0, pf_g = 0, pf_count = 0;
+        auto issue_res = [&]() {
+            while (pf_tile < p.num_tiles) {
+                const TileCoord t = decode_tile(p, pf_tile);
+                const bool mine = (pf_g % GA) == eg;
+                const int c = pf_chunk;
+                ++pf_g;
+                if (++pf_chunk == chunks_of(p, t.nb)) { pf_chunk = 0; pf_tile += gridDim.x; }
+                if (mine) {
+                    const int slot = pf_count % p.res_bufs;
+                    mbar_arrive_expect_tx(&resfull[slot], p.res_bytes);
+                    tma_load_4d(rsd_base + slot * kABytes, &tm.res, &resfull[slot], t.nb * p.block_n + c * 64,
+                                up2 ? (t.x0 >> 1) : t.x0, up2 ? (t.y0 >> 1) : t.y0, t.n);
+                    ++pf_count;
+                    return;
+                }
+            }
+        };
+        if (p.res_tma && issuer && eg < GA)
+            for (int i = 0; i < p.res_bufs; ++i) issue_res();
         int it = 0;
+        int g = 0;       // global 64-column chunk counter of this CTA (all groups count the same sequence)
+        int mine_k = 0;  // chunks this group has processed (residual ring position)
+        int ss_nb = -1;  // n-block whose scale/shift currently sit in smem
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const TileCoord t = decode_tile(p, tile);
             const int as = it & 1;
@@ -281,20 +414,133 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                    static_cast<uint32_t>(as * p.block_n);
-            for (int c = 0; c < p.block_n; c += 32) {
-                uint32_t v[32];
-                tmem_ld32(taddr + c, v);
-                tmem_ld_wait();
-                if (valid) epilogue_chunk(p, v, t.nb * p.block_n + c, t.n, oy, ox);
+            if (!p.epi_tma) {
+                if ((it % G) == eg) {  // direct stores: the groups take alternate tiles
+                    for (int c = 0; c < p.block_n; c += 32) {
+                        uint32_t v[32];
+                        tmem_ld32(taddr + c, v);
+                        tmem_ld_wait();
+                        if (valid) epilogue_direct32(p, v, t.nb * p.block_n + c, t.n, oy, ox);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.tempty[as]);
+                continue;
             }
+            if (eg >= GA) {  // idle group of a compute-bound layer
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.tempty[as]);
+                continue;
+            }
+            const int nchunks = chunks_of(p, t.nb);
+            if (ss_nb != t.nb) {  // (re)load this n-block's scale / shift into the group's smem copy
+                named_bar_sync(1 + eg, kEpiThreads);  // nobody still reads the old copy
+                for (int i = et; i < p.block_n; i += kEpiThreads) {
+                    ss[i] = __ldg(p.scale + t.nb * p.block_n + i);
+                    ss[256 + i] = __ldg(p.shift + t.nb * p.block_n + i);
+                }
+                named_bar_sync(1 + eg, kEpiThreads);
+                ss_nb = t.nb;
+            }
+            for (int c = 0; c < nchunks; ++c, ++g) {
+                if ((g % GA) != eg) continue;
+                const int col0 = t.nb * p.block_n + c * 64;
+                const int slot = mine_k % p.res_bufs;
+                uint8_t* const stg_buf = sm.stg + (eg * p.stg_bufs + (p.stg_bufs == 2 ? (mine_k & 1) : 0)) * kABytes;
+                uint8_t* const stg = stg_buf + row * 128;
+                const uint8_t* rsd = rsd_base + slot * kABytes + rrow * 128;
+                // pieces [p0, p0+np) of the chunk: scale/shift (+ residual) (+ ReLU) -> packed bf16, 8 columns per piece
+                auto compute = [&](const uint32_t* vv, int p0, int np, uint4* oo) {
+#pragma unroll
+                    for (int j = 0; j < np; ++j) {
+                        const int piece = p0 + j;
+                        float f[8];
+                        const float4 sc0 = *reinterpret_cast<const float4*>(ss + c * 64 + piece * 8);
+                        const float4 sc1 = *reinterpret_cast<const float4*>(ss + c * 64 + piece * 8 + 4);
+                        const float4 sh0 = *reinterpret_cast<const float4*>(ss + 256 + c * 64 + piece * 8);
+                        const float4 sh1 = *reinterpret_cast<const float4*>(ss + 256 + c * 64 + piece * 8 + 4);
+                        f[0] = fmaf(__uint_as_float(vv[j * 8 + 0]), sc0.x, sh0.x);
+                        f[1] = fmaf(__uint_as_float(vv[j * 8 + 1]), sc0.y, sh0.y);
+                        f[2] = fmaf(__uint_as_float(vv[j * 8 + 2]), sc0.z, sh0.z);
+                        f[3] = fmaf(__uint_as_float(vv[j * 8 + 3]), sc0.w, sh0.w);
+                        f[4] = fmaf(__uint_as_float(vv[j * 8 + 4]), sc1.x, sh1.x);
+                        f[5] = fmaf(__uint_as_float(vv[j * 8 + 5]), sc1.y, sh1.y);
+                        f[6] = fmaf(__uint_as_float(vv[j * 8 + 6]), sc1.z, sh1.z);
+                        f[7] = fmaf(__uint_as_float(vv[j * 8 + 7]), sc1.w, sh1.w);
+                        if (p.res_tma) {
+                            const uint4 u =
+                                *reinterpret_cast<const uint4*>(rsd + ((static_cast<uint32_t>(piece) ^ rswz) << 4));
+                            f[0] += bf16lo(u.x); f[1] += bf16hi(u.x);
+                            f[2] += bf16lo(u.y); f[3] += bf16hi(u.y);
+                            f[4] += bf16lo(u.z); f[5] += bf16hi(u.z);
+                            f[6] += bf16lo(u.w); f[7] += bf16hi(u.w);
+                        }
+                        if (p.flags & B200_EPI_RELU) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.0f);
+                        }
+                        oo[j].x = pack_bf16(f[0], f[1]);
+                        oo[j].y = pack_bf16(f[2], f[3]);
+                        oo[j].z = pack_bf16(f[4], f[5]);
+                        oo[j].w = pack_bf16(f[6], f[7]);
+                    }
+                };
+                if constexpr (!kGather) {
+                    uint32_t v[64];
+                    tmem_ld32(taddr + c * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+                    tmem_ld32(taddr + c * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+                    if (p.res_tma) mbar_wait(&resfull[slot], (mine_k / p.res_bufs) & 1);
+                    tmem_ld_wait();
+                    uint4 o[8];
+                    compute(v, 0, 8, o);
+                    // the staging buffer is free once the TMA store that last used it has read it
+                    if (issuer) { if (p.stg_bufs == 2) bulk_wait_read1(); else bulk_wait_read0(); }
+                    named_bar_sync(1 + eg, kEpiThreads);
+#pragma unroll
+                    for (int piece = 0; piece < 8; ++piece)
+                        *reinterpret_cast<uint4*>(stg + ((static_cast<uint32_t>(piece) ^ swz) << 4)) = o[piece];
+                } else {
+                    // register-lean variant (the gather kernel runs 22 warps): two 32-column halves
+                    if (issuer) { if (p.stg_bufs == 2) bulk_wait_read1(); else bulk_wait_read0(); }
+                    named_bar_sync(1 + eg, kEpiThreads);
+                    if (p.res_tma) mbar_wait(&resfull[slot], (mine_k / p.res_bufs) & 1);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t v[32];
+                        tmem_ld32(taddr + c * 64 + h * 32, v);
+                        tmem_ld_wait();
+                        uint4 o[4];
+                        compute(v, h * 4, 4, o);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<uint4*>(stg + ((static_cast<uint32_t>(h * 4 + j) ^ swz) << 4)) = o[j];
+                    }
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(1 + eg, kEpiThreads);
+                if (issuer) {
+                    if (p.flags & B200_EPI_SHUFFLE2) {
+                        const int sub = col0 / p.shuf_c;
+                        tma_store_4d(&tm.out[sub], stg_buf, col0 - sub * p.shuf_c, t.x0, t.y0, t.n);
+                    } else {
+                        tma_store_4d(&tm.out[0], stg_buf, col0, t.x0, t.y0, t.n);
+                    }
+                    bulk_commit();
+                    if (p.res_tma) issue_res();  // every thread is past the barrier: residual slot `slot` is free
+                }
+                ++mine_k;
+            }
+            // accumulator fully read by this warp: hand the TMEM buffer back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.tempty[as]);
         }
+        if (p.epi_tma && issuer) bulk_wait_all();
     } else if (kGather) {
-        // ===================================================================== gather producers
-        constexpr int kRowsPerWarp = kBlockM / kGatherWarps;  // 16
-        constexpr int kPasses = kRowsPerWarp / 4;             // 4 rows per pass (8 lanes x 16 B = one row)
+        // ===================================================================== gather producers (16 warps)
+        constexpr int kPasses = kBlockM / (kGatherWarps * 4);  // 2: a pass = 64 rows, 8 lanes x 16 B per row
         const int pw = warp - kBaseWarps;
         const int sub = lane >> 3;
         const int l8 = lane & 7;
@@ -307,7 +553,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
             uint32_t soff[kPasses];
 #pragma unroll
             for (int q = 0; q < kPasses; ++q) {
-                const int r = pw * kRowsPerWarp + q * 4 + sub;
+                const int r = q * 64 + pw * 4 + sub;
                 const int ty = r / p.tile_w;
                 oy[q] = t.y0 + ty;
                 ox[q] = t.x0 + (r - ty * p.tile_w);
@@ -335,70 +581,65 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                     if (++s == stages) { s = 0; ph ^= 1; }
                 }
             } else {
-                // modulated deformable sampling (torchvision deform_conv2d semantics, model/det/dcn.py:48-57)
-                const __nv_bfloat16* img = p.x + static_cast<int64_t>(t.n) * p.in_h * p.in_w * p.in_c + l8 * 8;
-                const float* offp[kPasses];
+                // modulated deformable sampling from b200_dcn_coord records.  Unit = (k-block, pass); the corner
+                // loads of unit u+1 and the record of unit u+2 are in flight while unit u is blended.
+                const __nv_bfloat16* img = p.x + static_cast<int64_t>(t.n) * p.in_h * p.in_w * p.x_ld + l8 * 8;
+                const uint4* rec[kPasses];
+                float vmul[kPasses];
 #pragma unroll
-                for (int q = 0; q < kPasses; ++q)
-                    offp[q] = p.offsets + ((static_cast<int64_t>(t.n) * p.out_h + oy[q]) * p.out_w + ox[q]) * 32;
-                for (int tap = 0; tap < 9; ++tap) {
-                    const int ky = tap / 3, kx = tap - ky * 3;
-                    int o1[kPasses], o2[kPasses], o3[kPasses], o4[kPasses];
-                    float w1[kPasses], w2[kPasses], w3[kPasses], w4[kPasses];
-#pragma unroll
-                    for (int q = 0; q < kPasses; ++q) {
-                        o1[q] = o2[q] = o3[q] = o4[q] = 0;
-                        w1[q] = w2[q] = w3[q] = w4[q] = 0.0f;
-                        if (valid[q]) {
-                            const float dy = __ldg(offp[q] + 2 * tap);
-                            const float dx = __ldg(offp[q] + 2 * tap + 1);
-                            const float ml = __ldg(offp[q] + 18 + tap);
-                            const float m = 1.0f / (1.0f + expf(-ml));
-                            const float h = static_cast<float>(oy[q] * p.stride - 1 + ky) + dy;
-                            const float w = static_cast<float>(ox[q] * p.stride - 1 + kx) + dx;
-                            if (h > -1.0f && w > -1.0f && h < static_cast<float>(p.in_h) &&
-                                w < static_cast<float>(p.in_w)) {
-                                const float hf = floorf(h), wf = floorf(w);
-                                const int hl = static_cast<int>(hf), wl = static_cast<int>(wf);
-                                const int hh = hl + 1, wh = wl + 1;
-                                const float lh = h - hf, lw = w - wf;
-                                const float uh = 1.0f - lh, uw = 1.0f - lw;
-                                const bool t_ok = hl >= 0, b_ok = hh <= p.in_h - 1;
-                                const bool l_ok = wl >= 0, r_ok = wh <= p.in_w - 1;
-                                if (t_ok && l_ok) { o1[q] = (hl * p.in_w + wl) * p.in_c; w1[q] = m * (uh * uw); }
-                                if (t_ok && r_ok) { o2[q] = (hl * p.in_w + wh) * p.in_c; w2[q] = m * (uh * lw); }
-                                if (b_ok && l_ok) { o3[q] = (hh * p.in_w + wl) * p.in_c; w3[q] = m * (lh * uw); }
-                                if (b_ok && r_ok) { o4[q] = (hh * p.in_w + wh) * p.in_c; w4[q] = m * (lh * lw); }
-                            }
-                        }
-                    }
-                    for (int cc = 0; cc < p.cchunks; ++cc) {
-                        const __nv_bfloat16* src = img + cc * kBlockK;
-                        uint4 res[kPasses];
-#pragma unroll
-                        for (int q = 0; q < kPasses; ++q) {
-                            const uint4 a = ldg128(src + o1[q]);
-                            const uint4 b = ldg128(src + o2[q]);
-                            const uint4 c = ldg128(src + o3[q]);
-                            const uint4 d = ldg128(src + o4[q]);
-                            const float A = w1[q], B = w2[q], C = w3[q], D = w4[q];
-#define B200_BLEND(f) pack_bf16(A * bf16lo(a.f) + B * bf16lo(b.f) + C * bf16lo(c.f) + D * bf16lo(d.f), \
-                                A * bf16hi(a.f) + B * bf16hi(b.f) + C * bf16hi(c.f) + D * bf16hi(d.f))
-                            res[q].x = B200_BLEND(x);
-                            res[q].y = B200_BLEND(y);
-                            res[q].z = B200_BLEND(z);
-                            res[q].w = B200_BLEND(w);
+                for (int q = 0; q < kPasses; ++q) {
+                    const int64_t pix = valid[q] ? (static_cast<int64_t>(t.n) * p.out_h + oy[q]) * p.out_w + ox[q] : 0;
+                    rec[q] = reinterpret_cast<const uint4*>(p.offsets) + pix * 18;
+                    vmul[q] = valid[q] ? 1.0f : 0.0f;
+                }
+                const int units = p.k_blocks * kPasses;
+                // K is ordered (64-channel chunk, tap): the 9 taps x 4 corners of one chunk re-touch the same
+                // neighbourhood back to back, so they hit in L1 (the kernel keeps its smem carve-out small).
+                auto load_rec = [&](int u, uint4& ro, uint4& rw) {
+                    const int kb = u / kPasses, q = u - kb * kPasses;
+                    const int tap = kb % 9;
+                    ro = ldg128(rec[q] + 2 * tap);
+                    rw = ldg128(rec[q] + 2 * tap + 1);
+                };
+                auto load_corners = [&](int u, const uint4& ro, uint4 (&d)[4]) {
+                    const int kb = u / kPasses;
+                    const __nv_bfloat16* src = img + (kb / 9) * kBlockK;
+                    d[0] = ldg128(src + static_cast<int>(ro.x));
+                    d[1] = ldg128(src + static_cast<int>(ro.y));
+                    d[2] = ldg128(src + static_cast<int>(ro.z));
+                    d[3] = ldg128(src + static_cast<int>(ro.w));
+                };
+                uint4 ro0, rw0, ro1, rw1, ro2, rw2;
+                uint4 d0[4], d1[4];
+                load_rec(0, ro0, rw0);
+                load_rec(1, ro1, rw1);  // units >= 2 always (k_blocks >= 9)
+                load_corners(0, ro0, d0);
+                for (int u = 0; u < units; ++u) {
+                    const int q = u & (kPasses - 1);
+                    if (u + 2 < units) load_rec(u + 2, ro2, rw2);
+                    if (u + 1 < units) load_corners(u + 1, ro1, d1);
+                    const float vm = (q == 0) ? vmul[0] : vmul[1];
+                    const float A = __uint_as_float(rw0.x) * vm, B = __uint_as_float(rw0.y) * vm;
+                    const float C = __uint_as_float(rw0.z) * vm, D = __uint_as_float(rw0.w) * vm;
+                    uint4 res;
+#define B200_BLEND(f) pack_bf16(A * bf16lo(d0[0].f) + B * bf16lo(d0[1].f) + C * bf16lo(d0[2].f) + D * bf16lo(d0[3].f), \
+                                A * bf16hi(d0[0].f) + B * bf16hi(d0[1].f) + C * bf16hi(d0[2].f) + D * bf16hi(d0[3].f))
+                    res.x = B200_BLEND(x);
+                    res.y = B200_BLEND(y);
+                    res.z = B200_BLEND(z);
+                    res.w = B200_BLEND(w);
 #undef B200_BLEND
-                        }
-                        mbar_wait(&sm.empty[s], ph ^ 1);
-                        uint8_t* a = sm.a + s * kABytes;
-#pragma unroll
-                        for (int q = 0; q < kPasses; ++q) *reinterpret_cast<uint4*>(a + soff[q]) = res[q];
+                    if (q == 0) mbar_wait(&sm.empty[s], ph ^ 1);
+                    *reinterpret_cast<uint4*>(sm.a + s * kABytes + (q == 0 ? soff[0] : soff[1])) = res;
+                    if (q == kPasses - 1) {
                         fence_proxy_async_smem();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&sm.full[s]);
                         if (++s == stages) { s = 0; ph ^= 1; }
                     }
+                    ro0 = ro1; rw0 = rw1; ro1 = ro2; rw1 = rw2;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) d0[i] = d1[i];
                 }
             }
         }
@@ -449,6 +690,16 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t
     return 0;
 }
 
+// NHWC bf16 tensor (n, h, w, ld) seen as a 4-D TMA tensor over `c` channels with a {64, tile_w, tile_h, 1} box
+static int encode_nhwc(CUtensorMap* m, const void* base, uint64_t c, uint64_t w, uint64_t h, uint64_t n, uint64_t ld,
+                       uint64_t xstep, uint64_t ystep, uint64_t row_pixels, uint64_t img_pixels, int tile_w, int tile_h,
+                       const char* what) {
+    const uint64_t dims[4] = {c, w, h, n};
+    const uint64_t str[3] = {xstep * ld * 2, ystep * row_pixels * ld * 2, img_pixels * ld * 2};
+    const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)tile_w, (uint32_t)tile_h, 1u};
+    return encode_map(m, base, 4, dims, str, box, what);
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -462,10 +713,10 @@ struct b200_igemm {
     int smem_bytes;
 };
 
-static int pick_tile_w(int out_h, int out_w) {
-    int best = 128;
+static int pick_tile_w(int out_h, int out_w, int max_tw) {
+    int best = max_tw;
     long best_area = -1;
-    for (int tw = 128; tw >= 8; tw >>= 1) {
+    for (int tw = max_tw; tw >= 8; tw >>= 1) {
         const int th = 128 / tw;
         const long area = (long)((out_w + tw - 1) / tw) * tw * (long)((out_h + th - 1) / th) * th;
         if (best_area < 0 || area < best_area) {
@@ -497,8 +748,12 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
             return set_error("igemm: stride 2 needs even input size");
         taps = d->ksize * d->ksize;
     }
+    const int x_ld = d->x_ld ? d->x_ld : d->in_c;
+    if (d->mode != B200_IGEMM_STEM && (x_ld < d->in_c || (x_ld % 8))) return set_error("igemm: bad x_ld");
     if (d->mode == B200_IGEMM_DCN && !d->offsets) return set_error("igemm: DCN needs offsets");
     if ((d->flags & (B200_EPI_RES | B200_EPI_RES_UP2)) && !d->residual) return set_error("igemm: residual missing");
+    if ((d->flags & B200_EPI_DCN_COORDS) && (d->out_c != 32 || d->ksize != 3 || d->mode != B200_IGEMM_CONV))
+        return set_error("igemm: DCN_COORDS is for the 3x3 offset conv with out_c == 32");
     int block_n = d->block_n;
     if (block_n == 0) {
         block_n = 256;
@@ -527,15 +782,16 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     p.in_h = d->in_h;
     p.in_w = d->in_w;
     p.in_c = d->in_c;
+    p.x_ld = x_ld;
     p.out_h = d->in_h / d->stride;
     p.out_w = d->in_w / d->stride;
-    if (d->stride == 1) { p.out_h = d->in_h; p.out_w = d->in_w; }
     p.out_c = d->out_c;
     p.ksize = d->ksize;
     p.stride = d->stride;
     p.flags = d->flags;
     p.block_n = block_n;
-    p.tile_w = pick_tile_w(p.out_h, p.out_w);
+    // RES_UP2 reads a half-resolution residual box: the tile needs at least two rows
+    p.tile_w = pick_tile_w(p.out_h, p.out_w, (d->flags & B200_EPI_RES_UP2) ? 64 : 128);
     p.tile_h = kBlockM / p.tile_w;
     p.tiles_x = (p.out_w + p.tile_w - 1) / p.tile_w;
     p.tiles_y = (p.out_h + p.tile_h - 1) / p.tile_h;
@@ -556,14 +812,59 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     p.offsets = d->offsets;
     op->gather = (d->mode != B200_IGEMM_CONV);
 
+    // bf16 outputs whose channel count is a multiple of 64 go out through swizzled staging + TMA stores
+    p.epi_tma = !(d->flags & (B200_EPI_OUT_F32 | B200_EPI_DCN_COORDS)) && (d->out_c % 64) == 0 &&
+                (!(d->flags & B200_EPI_SHUFFLE2) || (d->shuf_c % 64) == 0);
+    p.res_tma = p.epi_tma && (d->flags & (B200_EPI_RES | B200_EPI_RES_UP2)) && !(d->flags & B200_EPI_SHUFFLE2);
+    if ((d->flags & (B200_EPI_RES | B200_EPI_RES_UP2)) && !p.res_tma && p.epi_tma) {
+        delete op;
+        return set_error("igemm: residual with a pixel-shuffle store is not supported");
+    }
+    if ((d->flags & B200_EPI_RES_UP2) && ((p.out_h | p.out_w) & 1)) {
+        delete op;
+        return set_error("igemm: RES_UP2 needs even output size");
+    }
+    p.res_bytes = (d->flags & B200_EPI_RES_UP2) ? kABytes / 4 : kABytes;
+
+    const int G = epi_groups(op->gather);
     const int b_bytes = block_n * 128;
-    const int budget = kMaxSmem - 1024 /*alignment*/ - 256 /*barriers*/;
-    int stages = budget / (kABytes + b_bytes);
-    if (stages > kMaxStages) stages = kMaxStages;
-    if (stages < 2) stages = 2;
+    const int stage_bytes = kABytes + b_bytes;
+    // compute-bound layers (long K loop) hide a single epilogue group behind the double-buffered accumulator
+    p.epi_active = (G == 2 && p.k_blocks < 8) ? 2 : 1;
+    p.stg_bufs = (p.epi_active == 1 && d->mode != B200_IGEMM_DCN) ? 2 : 1;  // DCN: long K loop, small carve-out
+    const int GA = p.epi_active;
+    const int fixed = 1024 /*alignment*/ + G * 2048 /*scale+shift*/ + 512 /*barriers*/ +
+                      (p.epi_tma ? GA * p.stg_bufs * kABytes : 0);
+    // The DCN gather lives on L1 hits (K ordered chunk-major), so it keeps its carve-out <= 132 KB and leaves the
+    // rest of the 256 KB to L1; everything else may use the full 227 KB opt-in.
+    const int cap = (d->mode == B200_IGEMM_DCN) ? 131 * 1024 : kMaxSmem;
+    int stages, res_bufs = 0;
+    if (p.res_tma) {
+        // HBM-bound layers: a few mainloop stages, the rest of the memory prefetches residual boxes
+        stages = p.k_blocks + 1;
+        if (stages < 2) stages = 2;
+        if (stages > 3) stages = 3;
+        while (stages > 2 && fixed + stages * stage_bytes + GA * 2 * kABytes > cap) --stages;
+        res_bufs = (cap - fixed - stages * stage_bytes) / (GA * kABytes);
+        if (res_bufs > kMaxResBufs) res_bufs = kMaxResBufs;
+        if (res_bufs < 1) {
+            delete op;
+            return set_error("igemm: not enough shared memory for the residual ring");
+        }
+        const int spare = (cap - fixed - GA * res_bufs * kABytes) / stage_bytes;  // give leftovers back to the mainloop
+        if (spare > stages) stages = spare > kMaxStages ? kMaxStages : spare;
+    } else {
+        stages = (cap - fixed) / stage_bytes;
+        if (stages > kMaxStages) stages = kMaxStages;
+    }
+    if (stages < 2) {
+        delete op;
+        return set_error("igemm: not enough shared memory for two pipeline stages");
+    }
     p.stages = stages;
-    op->smem_bytes = stages * (kABytes + b_bytes) + 1024 + 256;
-    op->threads = (kBaseWarps + (op->gather ? kGatherWarps : 0)) * 32;
+    p.res_bufs = res_bufs > 0 ? res_bufs : 1;
+    op->smem_bytes = fixed + stages * stage_bytes + (p.res_tma ? GA * res_bufs * kABytes : 0);
+    op->threads = (base_warps(op->gather) + (op->gather ? kGatherWarps : 0)) * 32;
 
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess ||
@@ -574,34 +875,60 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     op->grid = p.num_tiles < sms ? p.num_tiles : sms;
 
     // ---- tensor maps
+    int err = 0;
     const int ktot = p.k_blocks * kBlockK;
     {
         const uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)d->n_pad};
         const uint64_t str[1] = {(uint64_t)ktot * 2};
         const uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)block_n};
-        if (encode_map(&op->tm.b, d->w, 2, dims, str, box, "weights")) { delete op; return 1; }
+        err |= encode_map(&op->tm.b, d->w, 2, dims, str, box, "weights");
     }
-    if (!op->gather) {
-        const uint64_t C = d->in_c, W = d->in_w, H = d->in_h;
-        const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)p.tile_w, (uint32_t)p.tile_h, 1u};
+    if (!err && !op->gather) {
+        const uint64_t C = d->in_c, W = d->in_w, H = d->in_h, LD = x_ld;
         if (d->stride == 1) {
-            const uint64_t dims[4] = {C, W, H, (uint64_t)d->batch};
-            const uint64_t str[3] = {C * 2, W * C * 2, H * W * C * 2};
-            if (encode_map(&op->tm.a[0], d->x, 4, dims, str, box, "activations")) { delete op; return 1; }
+            err |= encode_nhwc(&op->tm.a[0], d->x, C, W, H, d->batch, LD, 1, 1, W, H * W, p.tile_w, p.tile_h, "activations");
         } else {
             // stride 2: four (row parity, column parity) strided views of the NHWC tensor
-            const uint64_t dims[4] = {C, W / 2, H / 2, (uint64_t)d->batch};
-            const uint64_t str[3] = {2 * C * 2, 2 * W * C * 2, H * W * C * 2};
             const int nviews = (d->ksize == 3) ? 4 : 1;
-            for (int v = 0; v < nviews; ++v) {
+            for (int v = 0; v < nviews && !err; ++v) {
                 const int py = v >> 1, px = v & 1;
-                const char* base = reinterpret_cast<const char*>(d->x) + ((uint64_t)py * W + px) * C * 2;
-                if (encode_map(&op->tm.a[v], base, 4, dims, str, box, "strided activations")) { delete op; return 1; }
+                const char* base = reinterpret_cast<const char*>(d->x) + ((uint64_t)py * W + px) * LD * 2;
+                err |= encode_nhwc(&op->tm.a[v], base, C, W / 2, H / 2, d->batch, LD, 2, 2, W, H * W, p.tile_w, p.tile_h,
+                                   "strided activations");
             }
         }
     }
+    if (!err && p.epi_tma) {
+        const uint64_t OW = p.out_w, OH = p.out_h, LD = d->out_ld;
+        if (d->flags & B200_EPI_SHUFFLE2) {
+            for (int v = 0; v < 4 && !err; ++v) {
+                const int dy = v >> 1, dx = v & 1;
+                char* base = reinterpret_cast<char*>(d->y) + ((uint64_t)dy * 2 * OW + dx) * LD * 2;
+                err |= encode_nhwc(&op->tm.out[v], base, d->shuf_c, OW, OH, d->batch, LD, 2, 2, 2 * OW, 4 * OH * OW,
+                                   p.tile_w, p.tile_h, "pixel-shuffle output");
+            }
+        } else {
+            err |= encode_nhwc(&op->tm.out[0], d->y, d->out_c, OW, OH, d->batch, LD, 1, 1, OW, OH * OW, p.tile_w,
+                               p.tile_h, "output");
+        }
+    }
+    if (!err && p.res_tma) {
+        if (d->flags & B200_EPI_RES_UP2)
+            err |= encode_nhwc(&op->tm.res, d->residual, d->out_c, p.out_w / 2, p.out_h / 2, d->batch, d->res_ld, 1, 1,
+                               p.out_w / 2, (uint64_t)(p.out_h / 2) * (p.out_w / 2), p.tile_w / 2, p.tile_h / 2,
+                               "half-resolution residual");
+        else
+            err |= encode_nhwc(&op->tm.res, d->residual, d->out_c, p.out_w, p.out_h, d->batch, d->res_ld, 1, 1, p.out_w,
+                               (uint64_t)p.out_h * p.out_w, p.tile_w, p.tile_h, "residual");
+    }
+    if (err) {
+        delete op;
+        return 1;
+    }
     // the attribute is per kernel function, not per op: always raise it to the full 227 KB opt-in
     cudaError_t e = cudaFuncSetAttribute(igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e == cudaSuccess)  // let the gather kernel's L1 have what its launches do not ask for as shared memory
+        e = cudaFuncSetAttribute(igemm_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) {
@@ -640,4 +967,18 @@ extern "C" int b200_igemm_info(const b200_igemm* op, int32_t* out_h, int32_t* ou
     if (num_tiles) *num_tiles = op->p.num_tiles;
     if (smem_bytes) *smem_bytes = op->smem_bytes;
     return 0;
+}
+
+extern "C" int b200_dcn_coords(const float* raw, void* coords, int batch, int in_h, int in_w, int x_ld, int stride,
+                               void* stream) {
+    if (!raw || !coords) return set_error("b200_dcn_coords: null pointer");
+    if (batch <= 0 || in_h <= 0 || in_w <= 0 || (stride != 1 && stride != 2) || x_ld <= 0)
+        return set_error("b200_dcn_coords: bad shape");
+    const int out_h = in_h / stride, out_w = in_w / stride;
+    const int64_t total = static_cast<int64_t>(batch) * out_h * out_w;
+    int64_t blocks = (total + 127) / 128;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    dcn_coords_kernel<<<static_cast<int>(blocks), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        raw, reinterpret_cast<uint4*>(coords), batch, out_h, out_w, in_h, in_w, x_ld, stride);
+    return check_cuda(cudaGetLastError(), "b200_dcn_coords launch");
 }

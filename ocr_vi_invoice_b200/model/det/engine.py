@@ -32,8 +32,8 @@ class PreparedWeights:
         to = lambda t: t.detach().to(device=device, dtype=torch.float32)
         P: Dict[str, tuple] = {}
 
-        def conv_bn(name, conv_w, bn, n_pad=None, conv_bias=None):
-            w = ops.pack_conv_weight(to(conv_w), n_pad)
+        def conv_bn(name, conv_w, bn, n_pad=None, conv_bias=None, dcn=False):
+            w = ops.pack_conv_weight(to(conv_w), n_pad, dcn=dcn)
             s, t = _bn_fold(bn, None if conv_bias is None else to(conv_bias))
             P[name] = (w, ops.pad_vec(to(s), w.shape[0], 1.0), ops.pad_vec(to(t), w.shape[0]))
 
@@ -51,7 +51,7 @@ class PreparedWeights:
                     om = blk.conv2.offset_mask_conv
                     w = ops.pack_conv_weight(to(om.weight), 32)
                     P[p + ".offset"] = (w, torch.ones(32, device=device), ops.pad_vec(to(om.bias), 32))
-                conv_bn(p + ".conv2", blk.conv2.weight, blk.bn2)
+                conv_bn(p + ".conv2", blk.conv2.weight, blk.bn2, dcn=self.dcn and li >= 2)
                 conv_bn(p + ".conv3", blk.conv3.weight, blk.bn3)
                 if blk.downsample is not None:
                     conv_bn(p + ".down", blk.downsample[0].weight, blk.downsample[1])
@@ -63,8 +63,13 @@ class PreparedWeights:
             conv_bn(f"smooth{i}", nk.fpn_convs[i].conv.weight, nk.fpn_convs[i].bn)
         self.w_att = to(nk.asf.conv_atten.weight).reshape(4, 1024).contiguous()
         self.b_att = to(nk.asf.conv_atten.bias).contiguous()
-        for br, seq in (("bin", model.head.bin_conv), ("thr", model.head.thresh_conv)):
-            conv_bn(f"head.{br}.0", seq[0].conv.weight, seq[0].bn)
+        # head: the first 3x3 conv of both branches is one GEMM (N = 64 + 64, reads the fused map once)
+        hb, ht = model.head.bin_conv, model.head.thresh_conv
+        w0 = torch.cat([ops.pack_conv_weight(to(hb[0].conv.weight), 64), ops.pack_conv_weight(to(ht[0].conv.weight), 64)])
+        sb, tb = _bn_fold(hb[0].bn)
+        st, tt = _bn_fold(ht[0].bn)
+        P["head.0"] = (w0.contiguous(), torch.cat([to(sb), to(st)]).contiguous(), torch.cat([to(tb), to(tt)]).contiguous())
+        for br, seq in (("bin", hb), ("thr", ht)):
             w = ops.pack_convT_weight(to(seq[1].weight), 256)
             s, t = _bn_fold(seq[2], to(seq[1].bias))
             P[f"head.{br}.1"] = (w, to(s).repeat(4).contiguous(), to(t).repeat(4).contiguous())
@@ -94,11 +99,11 @@ class Plan:
         P = W.P
 
         def igemm(name, mode, x, key, y, *, in_h, in_w, in_c, out_c, ksize, stride, flags=0, residual=None, res_ld=0,
-                  offsets=None, shuf_c=0, out_ld=None):
+                  offsets=None, shuf_c=0, out_ld=None, x_ld=0):
             w, s, t = P[key]
             op = ops.Igemm(mode, x, w, s, t, y, batch=b, in_h=in_h, in_w=in_w, in_c=in_c, out_c=out_c, ksize=ksize,
                            stride=stride, flags=flags, residual=residual, res_ld=res_ld, offsets=offsets, shuf_c=shuf_c,
-                           out_ld=out_ld, name=name)
+                           out_ld=out_ld, x_ld=x_ld, name=name)
             self.steps.append(op)
             self.names.append(name)
             self.step_flops[name] = op.flops
@@ -130,9 +135,10 @@ class Plan:
                       stride=1, flags=ops.EPI_RELU)
                 t2 = bf(b, ho, wo, width)
                 if W.dcn and li >= 2:
-                    om = torch.empty(b, ho, wo, 32, device=dev, dtype=torch.float32)
+                    # offset_mask_conv with the sampling-record epilogue: [pixel][9 taps][4 offsets + 4 weights]
+                    om = torch.empty(b, ho, wo, 9, 8, device=dev, dtype=torch.int32)
                     igemm(p + ".offset", ops.IGEMM_CONV, t1, p + ".offset", om, in_h=h, in_w=w, in_c=width, out_c=32,
-                          ksize=3, stride=stride, flags=ops.EPI_OUT_F32)
+                          ksize=3, stride=stride, flags=ops.EPI_DCN_COORDS, out_ld=32)
                     igemm(p + ".dcn", ops.IGEMM_DCN, t1, p + ".conv2", t2, in_h=h, in_w=w, in_c=width, out_c=width,
                           ksize=3, stride=stride, flags=ops.EPI_RELU, offsets=om)
                 else:
@@ -179,13 +185,13 @@ class Plan:
         # ---- head
         h4, w4 = sizes[0]
         tails = {}
-        for br in ("bin", "thr"):
-            t = bf(b, h4, w4, 64)
-            igemm(f"head.{br}.0", ops.IGEMM_CONV, fused, f"head.{br}.0", t, in_h=h4, in_w=w4, in_c=256, out_c=64, ksize=3,
-                  stride=1, flags=ops.EPI_RELU)
+        t01 = bf(b, h4, w4, 128)  # [bin 64 | thr 64] channels per pixel
+        igemm("head.0", ops.IGEMM_CONV, fused, "head.0", t01, in_h=h4, in_w=w4, in_c=256, out_c=128, ksize=3, stride=1,
+              flags=ops.EPI_RELU)
+        for bi_, br in enumerate(("bin", "thr")):
             u = bf(b, 2 * h4, 2 * w4, 64)
-            igemm(f"head.{br}.1", ops.IGEMM_CONV, t, f"head.{br}.1", u, in_h=h4, in_w=w4, in_c=64, out_c=256, ksize=1,
-                  stride=1, flags=ops.EPI_RELU | ops.EPI_SHUFFLE2, shuf_c=64)
+            igemm(f"head.{br}.1", ops.IGEMM_CONV, t01[..., 64 * bi_:], f"head.{br}.1", u, in_h=h4, in_w=w4, in_c=64,
+                  out_c=256, ksize=1, stride=1, flags=ops.EPI_RELU | ops.EPI_SHUFFLE2, shuf_c=64, x_ld=128)
             tails[br] = u
             if keep_taps:
                 self.taps[f"head.{'bin_conv' if br == 'bin' else 'thresh_conv'}.3"] = (u, 64)

@@ -11,13 +11,13 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (EPI_OUT_F32, EPI_RELU, EPI_RES, EPI_RES_UP2, EPI_SHUFFLE2, IGEMM_CONV, IGEMM_DCN,
-                   IGEMM_STEM)
+from ._lib import (EPI_DCN_COORDS, EPI_OUT_F32, EPI_RELU, EPI_RES, EPI_RES_UP2, EPI_SHUFFLE2, IGEMM_CONV,
+                   IGEMM_DCN, IGEMM_STEM)
 
 __all__ = [
     "Igemm", "pack_conv_weight", "pack_stem_weight", "pack_convT_weight", "fold_bn", "pad_vec",
     "stem_pack", "maxpool3x3s2", "asf_fwd", "db_head_fwd", "postproc", "ref_conv2d", "ref_dcn2d",
-    "EPI_RELU", "EPI_RES", "EPI_RES_UP2", "EPI_OUT_F32", "EPI_SHUFFLE2", "IGEMM_CONV", "IGEMM_STEM", "IGEMM_DCN",
+    "EPI_RELU", "EPI_RES", "EPI_RES_UP2", "EPI_OUT_F32", "EPI_SHUFFLE2", "EPI_DCN_COORDS", "dcn_coords", "IGEMM_CONV", "IGEMM_STEM", "IGEMM_DCN",
 ]
 
 
@@ -34,16 +34,23 @@ def choose_n_pad(out_c: int) -> int:
     return _round_up(out_c, 256)
 
 
-def pack_conv_weight(w: torch.Tensor, n_pad: Optional[int] = None) -> torch.Tensor:
+def pack_conv_weight(w: torch.Tensor, n_pad: Optional[int] = None, dcn: bool = False) -> torch.Tensor:
     """(O, I, kh, kw) fp32 -> [n_pad][kh*kw*I] bf16 with K ordered (tap, cin).
 
     torchvision's deform_conv2d and nn.Conv2d flatten K as (cin, tap) (`weight.flatten(1)`); the NHWC
     kernels walk K tap-major so a 64-channel slice of one tap is one contiguous 128-byte row.
+    `dcn=True` orders K as (64-channel chunk, tap, 64 channels) instead: the deformable kernel walks all
+    9 taps of one channel chunk back to back so its gathers re-hit the same neighbourhood in L1.
     """
     o, i, kh, kw = w.shape
     n_pad = n_pad or choose_n_pad(o)
     out = torch.zeros(n_pad, kh * kw * i, dtype=torch.bfloat16, device=w.device)
-    out[:o] = w.permute(0, 2, 3, 1).reshape(o, kh * kw * i).to(torch.bfloat16)
+    if dcn:
+        assert i % 64 == 0
+        t = w.reshape(o, i // 64, 64, kh * kw).permute(0, 1, 3, 2)  # (o, chunk, tap, 64)
+        out[:o] = t.reshape(o, kh * kw * i).to(torch.bfloat16)
+    else:
+        out[:o] = w.permute(0, 2, 3, 1).reshape(o, kh * kw * i).to(torch.bfloat16)
     return out.contiguous()
 
 
@@ -98,7 +105,7 @@ class Igemm:
                  y: torch.Tensor, *, batch: int, in_h: int, in_w: int, in_c: int, out_c: int, ksize: int,
                  stride: int, flags: int = 0, residual: Optional[torch.Tensor] = None,
                  offsets: Optional[torch.Tensor] = None, out_ld: Optional[int] = None, res_ld: int = 0,
-                 shuf_c: int = 0, block_n: int = 0, name: str = ""):
+                 shuf_c: int = 0, block_n: int = 0, x_ld: int = 0, name: str = ""):
         lib = _lib.load()
         self.name = name
         self._keep = (x, w, scale, shift, y, residual, offsets)
@@ -109,7 +116,7 @@ class Igemm:
             out_ld = shuf_c if (flags & EPI_SHUFFLE2) else out_c
         d = _lib.IgemmDesc(
             mode=mode, batch=batch, in_h=in_h, in_w=in_w, in_c=in_c, out_c=out_c, n_pad=n_pad, ksize=ksize,
-            stride=stride, flags=flags, out_ld=out_ld, res_ld=res_ld, shuf_c=shuf_c, block_n=block_n,
+            stride=stride, flags=flags, out_ld=out_ld, res_ld=res_ld, shuf_c=shuf_c, block_n=block_n, x_ld=x_ld,
             x=_lib.ptr(x), w=_lib.ptr(w), scale=_lib.ptr(scale), shift=_lib.ptr(shift),
             residual=_lib.ptr(residual), y=_lib.ptr(y), offsets=_lib.ptr(offsets))
         h = C.c_void_p()
@@ -152,12 +159,18 @@ def asf_fwd(p2, p3, p4, p5, w_att, b_att, out, batch, sizes) -> None:
                                         _lib.current_stream()), "asf_fwd")
 
 
+def dcn_coords(raw: torch.Tensor, coords: torch.Tensor, batch: int, in_h: int, in_w: int, x_ld: int, stride: int) -> None:
+    """raw [b, ho, wo, 32] fp32 offset_mask_conv output -> b200_dcn_coord records [b, ho, wo, 9, 8] (4-byte words)."""
+    _lib.check(_lib.load().b200_dcn_coords(_lib.ptr(raw), _lib.ptr(coords), batch, in_h, in_w, x_ld, stride,
+                                           _lib.current_stream()), "dcn_coords")
+
+
 def db_head_fwd(t_bin, t_thr, w2_bin, b2_bin: float, w2_thr, b2_thr: float, k: float, maps: dict, batch: int,
-                h: int, w: int) -> None:
+                h: int, w: int, ld: int = 64) -> None:
     g = lambda n: _lib.ptr(maps.get(n))
     _lib.check(_lib.load().b200_db_head_fwd(_lib.ptr(t_bin), _lib.ptr(t_thr), _lib.ptr(w2_bin), b2_bin,
                                             _lib.ptr(w2_thr), b2_thr, k, g("binary"), g("thresh"), g("thresh_binary"),
-                                            g("bin_logits"), g("thresh_logits"), batch, h, w, _lib.current_stream()),
+                                            g("bin_logits"), g("thresh_logits"), batch, h, w, ld, _lib.current_stream()),
                "db_head_fwd")
 
 

@@ -51,6 +51,11 @@ CONV_CASES = [
     (1, 16, 16, 512, 256, 1, 1, "up2"),
     (1, 64, 256, 64, 64, 3, 1, "relu"),
     (3, 12, 12, 1024, 2048, 1, 1, ""),
+    (2, 48, 40, 64, 256, 1, 1, "res+relu"),
+    (1, 36, 28, 128, 512, 1, 1, "res+relu"),
+    (1, 64, 48, 256, 256, 1, 1, "up2"),
+    (2, 10, 6, 256, 1024, 1, 1, "res+relu"),
+    (1, 128, 128, 64, 64, 1, 1, "relu"),
 ]
 
 
@@ -204,18 +209,52 @@ def test_dcn_igemm(case):
     mask = torch.sigmoid(om[..., 18:27]).permute(0, 3, 1, 2).contiguous()
     ref = tvops.deform_conv2d(xb, offset, wb, None, stride=s, padding=1, mask=mask)
     ref = (ref * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)).relu()
-    wp = ops.pack_conv_weight(wt, ops.choose_n_pad(co))
+    wp = ops.pack_conv_weight(wt, ops.choose_n_pad(co), dcn=True)   # K = (chunk, tap, 64) for the tcgen05 DCN kernel
+    wp_ref = ops.pack_conv_weight(wt, ops.choose_n_pad(co))         # K = (tap, cin) for the cross-check kernel
     n_pad = wp.shape[0]
     sc, sh = ops.pad_vec(scale, n_pad, 1.0), ops.pad_vec(shift, n_pad)
     y = torch.full((b, oh, ow, co), float("nan"), device=dev, dtype=torch.bfloat16)
+    coords = torch.empty(b, oh, ow, 9, 8, device=dev, dtype=torch.int32)
+    ops.dcn_coords(om, coords, b, h, w, ci, s)
     op = ops.Igemm(ops.IGEMM_DCN, nhwc(x), wp, sc, sh, y, batch=b, in_h=h, in_w=w, in_c=ci, out_c=co, ksize=3,
-                   stride=s, flags=ops.EPI_RELU, offsets=om, name=str(case))
+                   stride=s, flags=ops.EPI_RELU, offsets=coords, name=str(case))
     op()
     torch.cuda.synchronize()
     close(nchw(y), ref, rel_rms=3e-2)
     y2 = torch.zeros_like(y)
-    ops.ref_dcn2d(nhwc(x), om, wp, sc, sh, y2, b, h, w, ci, co, s, ops.EPI_RELU, co)
+    ops.ref_dcn2d(nhwc(x), om, wp_ref, sc, sh, y2, b, h, w, ci, co, s, ops.EPI_RELU, co)
     torch.cuda.synchronize()
     close(nchw(y2), ref, rel_rms=3e-2)
     # tensor-core path vs cross-check kernel: same rounding points, only accumulation order differs
     close(nchw(y), nchw(y2), rel_rms=1e-2, rtol=1e-2)
+
+
+@pytest.mark.parametrize("case", [(1, 24, 40, 128, 1), (2, 32, 48, 256, 2)], ids=lambda c: "b%d_%dx%d_c%d_s%d" % c)
+def test_offset_conv_coords_epilogue(case):
+    """The offset conv's fused sampling-record epilogue equals raw fp32 output -> b200_dcn_coords, bit for bit."""
+    from ocr_vi_invoice_b200 import ops
+    _setup()
+    b, h, w, ci, s = case
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(21)
+    x = torch.randn(b, ci, h, w, device=dev, generator=g)
+    wt = torch.randn(27, ci, 3, 3, device=dev, generator=g) * (2.0 / (9 * ci) ** 0.5)
+    bias = torch.randn(27, device=dev, generator=g)
+    oh, ow = h // s, w // s
+    wp = ops.pack_conv_weight(wt, 32)
+    sc, sh = torch.ones(32, device=dev), ops.pad_vec(bias, 32)
+    raw = torch.empty(b, oh, ow, 32, device=dev, dtype=torch.float32)
+    ops.Igemm(ops.IGEMM_CONV, nhwc(x), wp, sc, sh, raw, batch=b, in_h=h, in_w=w, in_c=ci, out_c=32, ksize=3, stride=s,
+              flags=ops.EPI_OUT_F32, name="offset-raw")()
+    c_ref = torch.empty(b, oh, ow, 9, 8, device=dev, dtype=torch.int32)
+    ops.dcn_coords(raw, c_ref, b, h, w, ci, s)
+    c_fused = torch.full((b, oh, ow, 9, 8), -7, device=dev, dtype=torch.int32)
+    ops.Igemm(ops.IGEMM_CONV, nhwc(x), wp, sc, sh, c_fused, batch=b, in_h=h, in_w=w, in_c=ci, out_c=32, ksize=3, stride=s,
+              flags=ops.EPI_DCN_COORDS, out_ld=32, name="offset-coords")()
+    torch.cuda.synchronize()
+    assert torch.equal(c_fused, c_ref)
+    # records are sane: offsets inside the image, weights in [0, 1], and each tap's weights sum to <= sigmoid(mask)
+    off = c_ref[..., :4]
+    wg = c_ref[..., 4:].view(torch.float32)
+    assert off.min() >= 0 and off.max() < h * w * ci
+    assert wg.min() >= 0 and wg.sum(-1).max() <= 1.0 + 1e-5
