@@ -142,6 +142,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels one by one instead of replaying a CUDA graph")
+    ap.add_argument("--profile-launch", default="", help="run one forward, then only the named plan launch 3x (for ncu)")
     ap.add_argument("--dump-launches", default="", help="write the per-launch table (name, kind, ms, GFLOP) to this file")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -199,6 +200,19 @@ def main():
     x_dev = host.to(dev)
     model.use_cuda_graph = not args.no_graph
     model.output_maps = ("binary",)  # the production caller reads only 'binary' (pipeline2.py:318)
+
+    if args.profile_launch:
+        model.use_cuda_graph = False
+        model(x_dev)
+        torch.cuda.synchronize()
+        plan = model._get_plan(x_dev)
+        idx = plan.names.index(args.profile_launch)
+        n_ig = sum(1 for n in plan.names if n in plan.step_kind)
+        print(f"profile-launch {args.profile_launch}: plan step {idx}, {n_ig} igemm launches per forward", file=sys.stderr)
+        for _ in range(3):
+            plan.steps[idx]()
+        torch.cuda.synchronize()
+        return 0
 
     def step_device():
         out = model(x_dev)

@@ -55,12 +55,14 @@ enum {
                                  the DCN producers do no coordinate arithmetic (dcn.py:44-46 fused)    */
 };
 
-/* Sampling record of one (output pixel, tap) of the modulated deformable conv: the four bilinear corners as
- * element offsets into the image ((h*W + w)*x_ld, 0 when the corner is outside) and their weights already
- * multiplied by sigmoid(mask) (0 when outside).  torchvision deform_conv2d semantics. */
+/* Sampling record of one (output pixel, tap) of the modulated deformable conv (torchvision deform_conv2d
+ * semantics): `off` = element offset ((row*W + col)*x_ld) of the top-left pixel of a 2x2 block clamped inside
+ * the image; w[4] = bf16 bilinear weights of the block's pixels (0,0) (0,1) (1,0) (1,1), already multiplied by
+ * sigmoid(mask) and zero for corners torchvision treats as outside. */
 typedef struct b200_dcn_coord {
-    int32_t off[4];
-    float   wgt[4];
+    int32_t  off;
+    uint16_t w[4];
+    uint32_t pad;
 } b200_dcn_coord;
 
 typedef struct b200_igemm_desc {

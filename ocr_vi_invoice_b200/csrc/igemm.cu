@@ -2,9 +2,10 @@
 // warp-specialised persistent CTAs.  One kernel template covers
 //   * plain 1x1 / 3x3 convolutions, stride 1 or 2 (A operand = NHWC activations loaded by TMA boxes,
 //     one box per (tap, 64-channel slice); zero padding comes from TMA out-of-bounds fill),
-//   * the modulated deformable conv v2 (A operand gathered by 16 producer warps from pre-computed
-//     b200_dcn_coord records: 4-corner bilinear blend with mask-modulated weights, bf16 pack, written
-//     straight into the 128B-swizzled UMMA layout; loads software-pipelined one unit ahead),
+//   * the modulated deformable conv v2 (A operand gathered by 16 producer warps from pre-computed 16-byte
+//     b200_dcn_coord records: 2x2-block bilinear blend with mask-modulated bf16 weights in packed bf16x2 FMAs,
+//     written straight into the 128B-swizzled UMMA layout; loads software-pipelined one unit ahead, K ordered
+//     (channel chunk, tap) so the gathers hit in L1),
 //   * the 7x7 s2 stem on a space-to-depth buffer (A rows are contiguous 128 B runs, copied by the
 //     producer warps),
 // all with a fused epilogue (folded BN scale/shift or bias, residual add, ReLU) that either
@@ -123,40 +124,43 @@ __device__ __forceinline__ int chunks_of(const IgemmParams& p, int nb) {
 }
 
 // ------------------------------------------------------------------------------------------ DCN coordinates
-// torchvision deform_conv2d sampling of tap k at output pixel (oy, ox): see include/dbnet_b200.h b200_dcn_coord.
-__device__ __forceinline__ void dcn_make_coord(float dy, float dx, float mlogit, int oy, int ox, int tap, int stride,
-                                               int in_h, int in_w, int x_ld, int (&off)[4], float (&wgt)[4]) {
+// torchvision deform_conv2d sampling of tap k at output pixel (oy, ox) -> one 16-byte b200_dcn_coord record:
+// the element offset of the top-left pixel of a 2x2 block clamped inside the image, and the four bilinear weights
+// (already multiplied by sigmoid(mask), zero for corners outside the image) as bf16, in block order
+// (0,0) (0,1) (1,0) (1,1).  Clamping the block keeps all four addresses in bounds, so the producers need no
+// per-corner predicates: a corner torchvision would skip simply carries weight 0.
+__device__ __forceinline__ uint4 dcn_make_coord(float dy, float dx, float mlogit, int oy, int ox, int tap, int stride,
+                                                int in_h, int in_w, int x_ld) {
     const int ky = tap / 3, kx = tap - ky * 3;
     const float m = 1.0f / (1.0f + expf(-mlogit));
     const float h = static_cast<float>(oy * stride - 1 + ky) + dy;
     const float w = static_cast<float>(ox * stride - 1 + kx) + dx;
-    off[0] = off[1] = off[2] = off[3] = 0;
-    wgt[0] = wgt[1] = wgt[2] = wgt[3] = 0.0f;
+    float s00 = 0.0f, s01 = 0.0f, s10 = 0.0f, s11 = 0.0f;
+    int off = 0;
     if (h > -1.0f && w > -1.0f && h < static_cast<float>(in_h) && w < static_cast<float>(in_w)) {
         const float hf = floorf(h), wf = floorf(w);
         const int hl = static_cast<int>(hf), wl = static_cast<int>(wf);
-        const int hh = hl + 1, wh = wl + 1;
         const float lh = h - hf, lw = w - wf;
         const float uh = 1.0f - lh, uw = 1.0f - lw;
-        const bool t_ok = hl >= 0, b_ok = hh <= in_h - 1, l_ok = wl >= 0, r_ok = wh <= in_w - 1;
-        if (t_ok && l_ok) { off[0] = (hl * in_w + wl) * x_ld; wgt[0] = m * (uh * uw); }
-        if (t_ok && r_ok) { off[1] = (hl * in_w + wh) * x_ld; wgt[1] = m * (uh * lw); }
-        if (b_ok && l_ok) { off[2] = (hh * in_w + wl) * x_ld; wgt[2] = m * (lh * uw); }
-        if (b_ok && r_ok) { off[3] = (hh * in_w + wh) * x_ld; wgt[3] = m * (lh * lw); }
+        const int br = min(max(hl, 0), max(in_h - 2, 0)), bc = min(max(wl, 0), max(in_w - 2, 0));
+        // weight of actual row r in {hl, hl+1} lands in block row r - br (0 or 1) if r is inside the image
+        const float wt = (hl >= 0) ? uh : 0.0f, wb = (hl + 1 <= in_h - 1) ? lh : 0.0f;
+        const float wlft = (wl >= 0) ? uw : 0.0f, wrgt = (wl + 1 <= in_w - 1) ? lw : 0.0f;
+        const float r0 = (hl == br) ? wt : ((hl + 1 == br) ? wb : 0.0f);
+        const float r1 = (hl == br + 1) ? wt : ((hl + 1 == br + 1) ? wb : 0.0f);
+        const float c0 = (wl == bc) ? wlft : ((wl + 1 == bc) ? wrgt : 0.0f);
+        const float c1 = (wl == bc + 1) ? wlft : ((wl + 1 == bc + 1) ? wrgt : 0.0f);
+        s00 = m * (r0 * c0); s01 = m * (r0 * c1); s10 = m * (r1 * c0); s11 = m * (r1 * c1);
+        off = (br * in_w + bc) * x_ld;
     }
+    return make_uint4(static_cast<uint32_t>(off), pack_bf16(s00, s01), pack_bf16(s10, s11), 0u);
 }
 
 __device__ __forceinline__ void dcn_store_coords(uint4* dst, const float (&f)[32], int oy, int ox, int stride, int in_h,
                                                  int in_w, int x_ld) {
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-        int off[4];
-        float wgt[4];
-        dcn_make_coord(f[2 * tap], f[2 * tap + 1], f[18 + tap], oy, ox, tap, stride, in_h, in_w, x_ld, off, wgt);
-        dst[2 * tap] = make_uint4(off[0], off[1], off[2], off[3]);
-        dst[2 * tap + 1] = make_uint4(__float_as_uint(wgt[0]), __float_as_uint(wgt[1]), __float_as_uint(wgt[2]),
-                                      __float_as_uint(wgt[3]));
-    }
+    for (int tap = 0; tap < 9; ++tap)
+        dst[tap] = dcn_make_coord(f[2 * tap], f[2 * tap + 1], f[18 + tap], oy, ox, tap, stride, in_h, in_w, x_ld);
 }
 
 __global__ void dcn_coords_kernel(const float* __restrict__ raw, uint4* __restrict__ coords, int batch, int out_h,
@@ -172,7 +176,7 @@ __global__ void dcn_coords_kernel(const float* __restrict__ raw, uint4* __restri
             const float4 v = __ldg(reinterpret_cast<const float4*>(raw + i * 32 + j));
             f[j] = v.x; f[j + 1] = v.y; f[j + 2] = v.z; f[j + 3] = v.w;
         }
-        dcn_store_coords(coords + i * 18, f, oy, ox, stride, in_h, in_w, x_ld);
+        dcn_store_coords(coords + i * 9, f, oy, ox, stride, in_h, in_w, x_ld);
     }
 }
 
@@ -193,7 +197,7 @@ __device__ __forceinline__ void epilogue_direct32(const IgemmParams& p, const ui
     }
     if (p.flags & B200_EPI_DCN_COORDS) {
         const int64_t opix = (static_cast<int64_t>(n) * p.out_h + oy) * p.out_w + ox;
-        dcn_store_coords(reinterpret_cast<uint4*>(p.y) + opix * 18, f, oy, ox, p.stride, p.in_h, p.in_w, p.x_ld);
+        dcn_store_coords(reinterpret_cast<uint4*>(p.y) + opix * 9, f, oy, ox, p.stride, p.in_h, p.in_w, p.x_ld);
         return;
     }
     const int ncols = min(32, p.out_c - col0);  // multiple of 8
@@ -584,62 +588,79 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                 // modulated deformable sampling from b200_dcn_coord records.  Unit = (k-block, pass); the corner
                 // loads of unit u+1 and the record of unit u+2 are in flight while unit u is blended.
                 const __nv_bfloat16* img = p.x + static_cast<int64_t>(t.n) * p.in_h * p.in_w * p.x_ld + l8 * 8;
+                const int cs = (p.in_w > 1) ? p.x_ld : 0;            // element step to the block's right column
+                const int rs = (p.in_h > 1) ? p.in_w * p.x_ld : 0;   // element step to the block's bottom row
                 const uint4* rec[kPasses];
-                float vmul[kPasses];
 #pragma unroll
                 for (int q = 0; q < kPasses; ++q) {
                     const int64_t pix = valid[q] ? (static_cast<int64_t>(t.n) * p.out_h + oy[q]) * p.out_w + ox[q] : 0;
-                    rec[q] = reinterpret_cast<const uint4*>(p.offsets) + pix * 18;
-                    vmul[q] = valid[q] ? 1.0f : 0.0f;
+                    rec[q] = reinterpret_cast<const uint4*>(p.offsets) + pix * 9;
                 }
-                const int units = p.k_blocks * kPasses;
                 // K is ordered (64-channel chunk, tap): the 9 taps x 4 corners of one chunk re-touch the same
                 // neighbourhood back to back, so they hit in L1 (the kernel keeps its smem carve-out small).
-                auto load_rec = [&](int u, uint4& ro, uint4& rw) {
-                    const int kb = u / kPasses, q = u - kb * kPasses;
-                    const int tap = kb % 9;
-                    ro = ldg128(rec[q] + 2 * tap);
-                    rw = ldg128(rec[q] + 2 * tap + 1);
-                };
-                auto load_corners = [&](int u, const uint4& ro, uint4 (&d)[4]) {
-                    const int kb = u / kPasses;
-                    const __nv_bfloat16* src = img + (kb / 9) * kBlockK;
-                    d[0] = ldg128(src + static_cast<int>(ro.x));
-                    d[1] = ldg128(src + static_cast<int>(ro.y));
-                    d[2] = ldg128(src + static_cast<int>(ro.z));
-                    d[3] = ldg128(src + static_cast<int>(ro.w));
-                };
-                uint4 ro0, rw0, ro1, rw1, ro2, rw2;
-                uint4 d0[4], d1[4];
-                load_rec(0, ro0, rw0);
-                load_rec(1, ro1, rw1);  // units >= 2 always (k_blocks >= 9)
-                load_corners(0, ro0, d0);
-                for (int u = 0; u < units; ++u) {
-                    const int q = u & (kPasses - 1);
-                    if (u + 2 < units) load_rec(u + 2, ro2, rw2);
-                    if (u + 1 < units) load_corners(u + 1, ro1, d1);
-                    const float vm = (q == 0) ? vmul[0] : vmul[1];
-                    const float A = __uint_as_float(rw0.x) * vm, B = __uint_as_float(rw0.y) * vm;
-                    const float C = __uint_as_float(rw0.z) * vm, D = __uint_as_float(rw0.w) * vm;
-                    uint4 res;
-#define B200_BLEND(f) pack_bf16(A * bf16lo(d0[0].f) + B * bf16lo(d0[1].f) + C * bf16lo(d0[2].f) + D * bf16lo(d0[3].f), \
-                                A * bf16hi(d0[0].f) + B * bf16hi(d0[1].f) + C * bf16hi(d0[2].f) + D * bf16hi(d0[3].f))
-                    res.x = B200_BLEND(x);
-                    res.y = B200_BLEND(y);
-                    res.z = B200_BLEND(z);
-                    res.w = B200_BLEND(w);
-#undef B200_BLEND
-                    if (q == 0) mbar_wait(&sm.empty[s], ph ^ 1);
-                    *reinterpret_cast<uint4*>(sm.a + s * kABytes + (q == 0 ? soff[0] : soff[1])) = res;
-                    if (q == kPasses - 1) {
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&sm.full[s]);
-                        if (++s == stages) { s = 0; ph ^= 1; }
-                    }
-                    ro0 = ro1; rw0 = rw1; ro1 = ro2; rw1 = rw2;
+                // Unit = (k-block, pass).  While unit u is blended, the four corner loads of unit u+1 and the record of
+                // unit u+2 are in flight.  The loop is unrolled over 3 k-blocks = 6 units so the record ring (3 slots)
+                // and the corner ping-pong (2 slots) are addressed with compile-time indices (k_blocks = 9 * chunks).
+                uint4 rcd[3];
+                uint4 dat[2][4];
+                rcd[0] = ldg128(rec[0]);
+                rcd[1] = ldg128(rec[1]);
+                {
+                    const __nv_bfloat16* b0 = img + static_cast<int>(rcd[0].x);
+                    dat[0][0] = ldg128(b0);
+                    dat[0][1] = ldg128(b0 + cs);
+                    dat[0][2] = ldg128(b0 + rs);
+                    dat[0][3] = ldg128(b0 + rs + cs);
+                }
+                int tap0 = 0;                    // tap of k-block kb0 (0, 3 or 6)
+                const __nv_bfloat16* src = img;  // channel chunk of k-block kb0
+                for (int kb0 = 0; kb0 < p.k_blocks; kb0 += 3) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) d0[i] = d1[i];
+                    for (int j = 0; j < 6; ++j) {
+                        const int q = j & 1;
+                        {   // record of unit u+2: k-block kb0 + (j+2)/2, same pass
+                            const int dk = (j + 2) >> 1;
+                            if (kb0 + dk < p.k_blocks) {
+                                int tp = tap0 + dk;
+                                tp = (tp >= 9) ? tp - 9 : tp;
+                                rcd[(j + 2) % 3] = ldg128(rec[q] + tp);
+                            }
+                        }
+                        {   // corners of unit u+1: k-block kb0 + (j+1)/2, pass (j+1)&1
+                            const int dk = (j + 1) >> 1;
+                            if (kb0 + dk < p.k_blocks) {
+                                const __nv_bfloat16* b0 =
+                                    ((tap0 + dk >= 9) ? src + kBlockK : src) + static_cast<int>(rcd[(j + 1) % 3].x);
+                                dat[(j + 1) & 1][0] = ldg128(b0);
+                                dat[(j + 1) & 1][1] = ldg128(b0 + cs);
+                                dat[(j + 1) & 1][2] = ldg128(b0 + rs);
+                                dat[(j + 1) & 1][3] = ldg128(b0 + rs + cs);
+                            }
+                        }
+                        // blend unit u with packed bf16x2 FMAs (one bf16 rounding per FMA)
+                        const uint32_t w01 = valid[q] ? rcd[j % 3].y : 0u, w23 = valid[q] ? rcd[j % 3].z : 0u;
+                        const __nv_bfloat162 wa = __low2bfloat162(bits_bf162(w01)), wb = __high2bfloat162(bits_bf162(w01));
+                        const __nv_bfloat162 wc = __low2bfloat162(bits_bf162(w23)), wd = __high2bfloat162(bits_bf162(w23));
+                        const uint4 (&d)[4] = dat[j & 1];
+                        uint4 res;
+#define B200_BLEND2(f) bf162_bits(__hfma2(wd, bits_bf162(d[3].f), __hfma2(wc, bits_bf162(d[2].f), \
+                           __hfma2(wb, bits_bf162(d[1].f), __hmul2(wa, bits_bf162(d[0].f))))))
+                        res.x = B200_BLEND2(x);
+                        res.y = B200_BLEND2(y);
+                        res.z = B200_BLEND2(z);
+                        res.w = B200_BLEND2(w);
+#undef B200_BLEND2
+                        if (q == 0) mbar_wait(&sm.empty[s], ph ^ 1);
+                        *reinterpret_cast<uint4*>(sm.a + s * kABytes + soff[q]) = res;
+                        if (q == 1) {
+                            fence_proxy_async_smem();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&sm.full[s]);
+                            if (++s == stages) { s = 0; ph ^= 1; }
+                        }
+                    }
+                    tap0 += 3;
+                    if (tap0 == 9) { tap0 = 0; src += kBlockK; }
                 }
             }
         }

@@ -135,8 +135,8 @@ class Plan:
                       stride=1, flags=ops.EPI_RELU)
                 t2 = bf(b, ho, wo, width)
                 if W.dcn and li >= 2:
-                    # offset_mask_conv with the sampling-record epilogue: [pixel][9 taps][4 offsets + 4 weights]
-                    om = torch.empty(b, ho, wo, 9, 8, device=dev, dtype=torch.int32)
+                    # offset_mask_conv with the sampling-record epilogue: [pixel][9 taps][16-byte record]
+                    om = torch.empty(b, ho, wo, 9, 4, device=dev, dtype=torch.int32)
                     igemm(p + ".offset", ops.IGEMM_CONV, t1, p + ".offset", om, in_h=h, in_w=w, in_c=width, out_c=32,
                           ksize=3, stride=stride, flags=ops.EPI_DCN_COORDS, out_ld=32)
                     igemm(p + ".dcn", ops.IGEMM_DCN, t1, p + ".conv2", t2, in_h=h, in_w=w, in_c=width, out_c=width,

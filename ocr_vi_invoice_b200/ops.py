@@ -160,7 +160,7 @@ def asf_fwd(p2, p3, p4, p5, w_att, b_att, out, batch, sizes) -> None:
 
 
 def dcn_coords(raw: torch.Tensor, coords: torch.Tensor, batch: int, in_h: int, in_w: int, x_ld: int, stride: int) -> None:
-    """raw [b, ho, wo, 32] fp32 offset_mask_conv output -> b200_dcn_coord records [b, ho, wo, 9, 8] (4-byte words)."""
+    """raw [b, ho, wo, 32] fp32 offset_mask_conv output -> b200_dcn_coord records [b, ho, wo, 9, 4] (4-byte words)."""
     _lib.check(_lib.load().b200_dcn_coords(_lib.ptr(raw), _lib.ptr(coords), batch, in_h, in_w, x_ld, stride,
                                            _lib.current_stream()), "dcn_coords")
 

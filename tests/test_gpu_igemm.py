@@ -214,7 +214,7 @@ def test_dcn_igemm(case):
     n_pad = wp.shape[0]
     sc, sh = ops.pad_vec(scale, n_pad, 1.0), ops.pad_vec(shift, n_pad)
     y = torch.full((b, oh, ow, co), float("nan"), device=dev, dtype=torch.bfloat16)
-    coords = torch.empty(b, oh, ow, 9, 8, device=dev, dtype=torch.int32)
+    coords = torch.empty(b, oh, ow, 9, 4, device=dev, dtype=torch.int32)
     ops.dcn_coords(om, coords, b, h, w, ci, s)
     op = ops.Igemm(ops.IGEMM_DCN, nhwc(x), wp, sc, sh, y, batch=b, in_h=h, in_w=w, in_c=ci, out_c=co, ksize=3,
                    stride=s, flags=ops.EPI_RELU, offsets=coords, name=str(case))
@@ -225,8 +225,9 @@ def test_dcn_igemm(case):
     ops.ref_dcn2d(nhwc(x), om, wp_ref, sc, sh, y2, b, h, w, ci, co, s, ops.EPI_RELU, co)
     torch.cuda.synchronize()
     close(nchw(y2), ref, rel_rms=3e-2)
-    # tensor-core path vs cross-check kernel: same rounding points, only accumulation order differs
-    close(nchw(y), nchw(y2), rel_rms=1e-2, rtol=1e-2)
+    # tensor-core path vs cross-check kernel: the producers blend the corners with packed bf16x2 FMAs (bf16 weights,
+    # one rounding per FMA) where the cross-check kernel blends in fp32, so a few outputs differ by 1-2 bf16 ulps
+    close(nchw(y), nchw(y2), rel_rms=2e-2, rtol=1.6e-2)
 
 
 @pytest.mark.parametrize("case", [(1, 24, 40, 128, 1), (2, 32, 48, 256, 2)], ids=lambda c: "b%d_%dx%d_c%d_s%d" % c)
@@ -246,15 +247,15 @@ def test_offset_conv_coords_epilogue(case):
     raw = torch.empty(b, oh, ow, 32, device=dev, dtype=torch.float32)
     ops.Igemm(ops.IGEMM_CONV, nhwc(x), wp, sc, sh, raw, batch=b, in_h=h, in_w=w, in_c=ci, out_c=32, ksize=3, stride=s,
               flags=ops.EPI_OUT_F32, name="offset-raw")()
-    c_ref = torch.empty(b, oh, ow, 9, 8, device=dev, dtype=torch.int32)
+    c_ref = torch.empty(b, oh, ow, 9, 4, device=dev, dtype=torch.int32)
     ops.dcn_coords(raw, c_ref, b, h, w, ci, s)
-    c_fused = torch.full((b, oh, ow, 9, 8), -7, device=dev, dtype=torch.int32)
+    c_fused = torch.full((b, oh, ow, 9, 4), -7, device=dev, dtype=torch.int32)
     ops.Igemm(ops.IGEMM_CONV, nhwc(x), wp, sc, sh, c_fused, batch=b, in_h=h, in_w=w, in_c=ci, out_c=32, ksize=3, stride=s,
               flags=ops.EPI_DCN_COORDS, out_ld=32, name="offset-coords")()
     torch.cuda.synchronize()
     assert torch.equal(c_fused, c_ref)
-    # records are sane: offsets inside the image, weights in [0, 1], and each tap's weights sum to <= sigmoid(mask)
-    off = c_ref[..., :4]
-    wg = c_ref[..., 4:].view(torch.float32)
-    assert off.min() >= 0 and off.max() < h * w * ci
-    assert wg.min() >= 0 and wg.sum(-1).max() <= 1.0 + 1e-5
+    # records are sane: the clamped 2x2 block lies inside the image, weights in [0, 1], each tap's sum <= sigmoid(mask) <= 1
+    off = c_ref[..., 0]
+    wg = c_ref[..., 1:3].contiguous().view(torch.bfloat16).float()
+    assert off.min() >= 0 and off.max() <= ((h - 2) * w + (w - 2)) * ci
+    assert wg.min() >= 0 and wg.sum(-1).max() <= 1.0 + 1e-2
