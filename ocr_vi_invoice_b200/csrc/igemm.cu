@@ -22,6 +22,7 @@
 #include "internal.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -53,6 +54,7 @@ struct IgemmParams {
     int stg_bufs;          // output staging buffers per active group (2 when a single group must overlap its stores)
     int res_bufs;          // residual ring depth per epilogue group
     int res_bytes;         // bytes of one residual box (16 KB, or 4 KB for the half-resolution RES_UP2 box)
+    int debug;             // B200_DEBUG_EPI experiments (never set in production)
     const __nv_bfloat16* x;
     const float* scale;
     const float* shift;
@@ -317,7 +319,9 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                         const int c0 = (kb - tap * p.cchunks) * kBlockK;
                         int ax = t.x0, ay = t.y0;
                         const CUtensorMap* ma = &tm.a[0];
-                        if (p.ksize == 3) {
+                        if (p.mode == B200_IGEMM_STEM) {
+                            ay += tap;  // tap = block row of the 4x4 window; the view's rows overlap by 3 blocks
+                        } else if (p.ksize == 3) {
                             const int ky = tap / 3, kx = tap - ky * 3;
                             if (p.stride == 1) {
                                 ax += kx - 1;
@@ -498,7 +502,12 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                     if (p.res_tma) mbar_wait(&resfull[slot], (mine_k / p.res_bufs) & 1);
                     tmem_ld_wait();
                     uint4 o[8];
-                    compute(v, 0, 8, o);
+                    if (p.debug & 2) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) o[i] = make_uint4(v[i], v[i + 8], v[i + 16], v[i + 24]);
+                    } else {
+                        compute(v, 0, 8, o);
+                    }
                     // the staging buffer is free once the TMA store that last used it has read it
                     if (issuer) { if (p.stg_bufs == 2) bulk_wait_read1(); else bulk_wait_read0(); }
                     named_bar_sync(1 + eg, kEpiThreads);
@@ -525,7 +534,8 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                 fence_proxy_async_smem();
                 named_bar_sync(1 + eg, kEpiThreads);
                 if (issuer) {
-                    if (p.flags & B200_EPI_SHUFFLE2) {
+                    if (p.debug & 1) {
+                    } else if (p.flags & B200_EPI_SHUFFLE2) {
                         const int sub = col0 / p.shuf_c;
                         tma_store_4d(&tm.out[sub], stg_buf, col0 - sub * p.shuf_c, t.x0, t.y0, t.n);
                     } else {
@@ -831,7 +841,21 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     p.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual);
     p.y = d->y;
     p.offsets = d->offsets;
+    { const char* dbg = getenv("B200_DEBUG_EPI"); p.debug = dbg ? atoi(dbg) : 0; }
     op->gather = (d->mode != B200_IGEMM_CONV);
+    if (d->mode == B200_IGEMM_STEM) {
+        // Preferred stem path: no producer warps at all.  A row (pixel, window row ty) = 64 contiguous bf16 of the packed
+        // buffer starting at block (oy+ty, ox), i.e. a 4-D tensor {64, W/2, H/2+3, N} whose x stride is ONE block
+        // (32 bytes): consecutive rows overlap by three blocks.  TMA only needs 16-byte-multiple strides; if the
+        // driver refuses the overlapping view, fall back to the producer-warp copy.
+        const uint64_t dims[4] = {64, (uint64_t)(d->in_w / 2), (uint64_t)(d->in_h / 2 + 3), (uint64_t)d->batch};
+        const uint64_t pkw = d->in_w / 2 + 3, pkh = d->in_h / 2 + 3;
+        const uint64_t str[3] = {32, pkw * 32, pkh * pkw * 32};
+        const int tw = pick_tile_w(d->in_h / 2, d->in_w / 2, 128);
+        const uint32_t box[4] = {64u, (uint32_t)tw, (uint32_t)(kBlockM / tw), 1u};
+        if (!getenv("B200_STEM_GATHER") && encode_map(&op->tm.a[0], d->x, 4, dims, str, box, "overlapping stem view") == 0)
+            op->gather = 0;
+    }
 
     // bf16 outputs whose channel count is a multiple of 64 go out through swizzled staging + TMA stores
     p.epi_tma = !(d->flags & (B200_EPI_OUT_F32 | B200_EPI_DCN_COORDS)) && (d->out_c % 64) == 0 &&
@@ -904,7 +928,7 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
         const uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)block_n};
         err |= encode_map(&op->tm.b, d->w, 2, dims, str, box, "weights");
     }
-    if (!err && !op->gather) {
+    if (!err && !op->gather && d->mode != B200_IGEMM_STEM) {
         const uint64_t C = d->in_c, W = d->in_w, H = d->in_h, LD = x_ld;
         if (d->stride == 1) {
             err |= encode_nhwc(&op->tm.a[0], d->x, C, W, H, d->batch, LD, 1, 1, W, H * W, p.tile_w, p.tile_h, "activations");

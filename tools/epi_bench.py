@@ -1,0 +1,40 @@
+"""Times single igemm launches at production shapes (development aid, not part of the product)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from ocr_vi_invoice_b200 import ops
+
+def run(name, b, h, w, ci, co, k, s, flags, res=False, shuf=0, iters=20):
+    dev = "cuda"
+    x = torch.randn(b, h, w, ci, device=dev).to(torch.bfloat16)
+    n_pad = ops.choose_n_pad(co)
+    wt = (torch.randn(n_pad, k * k * ci, device=dev) / (k * k * ci) ** 0.5).to(torch.bfloat16)
+    sc, sh = torch.ones(n_pad, device=dev), torch.zeros(n_pad, device=dev)
+    oh, ow = h // s, w // s
+    if shuf:
+        y = torch.empty(b, 2 * oh, 2 * ow, shuf, device=dev, dtype=torch.bfloat16)
+    else:
+        y = torch.empty(b, oh, ow, co, device=dev, dtype=torch.bfloat16)
+    r = torch.randn(b, oh, ow, co, device=dev).to(torch.bfloat16) if res else None
+    op = ops.Igemm(ops.IGEMM_CONV, x, wt, sc, sh, y, batch=b, in_h=h, in_w=w, in_c=ci, out_c=co, ksize=k, stride=s,
+                   flags=flags | (ops.EPI_RES if res else 0), residual=r, res_ld=co if res else 0, shuf_c=shuf, name=name)
+    for _ in range(3):
+        op()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        op()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    byts = x.numel() * 2 + y.numel() * 2 + (r.numel() * 2 if res else 0)
+    print(f"{name:28s} {ms:7.3f} ms  {byts / ms / 1e9:7.2f} TB/s  {op.flops / ms / 1e9:8.1f} TF/s  dbg={os.environ.get('B200_DEBUG_EPI','0')}", flush=True)
+
+if __name__ == "__main__":
+    run("layer1.conv3 64->256 res", 16, 256, 256, 64, 256, 1, 1, ops.EPI_RELU, res=True)
+    run("layer1.conv3 no-res", 16, 256, 256, 64, 256, 1, 1, ops.EPI_RELU)
+    run("convT 64->4x64", 16, 256, 256, 64, 256, 1, 1, ops.EPI_RELU | ops.EPI_SHUFFLE2, shuf=64)
+    run("layer2.conv3 128->512 res", 16, 128, 128, 128, 512, 1, 1, ops.EPI_RELU, res=True)
+    run("layer1.conv1 256->64", 16, 256, 256, 256, 64, 1, 1, ops.EPI_RELU)
+    run("layer1.conv2 3x3 64->64", 16, 256, 256, 64, 64, 3, 1, ops.EPI_RELU)
