@@ -132,7 +132,6 @@ __global__ void __launch_bounds__(256) asf_kernel(const __nv_bfloat16* __restric
     }
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int warps_per_block = blockDim.x >> 5;
     const float sy3 = (h2 > 1) ? static_cast<float>(h3 - 1) / static_cast<float>(h2 - 1) : 0.0f;
     const float sx3 = (w2 > 1) ? static_cast<float>(w3 - 1) / static_cast<float>(w2 - 1) : 0.0f;
     const float sy4 = (h2 > 1) ? static_cast<float>(h4 - 1) / static_cast<float>(h2 - 1) : 0.0f;
@@ -140,13 +139,20 @@ __global__ void __launch_bounds__(256) asf_kernel(const __nv_bfloat16* __restric
     const float sy5 = (h2 > 1) ? static_cast<float>(h5 - 1) / static_cast<float>(h2 - 1) : 0.0f;
     const float sx5 = (w2 > 1) ? static_cast<float>(w5 - 1) / static_cast<float>(w2 - 1) : 0.0f;
     const float b0 = b_att[0], b1 = b_att[1], b2 = b_att[2], b3 = b_att[3];
-    const int64_t total = static_cast<int64_t>(batch) * h2 * w2;
-    for (int64_t pix = static_cast<int64_t>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); pix < total;
-         pix += static_cast<int64_t>(gridDim.x) * warps_per_block) {
-        const int x = static_cast<int>(pix % w2);
-        int64_t r = pix / w2;
-        const int y = static_cast<int>(r % h2);
-        const int n = static_cast<int>(r / h2);
+    // A block walks 8 x 16 pixel tiles (warp = tile row, 16 pixels along x each) so the bilinear taps of p3..p5, which
+    // neighbouring pixels share, are fetched from L2 once per tile and re-read from L1.
+    const int tiles_x = (w2 + 15) / 16, tiles_y = (h2 + 7) / 8;
+    const int64_t ntiles = static_cast<int64_t>(batch) * tiles_x * tiles_y;
+    const int wrow = threadIdx.x >> 5;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+    for (int px = 0; px < 16; ++px) {
+        const int tx = static_cast<int>(tile % tiles_x);
+        const int64_t r = tile / tiles_x;
+        const int tyi = static_cast<int>(r % tiles_y);
+        const int n = static_cast<int>(r / tiles_y);
+        const int x = tx * 16 + px, y = tyi * 8 + wrow;
+        if (x >= w2 || y >= h2) continue;
+        const int64_t pix = (static_cast<int64_t>(n) * h2 + y) * w2 + x;
         float f[4][8];
         unpack8(ldg128(p2 + pix * 256 + lane * 8), f[0]);
         bilinear_ac(p3, n, h3, w3, sy3, sx3, y, x, lane, f[1]);
@@ -298,8 +304,8 @@ extern "C" int b200_asf_fwd(const void* p2, const void* p3, const void* p4, cons
                             int h5, int w5, void* stream) {
     if (!p2 || !p3 || !p4 || !p5 || !w_att || !b_att || !out) return set_error("b200_asf_fwd: null pointer");
     if (batch <= 0 || h2 <= 0 || w2 <= 0) return set_error("b200_asf_fwd: bad shape");
-    const int64_t total = static_cast<int64_t>(batch) * h2 * w2;
-    asf_kernel<<<grid_for(total, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    const int64_t ntiles = static_cast<int64_t>(batch) * ((h2 + 7) / 8) * ((w2 + 15) / 16);
+    asf_kernel<<<grid_for(ntiles, 1), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const __nv_bfloat16*>(p2), reinterpret_cast<const __nv_bfloat16*>(p3),
         reinterpret_cast<const __nv_bfloat16*>(p4), reinterpret_cast<const __nv_bfloat16*>(p5), w_att, b_att,
         reinterpret_cast<__nv_bfloat16*>(out), batch, h2, w2, h3, w3, h4, w4, h5, w5);

@@ -1,0 +1,106 @@
+"""Detection driver around the drop-in model: double-buffered host->device staging, batched GPU post-processing,
+and the data-parallel sharding / host gather used on a multi-GPU box.
+
+The reference's production caller (src/pipeline/pipeline2.py:279-328) is a serial batch-1 loop:
+H2D -> forward -> D2H of the whole map -> CPU post-processing.  Images are independent, so on N GPUs each rank
+(one process per GPU) takes a shard of the image indices, runs the same loop on its own device with no collective,
+and rank 0 gathers the variable-length (image_id, boxes, scores) lists on the host.
+"""
+from __future__ import annotations
+
+from typing import Iterable, Iterator, List, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .model.det.dbnet import DBNetPP
+from .postprocess import DBPostProcessor
+
+Result = Tuple[List[np.ndarray], List[float]]
+
+
+def shard_indices(n_items: int, rank: int, world: int) -> range:
+    """Contiguous shard of `range(n_items)` for `rank`; the first n_items % world ranks get one extra item."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} not in [0, {world})")
+    base, extra = divmod(n_items, world)
+    start = rank * base + min(rank, extra)
+    return range(start, start + base + (1 if rank < extra else 0))
+
+
+def gather_results(local: Sequence[Tuple[int, Result]], group=None, dst: int = 0):
+    """Host gather of per-rank [(image_id, (boxes, scores))] lists; returns the merged, id-sorted list on `dst`
+    (None elsewhere).  Works on a gloo (CPU) or nccl group; single-process runs return the input sorted."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return sorted(local, key=lambda r: r[0])
+    world = dist.get_world_size(group)
+    bucket = [None] * world
+    dist.all_gather_object(bucket, list(local), group=group)
+    if dist.get_rank(group) != dst:
+        return None
+    merged = [item for part in bucket for item in part]
+    ids = [i for i, _ in merged]
+    if len(set(ids)) != len(ids):
+        raise RuntimeError("gather_results: an image id was produced by more than one rank")
+    return sorted(merged, key=lambda r: r[0])
+
+
+class Detector:
+    """model + post-processor with pinned staging and H2D copies overlapped with compute."""
+
+    def __init__(self, model: DBNetPP, post: DBPostProcessor, device=None, use_cuda_graph: bool = True):
+        self.device = torch.device(device) if device is not None else next(model.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("Detector needs a CUDA device (no CPU fallback)")
+        self.model, self.post = model, post
+        model.use_cuda_graph = use_cuda_graph
+        model.output_maps = ("binary",)  # the box list only needs the probability map (pipeline2.py:318)
+        self._copy_stream = torch.cuda.Stream(device=self.device)
+        self._dev_buf = [None, None]
+        self._consumed = [None, None]  # per slot: event after which the main stream no longer reads the slot
+
+    def _stage(self, host: torch.Tensor, slot: int) -> Tuple[torch.Tensor, torch.cuda.Event]:
+        """Async H2D of one batch into device slot `slot` on the copy stream."""
+        if not host.is_pinned():
+            host = host.pin_memory()
+        buf = self._dev_buf[slot]
+        if buf is None or buf.shape != host.shape:
+            buf = torch.empty(host.shape, dtype=torch.float32, device=self.device)
+            self._dev_buf[slot] = buf
+        ready = torch.cuda.Event()
+        with torch.cuda.stream(self._copy_stream):
+            if self._consumed[slot] is not None:
+                self._copy_stream.wait_event(self._consumed[slot])
+            buf.copy_(host, non_blocking=True)
+            ready.record(self._copy_stream)
+        return buf, ready
+
+    def detect(self, host_batch: torch.Tensor) -> List[Result]:
+        """One batch: H2D, forward, GPU post-processing, D2H of the box records."""
+        return next(self.detect_stream([host_batch]))
+
+    def detect_stream(self, batches: Iterable[torch.Tensor]) -> Iterator[List[Result]]:
+        """Yields per-batch results; the H2D copy of batch i+1 overlaps the kernels of batch i."""
+        it = iter(batches)
+        try:
+            cur = self._stage(next(it), 0)
+        except StopIteration:
+            return
+        slot = 0
+        with torch.cuda.device(self.device):
+            main = torch.cuda.current_stream(self.device)
+            while cur is not None:
+                x, ready = cur
+                main.wait_event(ready)
+                out = self.model(x)  # copies x into the plan's input buffer, then replays the captured graph
+                ev = torch.cuda.Event()
+                ev.record(main)
+                self._consumed[slot] = ev
+                try:
+                    cur = self._stage(next(it), slot ^ 1)  # overlaps the forward just queued
+                    slot ^= 1
+                except StopIteration:
+                    cur = None
+                recs, _ = self.post.fetch(self.post.run_device(out["binary"][:, 0], want_labels=False))
+                yield [self.post.records_to_boxes(r) for r in recs]

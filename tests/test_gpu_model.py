@@ -241,3 +241,27 @@ def test_dcn_false_variant_runs():
     ref = dbo.dbnet_forward(sd, x, dcn=False)
     torch.cuda.synchronize()
     assert rel_rms(out["bin_logits"].cpu(), ref["bin_logits"]) < 0.06
+
+
+def test_detector_stream_matches_direct_calls():
+    """pipeline.Detector (double-buffered H2D, graph replay) returns the same boxes as model + post called directly."""
+    from ocr_vi_invoice_b200.pipeline import Detector
+    from ocr_vi_invoice_b200.postprocess import DBPostProcessor
+    from ocr_vi_invoice_b200.synth import synthetic_batch
+    m, _ = _model(9)
+    post = DBPostProcessor(thresh=0.3, box_thresh=0.5, unclip_ratio=1.6)
+    batches = [torch.from_numpy(synthetic_batch(2, 160, 192, seed=s)) for s in range(4)]
+    direct = []
+    for hb in batches:
+        out = m(hb.cuda())
+        direct.append(post.batch(out["binary"]))
+    det = Detector(m, DBPostProcessor(thresh=0.3, box_thresh=0.5, unclip_ratio=1.6), use_cuda_graph=True)
+    streamed = list(det.detect_stream(batches))
+    assert len(streamed) == 4
+    for a, b in zip(direct, streamed):
+        assert len(a) == len(b) == 2
+        for (ba, sa), (bb, sb) in zip(a, b):
+            assert len(ba) == len(bb) and sa == sb
+            assert all(np.array_equal(x, y) for x, y in zip(ba, bb))
+    m.use_cuda_graph = False
+    m.output_maps = ("binary", "thresh", "thresh_binary", "bin_logits", "thresh_logits")
