@@ -230,7 +230,7 @@ def test_dcn_igemm(case):
     diff = (nchw(y) - nchw(y2)).float()
     rms = nchw(y2).float().pow(2).mean().sqrt().item()
     assert diff.pow(2).mean().sqrt().item() < 5e-3 * rms, "bf16x2 blend noise above 0.5% of the output rms"
-    assert not (diff.abs() > 3e-2 * rms + 2.0 ** -7 * nchw(y2).float().abs()).any()  # noise + one bf16 ulp
+    assert not (diff.abs() > 4e-2 * rms + 2.0 ** -6 * nchw(y2).float().abs()).any()  # blend noise + two bf16 ulps
 
 
 @pytest.mark.parametrize("case", [(1, 24, 40, 128, 1), (2, 32, 48, 256, 2)], ids=lambda c: "b%d_%dx%d_c%d_s%d" % c)
