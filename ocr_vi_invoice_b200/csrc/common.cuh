@@ -41,15 +41,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a pipeline bug turns into a trap (-> CUDA error on the host) instead of a hung GPU.
+// (No printf here: its argument buffer would cost a local-memory store on every fast-path wait.)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000ll) {  // ~2 s at 2 GHz
-            printf("b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
-                   threadIdx.x, smem_u32(bar), parity);
-            __trap();
-        }
+        if (clock64() - t0 > 4000000000ll) __trap();  // ~2 s at 2 GHz
     }
 }
 
@@ -173,6 +170,16 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
+}
+
+// 32-bit shared-window addressing: one register per address instead of a generic 64-bit pointer
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
 }
 
 // ---------------------------------------------------------------------------------- small helpers

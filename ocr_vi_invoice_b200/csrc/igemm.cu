@@ -35,11 +35,13 @@ constexpr int kGatherWarps = 16;                // producer warps of the gather 
 constexpr int kMaxStages = 8;
 constexpr int kMaxSmem = 227 * 1024;
 constexpr int kEpiThreads = 128;                // one epilogue group = 4 warps = the 4 TMEM lane quarters
-constexpr int kMaxResBufs = 8;
-// The TMA-fed conv kernel runs two epilogue groups (alternating 64-column chunks): its 1x1 layers are
-// epilogue-latency-bound with one warp per scheduler.  The gather kernel keeps one group (threads go to producers).
-__host__ __device__ constexpr int epi_groups(bool gather) { return gather ? 1 : 2; }
-__host__ __device__ constexpr int base_warps(bool gather) { return 2 + 4 * epi_groups(gather); }
+constexpr int kMaxEpiBufs = 12;
+// The TMA-fed conv kernel runs four epilogue groups (64-column chunks round-robin): its 1x1 layers are HBM-bound and
+// their epilogue math is latency-bound with one warp per scheduler.  The gather kernel keeps one group (its threads
+// go to the producers).  Warp 2 is the epilogue DMA warp: it alone issues the residual loads and the output stores.
+__host__ __device__ constexpr int epi_groups(bool gather) { return gather ? 1 : 4; }
+__host__ __device__ constexpr int kEpiWarp0 = 3;
+__host__ __device__ constexpr int base_warps(bool gather) { return kEpiWarp0 + 4 * epi_groups(gather); }
 
 struct IgemmParams {
     int mode, batch, in_h, in_w, in_c, out_h, out_w, out_c;
@@ -50,11 +52,10 @@ struct IgemmParams {
     int pk_h, pk_w;        // STEM: rows / columns of the packed space-to-depth buffer
     int x_ld;              // elements between consecutive input pixels
     int epi_tma, res_tma;  // epilogue stores through TMA / residual prefetched through TMA
-    int epi_active;        // epilogue groups that take chunks (1 for compute-bound layers: frees staging smem)
-    int stg_bufs;          // output staging buffers per active group (2 when a single group must overlap its stores)
-    int res_bufs;          // residual ring depth per epilogue group
+    int epi_active;        // epilogue groups that take chunks (the others only keep the TMEM hand-shake going)
+    int epi_bufs;          // 16 KB epilogue buffers (residual lands in them, the result is written in place, TMA stores it)
+    int ss_shared;         // one scale/shift copy for the CTA (single n-block) instead of one per group
     int res_bytes;         // bytes of one residual box (16 KB, or 4 KB for the half-resolution RES_UP2 box)
-    int debug;             // B200_DEBUG_EPI experiments (never set in production)
     const __nv_bfloat16* x;
     const float* scale;
     const float* shift;
@@ -73,14 +74,15 @@ struct TmapPack {
 struct SmemLayout {
     uint8_t* a;
     uint8_t* b;
-    uint8_t* stg;  // one 16 KB output staging buffer per epilogue group
-    uint8_t* rsd;  // groups x res_bufs residual boxes (16 KB stride)
-    float* ss;     // per group: scale[256] then shift[256] of the current n-block
+    uint8_t* epi;  // epi_bufs x 16 KB
+    float* ss;     // scale[256] then shift[256] of the current n-block (one copy, or one per epilogue group)
     uint64_t* full;
     uint64_t* empty;
     uint64_t* tfull;
     uint64_t* tempty;
-    uint64_t* resfull;  // [group][kMaxResBufs]
+    uint64_t* res_full;   // [kMaxEpiBufs] residual box landed in the buffer
+    uint64_t* slot_free;  // [kMaxEpiBufs] the store that used the buffer has read it (layers without residual)
+    uint64_t* out_ready;  // [kMaxEpiBufs] the epilogue group has written its result
     uint32_t* tmem_slot;
 };
 
@@ -91,17 +93,18 @@ __device__ __forceinline__ SmemLayout carve(uint8_t* raw, const IgemmParams& p) 
     SmemLayout s;
     s.a = base;
     s.b = s.a + p.stages * kABytes;
-    s.stg = s.b + p.stages * p.block_n * 128;
-    s.rsd = s.stg + (p.epi_tma ? p.epi_active * p.stg_bufs * kABytes : 0);
-    uint8_t* rest = s.rsd + (p.res_tma ? p.epi_active * p.res_bufs * kABytes : 0);
+    s.epi = s.b + p.stages * p.block_n * 128;
+    uint8_t* rest = s.epi + p.epi_bufs * kABytes;
     s.ss = reinterpret_cast<float*>(rest);
-    uint8_t* bars = rest + G * 2048;
+    uint8_t* bars = rest + (p.ss_shared ? 1 : G) * 2048;
     s.full = reinterpret_cast<uint64_t*>(bars);
     s.empty = s.full + kMaxStages;
     s.tfull = s.empty + kMaxStages;
     s.tempty = s.tfull + 2;
-    s.resfull = s.tempty + 2;
-    s.tmem_slot = reinterpret_cast<uint32_t*>(s.resfull + 2 * kMaxResBufs);
+    s.res_full = s.tempty + 2;
+    s.slot_free = s.res_full + kMaxEpiBufs;
+    s.out_ready = s.slot_free + kMaxEpiBufs;
+    s.tmem_slot = reinterpret_cast<uint32_t*>(s.out_ready + kMaxEpiBufs);
     return s;
 }
 
@@ -292,12 +295,22 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                 mbar_init(&sm.tfull[a], 1);
                 mbar_init(&sm.tempty[a], 4 * G);
             }
-            for (int a = 0; a < 2 * kMaxResBufs; ++a) mbar_init(&sm.resfull[a], 1);
+            for (int a = 0; a < kMaxEpiBufs; ++a) {
+                mbar_init(&sm.res_full[a], 1);
+                mbar_init(&sm.slot_free[a], 1);
+                mbar_init(&sm.out_ready[a], 4);
+            }
             fence_mbar_init();
         }
         __syncwarp();
         tmem_alloc(sm.tmem_slot, tmem_cols);
         tmem_relinquish();
+    }
+    if (p.epi_tma && p.ss_shared) {  // single n-block: stage its scale / shift once for every epilogue group
+        for (int i = threadIdx.x; i < p.block_n; i += blockDim.x) {
+            sm.ss[i] = __ldg(p.scale + i);
+            sm.ss[256 + i] = __ldg(p.shift + i);
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -369,49 +382,71 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                 umma_commit(&sm.tfull[as]);
             }
         }
+    } else if (warp == 2) {
+        // ===================================================================== epilogue DMA warp
+        // One thread owns every epilogue TMA transfer.  Chunk g (CTA-wide order) uses buffer g % B.  After the store of
+        // chunk g is queued, the store of chunk g-1 has surely read its buffer (wait_group.read 1), so that buffer
+        // is recycled: the residual box of chunk g-1+B is loaded into it (B-1 chunks of prefetch), or it is marked free.
+        if (lane == 0 && p.epi_tma) {
+            const int B = p.epi_bufs, L = (B > 1) ? 1 : 0;
+            const bool up2 = (p.flags & B200_EPI_RES_UP2) != 0;
+            int ld_tile = blockIdx.x, ld_chunk = 0;
+            auto issue_load = [&](int slot) {
+                if (ld_tile >= p.num_tiles) return;
+                const TileCoord t = decode_tile(p, ld_tile);
+                mbar_arrive_expect_tx(&sm.res_full[slot], p.res_bytes);
+                tma_load_4d(sm.epi + slot * kABytes, &tm.res, &sm.res_full[slot], t.nb * p.block_n + ld_chunk * 64,
+                            up2 ? (t.x0 >> 1) : t.x0, up2 ? (t.y0 >> 1) : t.y0, t.n);
+                if (++ld_chunk == chunks_of(p, t.nb)) { ld_chunk = 0; ld_tile += gridDim.x; }
+            };
+            if (p.res_tma)
+                for (int i = 0; i < B; ++i) issue_load(i);
+            int g = 0, slot = 0, rslot = 0;
+            uint32_t par = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const TileCoord t = decode_tile(p, tile);
+                const int nchunks = chunks_of(p, t.nb);
+                for (int c = 0; c < nchunks; ++c, ++g) {
+                    mbar_wait(&sm.out_ready[slot], par);
+                    const int col0 = t.nb * p.block_n + c * 64;
+                    if (p.flags & B200_EPI_SHUFFLE2) {
+                        const int sub = col0 / p.shuf_c;
+                        tma_store_4d(&tm.out[sub], sm.epi + slot * kABytes, col0 - sub * p.shuf_c, t.x0, t.y0, t.n);
+                    } else {
+                        tma_store_4d(&tm.out[0], sm.epi + slot * kABytes, col0, t.x0, t.y0, t.n);
+                    }
+                    bulk_commit();
+                    if (g >= L) {
+                        if (L) bulk_wait_read1(); else bulk_wait_read0();
+                        if (p.res_tma) issue_load(rslot); else mbar_arrive(&sm.slot_free[rslot]);
+                        if (++rslot == B) rslot = 0;
+                    }
+                    if (++slot == B) { slot = 0; par ^= 1; }
+                }
+            }
+            bulk_wait_all();
+        }
     } else if (warp < kBaseWarps) {
         // ===================================================================== epilogue (G groups of 4 warps)
-        const int eg = (warp - 2) >> 2;  // epilogue group
-        const int quarter = warp & 3;    // TMEM lane quarter this warp may touch
+        const int eg = (warp - kEpiWarp0) >> 2;  // epilogue group
+        const int quarter = warp & 3;            // TMEM lane quarter this warp may touch
         const int row = quarter * 32 + lane;
-        const int et = ((warp - 2) & 3) * 32 + lane;  // thread index inside the group
+        const int et = ((warp - kEpiWarp0) & 3) * 32 + lane;  // thread index inside the group
         const int ty = row / p.tile_w;
         const int tx = row - ty * p.tile_w;
-        const bool issuer = (et == 0);
         const uint32_t swz = static_cast<uint32_t>(row & 7);
-        const int GA = p.epi_active;  // groups that take work; the others only keep the TMEM hand-shake going
-        uint8_t* const rsd_base = sm.rsd + eg * p.res_bufs * kABytes;
-        uint64_t* const resfull = sm.resfull + eg * kMaxResBufs;
-        float* const ss = sm.ss + eg * 512;
+        const int GA = p.epi_active, B = p.epi_bufs;
+        float* const ss = sm.ss + (p.ss_shared ? 0 : eg * 512);
         // residual row this thread reads: its own pixel, or (y>>1, x>>1) of the half-resolution RES_UP2 box
         const bool up2 = (p.flags & B200_EPI_RES_UP2) != 0;
         const int rrow = up2 ? ((ty >> 1) * (p.tile_w >> 1) + (tx >> 1)) : row;
         const uint32_t rswz = static_cast<uint32_t>(rrow & 7);
-        // residual prefetch cursor (issuer only): walks this group's (tile, chunk) sequence res_bufs chunks ahead
-        int pf_tile = blockIdx.x, pf_chunk = 0, pf_g = 0, pf_count = 0;
-        auto issue_res = [&]() {
-            while (pf_tile < p.num_tiles) {
-                const TileCoord t = decode_tile(p, pf_tile);
-                const bool mine = (pf_g % GA) == eg;
-                const int c = pf_chunk;
-                ++pf_g;
-                if (++pf_chunk == chunks_of(p, t.nb)) { pf_chunk = 0; pf_tile += gridDim.x; }
-                if (mine) {
-                    const int slot = pf_count % p.res_bufs;
-                    mbar_arrive_expect_tx(&resfull[slot], p.res_bytes);
-                    tma_load_4d(rsd_base + slot * kABytes, &tm.res, &resfull[slot], t.nb * p.block_n + c * 64,
-                                up2 ? (t.x0 >> 1) : t.x0, up2 ? (t.y0 >> 1) : t.y0, t.n);
-                    ++pf_count;
-                    return;
-                }
-            }
-        };
-        if (p.res_tma && issuer && eg < GA)
-            for (int i = 0; i < p.res_bufs; ++i) issue_res();
         int it = 0;
-        int g = 0;       // global 64-column chunk counter of this CTA (all groups count the same sequence)
-        int mine_k = 0;  // chunks this group has processed (residual ring position)
-        int ss_nb = -1;  // n-block whose scale/shift currently sit in smem
+        int g = 0;          // CTA-wide 64-column chunk counter (every group counts the same sequence)
+        int next_mine = eg;  // next chunk index this group takes
+        int slot = eg;       // its buffer (g % B) and the parity of that buffer's barriers ((g / B) & 1); GA <= B
+        uint32_t par = 0;
+        int ss_nb = p.ss_shared ? 0 : -1;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const TileCoord t = decode_tile(p, tile);
             const int as = it & 1;
@@ -431,127 +466,87 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                         if (valid) epilogue_direct32(p, v, t.nb * p.block_n + c, t.n, oy, ox);
                     }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.tempty[as]);
-                continue;
-            }
-            if (eg >= GA) {  // idle group of a compute-bound layer
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.tempty[as]);
-                continue;
-            }
-            const int nchunks = chunks_of(p, t.nb);
-            if (ss_nb != t.nb) {  // (re)load this n-block's scale / shift into the group's smem copy
-                named_bar_sync(1 + eg, kEpiThreads);  // nobody still reads the old copy
-                for (int i = et; i < p.block_n; i += kEpiThreads) {
-                    ss[i] = __ldg(p.scale + t.nb * p.block_n + i);
-                    ss[256 + i] = __ldg(p.shift + t.nb * p.block_n + i);
+            } else if (eg < GA) {
+                const int nchunks = chunks_of(p, t.nb);
+                if (ss_nb != t.nb) {  // (re)load this n-block's scale / shift into the group's smem copy
+                    named_bar_sync(1 + eg, kEpiThreads);  // nobody still reads the old copy
+                    for (int i = et; i < p.block_n; i += kEpiThreads) {
+                        ss[i] = __ldg(p.scale + t.nb * p.block_n + i);
+                        ss[256 + i] = __ldg(p.shift + t.nb * p.block_n + i);
+                    }
+                    named_bar_sync(1 + eg, kEpiThreads);
+                    ss_nb = t.nb;
                 }
-                named_bar_sync(1 + eg, kEpiThreads);
-                ss_nb = t.nb;
-            }
-            for (int c = 0; c < nchunks; ++c, ++g) {
-                if ((g % GA) != eg) continue;
-                const int col0 = t.nb * p.block_n + c * 64;
-                const int slot = mine_k % p.res_bufs;
-                uint8_t* const stg_buf = sm.stg + (eg * p.stg_bufs + (p.stg_bufs == 2 ? (mine_k & 1) : 0)) * kABytes;
-                uint8_t* const stg = stg_buf + row * 128;
-                const uint8_t* rsd = rsd_base + slot * kABytes + rrow * 128;
-                // pieces [p0, p0+np) of the chunk: scale/shift (+ residual) (+ ReLU) -> packed bf16, 8 columns per piece
-                auto compute = [&](const uint32_t* vv, int p0, int np, uint4* oo) {
+                for (int c = 0; c < nchunks; ++c, ++g) {
+                    if (g != next_mine) continue;
+                    next_mine += GA;
+                    const uint32_t buf = smem_u32(sm.epi) + static_cast<uint32_t>(slot) * kABytes;
+                    const uint32_t mine = buf + static_cast<uint32_t>(row) * 128;
+                    const uint32_t rsd = buf + static_cast<uint32_t>(rrow) * 128;
+                    if (p.res_tma) mbar_wait(&sm.res_full[slot], par);
+                    else mbar_wait(&sm.slot_free[slot], par ^ 1);
+                    uint4 rup[8];
+                    if (up2) {  // the 4 KB half-resolution box is shared by four pixels: read it before anyone overwrites
 #pragma unroll
-                    for (int j = 0; j < np; ++j) {
-                        const int piece = p0 + j;
-                        float f[8];
-                        const float4 sc0 = *reinterpret_cast<const float4*>(ss + c * 64 + piece * 8);
-                        const float4 sc1 = *reinterpret_cast<const float4*>(ss + c * 64 + piece * 8 + 4);
-                        const float4 sh0 = *reinterpret_cast<const float4*>(ss + 256 + c * 64 + piece * 8);
-                        const float4 sh1 = *reinterpret_cast<const float4*>(ss + 256 + c * 64 + piece * 8 + 4);
-                        f[0] = fmaf(__uint_as_float(vv[j * 8 + 0]), sc0.x, sh0.x);
-                        f[1] = fmaf(__uint_as_float(vv[j * 8 + 1]), sc0.y, sh0.y);
-                        f[2] = fmaf(__uint_as_float(vv[j * 8 + 2]), sc0.z, sh0.z);
-                        f[3] = fmaf(__uint_as_float(vv[j * 8 + 3]), sc0.w, sh0.w);
-                        f[4] = fmaf(__uint_as_float(vv[j * 8 + 4]), sc1.x, sh1.x);
-                        f[5] = fmaf(__uint_as_float(vv[j * 8 + 5]), sc1.y, sh1.y);
-                        f[6] = fmaf(__uint_as_float(vv[j * 8 + 6]), sc1.z, sh1.z);
-                        f[7] = fmaf(__uint_as_float(vv[j * 8 + 7]), sc1.w, sh1.w);
-                        if (p.res_tma) {
-                            const uint4 u =
-                                *reinterpret_cast<const uint4*>(rsd + ((static_cast<uint32_t>(piece) ^ rswz) << 4));
-                            f[0] += bf16lo(u.x); f[1] += bf16hi(u.x);
-                            f[2] += bf16lo(u.y); f[3] += bf16hi(u.y);
-                            f[4] += bf16lo(u.z); f[5] += bf16hi(u.z);
-                            f[6] += bf16lo(u.w); f[7] += bf16hi(u.w);
-                        }
-                        if (p.flags & B200_EPI_RELU) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.0f);
-                        }
-                        oo[j].x = pack_bf16(f[0], f[1]);
-                        oo[j].y = pack_bf16(f[2], f[3]);
-                        oo[j].z = pack_bf16(f[4], f[5]);
-                        oo[j].w = pack_bf16(f[6], f[7]);
+                        for (int i = 0; i < 8; ++i)
+                            rup[i] = lds128(rsd + ((static_cast<uint32_t>(i) ^ rswz) << 4));
+                        named_bar_sync(1 + eg, kEpiThreads);
                     }
-                };
-                if constexpr (!kGather) {
-                    uint32_t v[64];
-                    tmem_ld32(taddr + c * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-                    tmem_ld32(taddr + c * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-                    if (p.res_tma) mbar_wait(&resfull[slot], (mine_k / p.res_bufs) & 1);
-                    tmem_ld_wait();
-                    uint4 o[8];
-                    if (p.debug & 2) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) o[i] = make_uint4(v[i], v[i + 8], v[i + 16], v[i + 24]);
-                    } else {
-                        compute(v, 0, 8, o);
-                    }
-                    // the staging buffer is free once the TMA store that last used it has read it
-                    if (issuer) { if (p.stg_bufs == 2) bulk_wait_read1(); else bulk_wait_read0(); }
-                    named_bar_sync(1 + eg, kEpiThreads);
-#pragma unroll
-                    for (int piece = 0; piece < 8; ++piece)
-                        *reinterpret_cast<uint4*>(stg + ((static_cast<uint32_t>(piece) ^ swz) << 4)) = o[piece];
-                } else {
-                    // register-lean variant (the gather kernel runs 22 warps): two 32-column halves
-                    if (issuer) { if (p.stg_bufs == 2) bulk_wait_read1(); else bulk_wait_read0(); }
-                    named_bar_sync(1 + eg, kEpiThreads);
-                    if (p.res_tma) mbar_wait(&resfull[slot], (mine_k / p.res_bufs) & 1);
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
+                    for (int h = 0; h < 2; ++h) {  // two 32-column halves (register-lean: 19-23 warps per CTA)
                         uint32_t v[32];
                         tmem_ld32(taddr + c * 64 + h * 32, v);
                         tmem_ld_wait();
-                        uint4 o[4];
-                        compute(v, h * 4, 4, o);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            *reinterpret_cast<uint4*>(stg + ((static_cast<uint32_t>(h * 4 + j) ^ swz) << 4)) = o[j];
+                        for (int j = 0; j < 4; ++j) {  // 8 columns = one 16-byte piece of the pixel's 128-byte row
+                            const int piece = h * 4 + j;
+                            const uint32_t so = (static_cast<uint32_t>(piece) ^ swz) << 4;
+                            float f[8];
+                            const float4 sc0 = *reinterpret_cast<const float4*>(ss + c * 64 + piece * 8);
+                            const float4 sc1 = *reinterpret_cast<const float4*>(ss + c * 64 + piece * 8 + 4);
+                            const float4 sh0 = *reinterpret_cast<const float4*>(ss + 256 + c * 64 + piece * 8);
+                            const float4 sh1 = *reinterpret_cast<const float4*>(ss + 256 + c * 64 + piece * 8 + 4);
+                            f[0] = fmaf(__uint_as_float(v[j * 8 + 0]), sc0.x, sh0.x);
+                            f[1] = fmaf(__uint_as_float(v[j * 8 + 1]), sc0.y, sh0.y);
+                            f[2] = fmaf(__uint_as_float(v[j * 8 + 2]), sc0.z, sh0.z);
+                            f[3] = fmaf(__uint_as_float(v[j * 8 + 3]), sc0.w, sh0.w);
+                            f[4] = fmaf(__uint_as_float(v[j * 8 + 4]), sc1.x, sh1.x);
+                            f[5] = fmaf(__uint_as_float(v[j * 8 + 5]), sc1.y, sh1.y);
+                            f[6] = fmaf(__uint_as_float(v[j * 8 + 6]), sc1.z, sh1.z);
+                            f[7] = fmaf(__uint_as_float(v[j * 8 + 7]), sc1.w, sh1.w);
+                            if (p.res_tma) {
+                                uint4 u;
+                                if (up2) u = rup[piece];
+                                else u = lds128(mine + so);  // residual of this very pixel, in place
+                                f[0] += bf16lo(u.x); f[1] += bf16hi(u.x);
+                                f[2] += bf16lo(u.y); f[3] += bf16hi(u.y);
+                                f[4] += bf16lo(u.z); f[5] += bf16hi(u.z);
+                                f[6] += bf16lo(u.w); f[7] += bf16hi(u.w);
+                            }
+                            if (p.flags & B200_EPI_RELU) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.0f);
+                            }
+                            uint4 o;
+                            o.x = pack_bf16(f[0], f[1]);
+                            o.y = pack_bf16(f[2], f[3]);
+                            o.z = pack_bf16(f[4], f[5]);
+                            o.w = pack_bf16(f[6], f[7]);
+                            sts128(mine + so, o);
+                        }
                     }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.out_ready[slot]);
+                    slot += GA;
+                    if (slot >= B) { slot -= B; par ^= 1; }
                 }
-                fence_proxy_async_smem();
-                named_bar_sync(1 + eg, kEpiThreads);
-                if (issuer) {
-                    if (p.debug & 1) {
-                    } else if (p.flags & B200_EPI_SHUFFLE2) {
-                        const int sub = col0 / p.shuf_c;
-                        tma_store_4d(&tm.out[sub], stg_buf, col0 - sub * p.shuf_c, t.x0, t.y0, t.n);
-                    } else {
-                        tma_store_4d(&tm.out[0], stg_buf, col0, t.x0, t.y0, t.n);
-                    }
-                    bulk_commit();
-                    if (p.res_tma) issue_res();  // every thread is past the barrier: residual slot `slot` is free
-                }
-                ++mine_k;
             }
-            // accumulator fully read by this warp: hand the TMEM buffer back to the MMA warp
+            // accumulator fully read by this warp (or not needed): hand the TMEM buffer back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.tempty[as]);
         }
-        if (p.epi_tma && issuer) bulk_wait_all();
     } else if (kGather) {
         // ===================================================================== gather producers (16 warps)
         constexpr int kPasses = kBlockM / (kGatherWarps * 4);  // 2: a pass = 64 rows, 8 lanes x 16 B per row
@@ -622,6 +617,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                     dat[0][2] = ldg128(b0 + rs);
                     dat[0][3] = ldg128(b0 + rs + cs);
                 }
+                const uint32_t a_base = smem_u32(sm.a);
                 int tap0 = 0;                    // tap of k-block kb0 (0, 3 or 6)
                 const __nv_bfloat16* src = img;  // channel chunk of k-block kb0
                 for (int kb0 = 0; kb0 < p.k_blocks; kb0 += 3) {
@@ -661,7 +657,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                         res.w = B200_BLEND2(w);
 #undef B200_BLEND2
                         if (q == 0) mbar_wait(&sm.empty[s], ph ^ 1);
-                        *reinterpret_cast<uint4*>(sm.a + s * kABytes + soff[q]) = res;
+                        sts128(a_base + static_cast<uint32_t>(s) * kABytes + soff[q], res);
                         if (q == 1) {
                             fence_proxy_async_smem();
                             __syncwarp();
@@ -841,7 +837,6 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     p.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual);
     p.y = d->y;
     p.offsets = d->offsets;
-    { const char* dbg = getenv("B200_DEBUG_EPI"); p.debug = dbg ? atoi(dbg) : 0; }
     op->gather = (d->mode != B200_IGEMM_CONV);
     if (d->mode == B200_IGEMM_STEM) {
         // Preferred stem path: no producer warps at all.  A row (pixel, window row ty) = 64 contiguous bf16 of the packed
@@ -874,41 +869,51 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     const int G = epi_groups(op->gather);
     const int b_bytes = block_n * 128;
     const int stage_bytes = kABytes + b_bytes;
-    // compute-bound layers (long K loop) hide a single epilogue group behind the double-buffered accumulator
-    p.epi_active = (G == 2 && p.k_blocks < 8) ? 2 : 1;
-    p.stg_bufs = (p.epi_active == 1 && d->mode != B200_IGEMM_DCN) ? 2 : 1;  // DCN: long K loop, small carve-out
-    const int GA = p.epi_active;
-    const int fixed = 1024 /*alignment*/ + G * 2048 /*scale+shift*/ + 512 /*barriers*/ +
-                      (p.epi_tma ? GA * p.stg_bufs * kABytes : 0);
+    p.ss_shared = (p.num_n_blocks == 1) ? 1 : 0;
+    const int fixed = 1024 /*alignment*/ + 1024 /*barriers*/ + (p.ss_shared ? 1 : G) * 2048 /*scale+shift*/;
     // The DCN gather lives on L1 hits (K ordered chunk-major), so it keeps its carve-out <= 132 KB and leaves the
     // rest of the 256 KB to L1; everything else may use the full 227 KB opt-in.
     const int cap = (d->mode == B200_IGEMM_DCN) ? 131 * 1024 : kMaxSmem;
-    int stages, res_bufs = 0;
-    if (p.res_tma) {
-        // HBM-bound layers: a few mainloop stages, the rest of the memory prefetches residual boxes
-        stages = p.k_blocks + 1;
-        if (stages < 2) stages = 2;
-        if (stages > 3) stages = 3;
-        while (stages > 2 && fixed + stages * stage_bytes + GA * 2 * kABytes > cap) --stages;
-        res_bufs = (cap - fixed - stages * stage_bytes) / (GA * kABytes);
-        if (res_bufs > kMaxResBufs) res_bufs = kMaxResBufs;
-        if (res_bufs < 1) {
-            delete op;
-            return set_error("igemm: not enough shared memory for the residual ring");
-        }
-        const int spare = (cap - fixed - GA * res_bufs * kABytes) / stage_bytes;  // give leftovers back to the mainloop
-        if (spare > stages) stages = spare > kMaxStages ? kMaxStages : spare;
-    } else {
+    int stages, bufs = 0, ga = 1;
+    if (!p.epi_tma) {
         stages = (cap - fixed) / stage_bytes;
+    } else {
+        // Split the shared memory between mainloop stages and epilogue buffers by where the time goes:
+        // mainloop ~ k_blocks * 2 * block_n cycles per tile (tcgen05 issue rate), epilogue ~ 1600 cycles per 64-column
+        // chunk and group.  Enough groups to keep up with the mainloop, one buffer per group plus one draining (plus
+        // two more of residual prefetch), the rest to the pipeline stages.
+        const int chunks = (block_n < d->out_c ? block_n : d->out_c) / 64;
+        const int main_clk = p.k_blocks * 2 * block_n, epi_clk = chunks * 1600;
+        ga = (epi_clk + main_clk - 1) / main_clk;
+        if (ga > G) ga = G;
+        if (ga < 1) ga = 1;
+        const int min_stages = p.k_blocks >= 4 ? 3 : 2;
+        bufs = (ga == 1 && !p.res_tma) ? 1 : ga + 1 + (p.res_tma ? 2 : 0);
+        stages = (cap - fixed - bufs * kABytes) / stage_bytes;
+        while (stages < min_stages && bufs > 1) {
+            --bufs;
+            stages = (cap - fixed - bufs * kABytes) / stage_bytes;
+        }
         if (stages > kMaxStages) stages = kMaxStages;
+        if (stages >= 2) {
+            bufs = (cap - fixed - stages * stage_bytes) / kABytes;  // leftovers deepen the residual prefetch
+            if (bufs > kMaxEpiBufs) bufs = kMaxEpiBufs;
+        }
+        if (bufs < 1) {
+            delete op;
+            return set_error("igemm: not enough shared memory for an epilogue buffer");
+        }
+        if (ga > bufs - 1) ga = bufs > 1 ? bufs - 1 : 1;
     }
+    if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) {
         delete op;
         return set_error("igemm: not enough shared memory for two pipeline stages");
     }
     p.stages = stages;
-    p.res_bufs = res_bufs > 0 ? res_bufs : 1;
-    op->smem_bytes = fixed + stages * stage_bytes + (p.res_tma ? GA * res_bufs * kABytes : 0);
+    p.epi_bufs = bufs;
+    p.epi_active = ga;
+    op->smem_bytes = fixed + stages * stage_bytes + bufs * kABytes;
     op->threads = (base_warps(op->gather) + (op->gather ? kGatherWarps : 0)) * 32;
 
     int dev = 0, sms = 0;
