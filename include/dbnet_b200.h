@@ -122,6 +122,14 @@ int b200_asf_fwd(const void* p2, const void* p3, const void* p4, const void* p5,
                  const float* w_att, const float* b_att, void* out,
                  int batch, int h2, int w2, int h3, int w3, int h4, int w4, int h5, int w5,
                  void* stream);
+/* Same module, split form used by the engine: z_l = W_l p_l (the 4 attention-logit contributions of level l,
+ * conv_atten's weight columns [256 l, 256 (l+1)), no bias) computed at each level's native resolution by the
+ * implicit-GEMM kernel, fp32 [pixel][zld]; this call interpolates the z maps (bilinear, align_corners=True, exact
+ * because upsampling commutes with the 1x1 conv), adds b_att, takes the softmax and blends p2..p5. */
+int b200_asf_combine(const void* p2, const void* p3, const void* p4, const void* p5,
+                     const float* z2, const float* z3, const float* z4, const float* z5, int zld,
+                     const float* b_att, void* out, int batch, int h2, int w2, int h3, int w3,
+                     int h4, int w4, int h5, int w5, void* stream);
 /* DBHead tail (model/det/head.py:15,23,28-48): last ConvTranspose2d(64->1, 2x2 s2) of both branches,
  * sigmoid, differentiable-binarisation step.  t_bin/t_thr: NHWC bf16, 64 channels each (already
  * BN+ReLU'd), `ld` elements between consecutive pixels (64 for two dense tensors, 128 when both branches

@@ -187,6 +187,113 @@ __global__ void __launch_bounds__(256) asf_kernel(const __nv_bfloat16* __restric
     }
 }
 
+// ------------------------------------------------------------------------------------------ ASF, split form
+// The attention logits are linear in the (bilinearly upsampled) features, and bilinear upsampling commutes with the
+// per-pixel 1x1 conv:  conv_atten(cat(up(p_l))) = sum_l up(W_l p_l).  So z_l = W_l p_l (4 channels) is computed at
+// each level's NATIVE resolution by four tiny GEMMs, and this kernel only (a) interpolates the z maps, (b) takes the
+// softmax, (c) blends the 13 feature taps with pre-multiplied weights s_l * w_corner.  No dot products, no shuffles.
+struct AsfLevel {
+    const __nv_bfloat16* p;
+    const float* z;  // [pixel][zld] fp32, first 4 entries = logit contributions
+    int h, w;
+    float sy, sx;
+};
+struct AsfParams {
+    AsfLevel lv[4];
+    const float* b_att;
+    __nv_bfloat16* out;
+    int batch, zld;
+};
+
+// One warp = 4 consecutive pixels of a row; lane = (pixel, channel group cg); the lane owns channels k*64 + cg*8 + j
+// (k < 4, j < 8), so the 8 lanes of a pixel read 128 contiguous bytes per load instruction.
+__global__ void __launch_bounds__(256, 3) asf_combine_kernel(const AsfParams P) {
+    const int lane = threadIdx.x & 31;
+    const int pq = lane >> 3, cg = lane & 7;
+    const int h2 = P.lv[0].h, w2 = P.lv[0].w;
+    const int quads_x = (w2 + 3) >> 2;
+    const int64_t nquads = static_cast<int64_t>(P.batch) * h2 * quads_x;
+    const float b0 = P.b_att[0], b1 = P.b_att[1], b2 = P.b_att[2], b3 = P.b_att[3];
+    for (int64_t qd = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5; qd < nquads;
+         qd += (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5) {
+        const int qx = static_cast<int>(qd % quads_x);
+        const int64_t r = qd / quads_x;
+        const int y = static_cast<int>(r % h2);
+        const int n = static_cast<int>(r / h2);
+        const int x = qx * 4 + pq;
+        if (x >= w2) continue;
+        const int64_t pix = (static_cast<int64_t>(n) * h2 + y) * w2 + x;
+        // ---- logits: z2 at the pixel + bilinear(align_corners) taps of z3..z5
+        float4 lg = __ldg(reinterpret_cast<const float4*>(P.lv[0].z + pix * P.zld));
+        int cidx[3][4];  // pixel index inside the level (batch * h * w < 2^31)
+        float cw[3][4];
+#pragma unroll
+        for (int l = 1; l < 4; ++l) {
+            const AsfLevel& L = P.lv[l];
+            const float fy = L.sy * static_cast<float>(y), fx = L.sx * static_cast<float>(x);
+            const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+            const int y1 = y0 + ((y0 < L.h - 1) ? 1 : 0), x1 = x0 + ((x0 < L.w - 1) ? 1 : 0);
+            const float ly = fy - static_cast<float>(y0), lx = fx - static_cast<float>(x0);
+            const float hy = 1.0f - ly, hx = 1.0f - lx;
+            const int base = n * L.h * L.w;
+            cidx[l - 1][0] = base + y0 * L.w + x0;  cw[l - 1][0] = hy * hx;
+            cidx[l - 1][1] = base + y0 * L.w + x1;  cw[l - 1][1] = hy * lx;
+            cidx[l - 1][2] = base + y1 * L.w + x0;  cw[l - 1][2] = ly * hx;
+            cidx[l - 1][3] = base + y1 * L.w + x1;  cw[l - 1][3] = ly * lx;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float4 zc = __ldg(reinterpret_cast<const float4*>(L.z + static_cast<int64_t>(cidx[l - 1][c]) * P.zld));
+                lg.x = fmaf(cw[l - 1][c], zc.x, lg.x);
+                lg.y = fmaf(cw[l - 1][c], zc.y, lg.y);
+                lg.z = fmaf(cw[l - 1][c], zc.z, lg.z);
+                lg.w = fmaf(cw[l - 1][c], zc.w, lg.w);
+            }
+        }
+        const float a0 = lg.x + b0, a1 = lg.y + b1, a2 = lg.z + b2, a3 = lg.w + b3;
+        const float mx = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+        const float e0 = expf(a0 - mx), e1 = expf(a1 - mx), e2 = expf(a2 - mx), e3 = expf(a3 - mx);
+        const float inv = 1.0f / (e0 + e1 + e2 + e3);
+        const float sl[4] = {e0 * inv, e1 * inv, e2 * inv, e3 * inv};
+        // ---- blend: out = s0 * p2 + sum_l s_l * sum_corner w_corner * p_l[corner]
+        float acc[4][8];
+        {
+            const __nv_bfloat16* src = P.lv[0].p + pix * 256 + cg * 8;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float f[8];
+                unpack8(ldg128(src + k * 64), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[k][j] = sl[0] * f[j];
+            }
+        }
+#pragma unroll
+        for (int l = 1; l < 4; ++l) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float wgt = sl[l] * cw[l - 1][c];
+                const __nv_bfloat16* src = P.lv[l].p + static_cast<int64_t>(cidx[l - 1][c]) * 256 + cg * 8;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float f[8];
+                    unpack8(ldg128(src + k * 64), f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[k][j] = fmaf(wgt, f[j], acc[k][j]);
+                }
+            }
+        }
+        __nv_bfloat16* dst = P.out + pix * 256 + cg * 8;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint4 u;
+            u.x = pack_bf16(acc[k][0], acc[k][1]);
+            u.y = pack_bf16(acc[k][2], acc[k][3]);
+            u.z = pack_bf16(acc[k][4], acc[k][5]);
+            u.w = pack_bf16(acc[k][6], acc[k][7]);
+            *reinterpret_cast<uint4*>(dst + k * 64) = u;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ DB head tail
 struct HeadParams {
     const __nv_bfloat16* t_bin;
@@ -310,6 +417,32 @@ extern "C" int b200_asf_fwd(const void* p2, const void* p3, const void* p4, cons
         reinterpret_cast<const __nv_bfloat16*>(p4), reinterpret_cast<const __nv_bfloat16*>(p5), w_att, b_att,
         reinterpret_cast<__nv_bfloat16*>(out), batch, h2, w2, h3, w3, h4, w4, h5, w5);
     return check_cuda(cudaGetLastError(), "b200_asf_fwd launch");
+}
+
+extern "C" int b200_asf_combine(const void* p2, const void* p3, const void* p4, const void* p5, const float* z2,
+                                const float* z3, const float* z4, const float* z5, int zld, const float* b_att, void* out,
+                                int batch, int h2, int w2, int h3, int w3, int h4, int w4, int h5, int w5, void* stream) {
+    if (!p2 || !p3 || !p4 || !p5 || !z2 || !z3 || !z4 || !z5 || !b_att || !out) return set_error("b200_asf_combine: null pointer");
+    if (batch <= 0 || h2 <= 0 || w2 <= 0 || zld < 4 || (zld % 4)) return set_error("b200_asf_combine: bad shape");
+    AsfParams P;
+    const void* ps[4] = {p2, p3, p4, p5};
+    const float* zs[4] = {z2, z3, z4, z5};
+    const int hs[4] = {h2, h3, h4, h5}, ws[4] = {w2, w3, w4, w5};
+    for (int l = 0; l < 4; ++l) {
+        P.lv[l].p = reinterpret_cast<const __nv_bfloat16*>(ps[l]);
+        P.lv[l].z = zs[l];
+        P.lv[l].h = hs[l];
+        P.lv[l].w = ws[l];
+        P.lv[l].sy = (h2 > 1) ? static_cast<float>(hs[l] - 1) / static_cast<float>(h2 - 1) : 0.0f;
+        P.lv[l].sx = (w2 > 1) ? static_cast<float>(ws[l] - 1) / static_cast<float>(w2 - 1) : 0.0f;
+    }
+    P.b_att = b_att;
+    P.out = reinterpret_cast<__nv_bfloat16*>(out);
+    P.batch = batch;
+    P.zld = zld;
+    const int64_t nquads = static_cast<int64_t>(batch) * h2 * ((w2 + 3) / 4);
+    asf_combine_kernel<<<grid_for(nquads, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(P);
+    return check_cuda(cudaGetLastError(), "b200_asf_combine launch");
 }
 
 extern "C" int b200_db_head_fwd(const void* t_bin, const void* t_thr, const float* w2_bin, float b2_bin,

@@ -56,6 +56,7 @@ struct IgemmParams {
     int epi_bufs;          // 16 KB epilogue buffers (residual lands in them, the result is written in place, TMA stores it)
     int ss_shared;         // one scale/shift copy for the CTA (single n-block) instead of one per group
     int res_bytes;         // bytes of one residual box (16 KB, or 4 KB for the half-resolution RES_UP2 box)
+    int dbg_shift;         // experiment: place the A tile k rows (k * 128 B) into its (padded) stage
     const __nv_bfloat16* x;
     const float* scale;
     const float* shift;
@@ -92,7 +93,7 @@ __device__ __forceinline__ SmemLayout carve(uint8_t* raw, const IgemmParams& p) 
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
     SmemLayout s;
     s.a = base;
-    s.b = s.a + p.stages * kABytes;
+    s.b = s.a + p.stages * kABytes + (p.dbg_shift ? 1024 : 0);
     s.epi = s.b + p.stages * p.block_n * 128;
     uint8_t* rest = s.epi + p.epi_bufs * kABytes;
     s.ss = reinterpret_cast<float*>(rest);
@@ -346,7 +347,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                                 ay += (ky == 0) ? -1 : 0;
                             }
                         }
-                        tma_load_4d(sm.a + s * kABytes, ma, &sm.full[s], c0, ax, ay, t.n);
+                        tma_load_4d(sm.a + s * kABytes + p.dbg_shift * 128, ma, &sm.full[s], c0, ax, ay, t.n);
                     }
                     tma_load_2d(sm.b + s * b_bytes, &tm.b, &sm.full[s], kb * kBlockK, t.nb * p.block_n);
                     if (++s == stages) { s = 0; ph ^= 1; }
@@ -369,7 +370,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
                     mbar_wait(&sm.full[s], ph);
                     tc_fence_after();
-                    const uint64_t da = umma_desc_sw128(smem_u32(sm.a + s * kABytes));
+                    const uint64_t da = umma_desc_sw128(smem_u32(sm.a + s * kABytes + p.dbg_shift * 128));
                     const uint64_t db = umma_desc_sw128(smem_u32(sm.b + s * b_bytes));
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
@@ -838,6 +839,7 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     p.y = d->y;
     p.offsets = d->offsets;
     op->gather = (d->mode != B200_IGEMM_CONV);
+    { const char* e = getenv("B200_DEBUG_ASHIFT"); p.dbg_shift = e ? atoi(e) : 0; }
     if (d->mode == B200_IGEMM_STEM) {
         // Preferred stem path: no producer warps at all.  A row (pixel, window row ty) = 64 contiguous bf16 of the packed
         // buffer starting at block (oy+ty, ox), i.e. a 4-D tensor {64, W/2, H/2+3, N} whose x stride is ONE block
@@ -914,6 +916,7 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     p.epi_bufs = bufs;
     p.epi_active = ga;
     op->smem_bytes = fixed + stages * stage_bytes + bufs * kABytes;
+    if (p.dbg_shift) { if (op->smem_bytes + 1024 > kMaxSmem) { --p.stages; op->smem_bytes -= stage_bytes; } op->smem_bytes += 1024; }
     op->threads = (base_warps(op->gather) + (op->gather ? kGatherWarps : 0)) * 32;
 
     int dev = 0, sms = 0;

@@ -63,6 +63,9 @@ class PreparedWeights:
             conv_bn(f"smooth{i}", nk.fpn_convs[i].conv.weight, nk.fpn_convs[i].bn)
         self.w_att = to(nk.asf.conv_atten.weight).reshape(4, 1024).contiguous()
         self.b_att = to(nk.asf.conv_atten.bias).contiguous()
+        for i in range(4):  # z_l = W_l p_l: the level's 256 attention columns as a 1x1 conv with N padded to 32
+            wz = ops.pack_conv_weight(self.w_att[:, 256 * i:256 * (i + 1)].reshape(4, 256, 1, 1), 32)
+            P[f"asf.z{i}"] = (wz, torch.ones(32, device=device), torch.zeros(32, device=device))
         # head: the first 3x3 conv of both branches is one GEMM (N = 64 + 64, reads the fused map once)
         hb, ht = model.head.bin_conv, model.head.thresh_conv
         w0 = torch.cat([ops.pack_conv_weight(to(hb[0].conv.weight), 64), ops.pack_conv_weight(to(ht[0].conv.weight), 64)])
@@ -178,7 +181,13 @@ class Plan:
                 self.taps[f"p{i + 2}"] = (ps[i], 256)
         sizes = [(feats[i][2], feats[i][3]) for i in range(4)]
         fused = bf(b, sizes[0][0], sizes[0][1], 256)
-        self.steps.append(lambda: ops.asf_fwd(ps[0], ps[1], ps[2], ps[3], W.w_att, W.b_att, fused, b, sizes))
+        zs = []
+        for i in range(4):  # attention-logit contributions at native resolution (fp32, 8 floats per pixel, 4 used)
+            z = torch.empty(b, sizes[i][0], sizes[i][1], 8, device=dev, dtype=torch.float32)
+            igemm(f"asf.z{i}", ops.IGEMM_CONV, ps[i], f"asf.z{i}", z, in_h=sizes[i][0], in_w=sizes[i][1], in_c=256, out_c=8,
+                  ksize=1, stride=1, flags=ops.EPI_OUT_F32, out_ld=8)
+            zs.append(z)
+        self.steps.append(lambda: ops.asf_combine(ps, zs, 8, W.b_att, fused, b, sizes))
         self.names.append("asf")
         if keep_taps:
             self.taps["asf"] = (fused, 256)

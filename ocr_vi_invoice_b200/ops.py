@@ -16,7 +16,7 @@ from ._lib import (EPI_DCN_COORDS, EPI_OUT_F32, EPI_RELU, EPI_RES, EPI_RES_UP2, 
 
 __all__ = [
     "Igemm", "pack_conv_weight", "pack_stem_weight", "pack_convT_weight", "fold_bn", "pad_vec",
-    "stem_pack", "maxpool3x3s2", "asf_fwd", "db_head_fwd", "postproc", "ref_conv2d", "ref_dcn2d",
+    "stem_pack", "maxpool3x3s2", "asf_fwd", "asf_combine", "db_head_fwd", "postproc", "ref_conv2d", "ref_dcn2d",
     "EPI_RELU", "EPI_RES", "EPI_RES_UP2", "EPI_OUT_F32", "EPI_SHUFFLE2", "EPI_DCN_COORDS", "dcn_coords", "IGEMM_CONV", "IGEMM_STEM", "IGEMM_DCN",
 ]
 
@@ -157,6 +157,13 @@ def asf_fwd(p2, p3, p4, p5, w_att, b_att, out, batch, sizes) -> None:
     _lib.check(_lib.load().b200_asf_fwd(_lib.ptr(p2), _lib.ptr(p3), _lib.ptr(p4), _lib.ptr(p5), _lib.ptr(w_att),
                                         _lib.ptr(b_att), _lib.ptr(out), batch, h2, w2, h3, w3, h4, w4, h5, w5,
                                         _lib.current_stream()), "asf_fwd")
+
+
+def asf_combine(ps, zs, zld: int, b_att, out, batch: int, sizes) -> None:
+    (h2, w2), (h3, w3), (h4, w4), (h5, w5) = sizes
+    _lib.check(_lib.load().b200_asf_combine(*[_lib.ptr(t) for t in ps], *[_lib.ptr(t) for t in zs], zld, _lib.ptr(b_att),
+                                            _lib.ptr(out), batch, h2, w2, h3, w3, h4, w4, h5, w5, _lib.current_stream()),
+               "asf_combine")
 
 
 def dcn_coords(raw: torch.Tensor, coords: torch.Tensor, batch: int, in_h: int, in_w: int, x_ld: int, stride: int) -> None:

@@ -51,6 +51,33 @@ def test_asf_kernel(size):
     torch.testing.assert_close(got, ref, rtol=1.6e-2, atol=2e-2)
 
 
+@pytest.mark.parametrize("size", [(1, 16, 24), (2, 40, 56), (1, 8, 10)])
+def test_asf_split_form(size):
+    """z_l = W_l p_l at native resolution (fp32 here) + b200_asf_combine == the reference ScaleFeatureSelection."""
+    from ocr_vi_invoice_b200 import ops
+    b, h2, w2 = size
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(13)
+    sizes = [(h2, w2), (max(1, h2 // 2), max(1, w2 // 2)), (max(1, h2 // 4), max(1, w2 // 4)), (max(1, h2 // 8), max(1, w2 // 8))]
+    ps = [torch.randn(b, 256, h, w, device=dev, generator=g).to(torch.bfloat16) for h, w in sizes]
+    w_att = torch.randn(4, 1024, device=dev, generator=g) * 0.05
+    b_att = torch.randn(4, device=dev, generator=g) * 0.1
+    zs = []
+    for i, p in enumerate(ps):
+        z = torch.zeros(b, sizes[i][0], sizes[i][1], 8, device=dev)
+        z[..., :4] = torch.einsum("bchw,oc->bhwo", p.float(), w_att[:, 256 * i:256 * (i + 1)])
+        zs.append(z.contiguous())
+    out = torch.empty(b, h2, w2, 256, device=dev, dtype=torch.bfloat16)
+    ops.asf_combine([nhwc(p.float()) for p in ps], zs, 8, b_att, out, b, sizes)
+    torch.cuda.synchronize()
+    ups = [ps[0].float()] + [F.interpolate(p.float(), size=(h2, w2), mode="bilinear", align_corners=True) for p in ps[1:]]
+    score = F.softmax(F.conv2d(torch.cat(ups, 1), w_att.view(4, 1024, 1, 1), b_att), dim=1)
+    ref = sum(u * score[:, i:i + 1] for i, u in enumerate(ups))
+    got = nchw(out)
+    assert rel_rms(got, ref) < 4e-3
+    torch.testing.assert_close(got, ref, rtol=1.6e-2, atol=2e-2)
+
+
 @pytest.mark.parametrize("size", [(1, 32, 48), (2, 70, 36)])
 def test_db_head_kernel(size):
     from ocr_vi_invoice_b200 import ops
