@@ -113,6 +113,11 @@ int b200_dcn_coords(const float* raw, void* coords, int batch, int in_h, int in_
  * B200_IGEMM_STEM with weights [n_pad][4 rows][4 blocks][16] (replaces the layout half of
  * torchvision conv1 7x7 s2, resnet.py:197 via model/det/backbone.py:34). */
 int b200_stem_pack(const float* img, void* packed, int batch, int h, int w, void* stream);
+/* Same, from the decoded image: uint8 HWC RGB (b, H, W, 3) -> (v/255 - mean[c]) / std[c] -> packed bf16 buffer.
+ * Replaces the host-side normalisation + HWC->CHW permute of src/pipeline/pipeline2.py:312-314 (mean3 / std3 are
+ * HOST pointers to 3 floats). */
+int b200_stem_pack_u8(const void* img_hwc, void* packed, int batch, int h, int w, const float* mean3,
+                      const float* std3, void* stream);
 /* MaxPool2d(3, stride 2, pad 1) on NHWC bf16 (torchvision resnet.py:200). */
 int b200_maxpool3x3s2(const void* x, void* y, int batch, int h, int w, int c, void* stream);
 /* ScaleFeatureSelection.forward (model/det/neck.py:57-79): bilinear(align_corners=True) upsample of

@@ -15,7 +15,10 @@
 //   * stores directly from registers (fp32 outputs, DCN coordinate records, nearest-upsampled residual).
 //
 // GEMM view:  D[M = output pixels of one 128-pixel tile][N = out channels] =
-//             A[M][K = taps * Cin] * B[N][K]^T,   K ordered (tap, cin),  BLOCK_K = 64 (one SW128 atom).
+//             A[M][K = taps * Cin] * B[N][K]^T,   K ordered (64-channel chunk, tap),  BLOCK_K = 64 (one SW128 atom).
+// (Measured and dropped: sharing one 130-pixel halo row between the three taps of a kernel row -- legal, because TMA
+//  and UMMA both swizzle on absolute shared-memory address bits -- cut L2->SM traffic by a third but did not speed up
+//  any layer: these GEMMs are bound by shared-memory bandwidth (every operand byte is written once and read once).)
 //
 // Reference call sites replaced: see include/dbnet_b200.h.
 #include "common.cuh"
@@ -56,7 +59,6 @@ struct IgemmParams {
     int epi_bufs;          // 16 KB epilogue buffers (residual lands in them, the result is written in place, TMA stores it)
     int ss_shared;         // one scale/shift copy for the CTA (single n-block) instead of one per group
     int res_bytes;         // bytes of one residual box (16 KB, or 4 KB for the half-resolution RES_UP2 box)
-    int dbg_shift;         // experiment: place the A tile k rows (k * 128 B) into its (padded) stage
     const __nv_bfloat16* x;
     const float* scale;
     const float* shift;
@@ -93,7 +95,7 @@ __device__ __forceinline__ SmemLayout carve(uint8_t* raw, const IgemmParams& p) 
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
     SmemLayout s;
     s.a = base;
-    s.b = s.a + p.stages * kABytes + (p.dbg_shift ? 1024 : 0);
+    s.b = s.a + p.stages * kABytes;
     s.epi = s.b + p.stages * p.block_n * 128;
     uint8_t* rest = s.epi + p.epi_bufs * kABytes;
     s.ss = reinterpret_cast<float*>(rest);
@@ -323,14 +325,14 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
+            const int taps = p.k_blocks / p.cchunks;  // K is ordered (64-channel chunk, tap)
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const TileCoord t = decode_tile(p, tile);
+                int tap = 0, c0 = 0;
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
                     mbar_wait(&sm.empty[s], ph ^ 1);
                     mbar_arrive_expect_tx(&sm.full[s], (kGather ? 0 : kABytes) + b_bytes);
                     if (!kGather) {
-                        const int tap = kb / p.cchunks;
-                        const int c0 = (kb - tap * p.cchunks) * kBlockK;
                         int ax = t.x0, ay = t.y0;
                         const CUtensorMap* ma = &tm.a[0];
                         if (p.mode == B200_IGEMM_STEM) {
@@ -347,10 +349,11 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                                 ay += (ky == 0) ? -1 : 0;
                             }
                         }
-                        tma_load_4d(sm.a + s * kABytes + p.dbg_shift * 128, ma, &sm.full[s], c0, ax, ay, t.n);
+                        tma_load_4d(sm.a + s * kABytes, ma, &sm.full[s], c0, ax, ay, t.n);
                     }
                     tma_load_2d(sm.b + s * b_bytes, &tm.b, &sm.full[s], kb * kBlockK, t.nb * p.block_n);
                     if (++s == stages) { s = 0; ph ^= 1; }
+                    if (++tap == taps) { tap = 0; c0 += kBlockK; }
                 }
             }
         }
@@ -370,7 +373,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
                     mbar_wait(&sm.full[s], ph);
                     tc_fence_after();
-                    const uint64_t da = umma_desc_sw128(smem_u32(sm.a + s * kABytes + p.dbg_shift * 128));
+                    const uint64_t da = umma_desc_sw128(smem_u32(sm.a + s * kABytes));
                     const uint64_t db = umma_desc_sw128(smem_u32(sm.b + s * b_bytes));
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
@@ -839,7 +842,6 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     p.y = d->y;
     p.offsets = d->offsets;
     op->gather = (d->mode != B200_IGEMM_CONV);
-    { const char* e = getenv("B200_DEBUG_ASHIFT"); p.dbg_shift = e ? atoi(e) : 0; }
     if (d->mode == B200_IGEMM_STEM) {
         // Preferred stem path: no producer warps at all.  A row (pixel, window row ty) = 64 contiguous bf16 of the packed
         // buffer starting at block (oy+ty, ox), i.e. a 4-D tensor {64, W/2, H/2+3, N} whose x stride is ONE block
@@ -916,7 +918,7 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     p.epi_bufs = bufs;
     p.epi_active = ga;
     op->smem_bytes = fixed + stages * stage_bytes + bufs * kABytes;
-    if (p.dbg_shift) { if (op->smem_bytes + 1024 > kMaxSmem) { --p.stages; op->smem_bytes -= stage_bytes; } op->smem_bytes += 1024; }
+
     op->threads = (base_warps(op->gather) + (op->gather ? kGatherWarps : 0)) * 32;
 
     int dev = 0, sms = 0;

@@ -61,8 +61,11 @@ __global__ void ref_conv_kernel(const RefParams p) {
                 const int ix = ox * p.stride - pad + kx;
                 if (ix < 0 || ix >= p.in_w) continue;
                 const __nv_bfloat16* xs = p.x + ((static_cast<int64_t>(n) * p.in_h + iy) * p.in_w + ix) * p.in_c;
-                const __nv_bfloat16* ws = p.w + static_cast<int64_t>(co) * p.w_ld + (ky * p.ksize + kx) * p.in_c;
-                for (int c = 0; c < p.in_c; ++c) acc = fmaf(__bfloat162float(xs[c]), __bfloat162float(ws[c]), acc);
+                // K order (64-channel chunk, tap, channel in chunk), as the tensor-core path
+                const int taps = p.ksize * p.ksize, tap = ky * p.ksize + kx;
+                const __nv_bfloat16* ws = p.w + static_cast<int64_t>(co) * p.w_ld;
+                for (int c = 0; c < p.in_c; ++c)
+                    acc = fmaf(__bfloat162float(xs[c]), __bfloat162float(ws[((c >> 6) * taps + tap) * 64 + (c & 63)]), acc);
             }
         }
         ref_store(p, acc, n, oy, ox, co);
@@ -102,11 +105,11 @@ __global__ void ref_dcn_kernel(const RefParams p) {
             const __nv_bfloat16* p2 = img + (static_cast<int64_t>(t_ok && r_ok ? hl : 0) * p.in_w + (t_ok && r_ok ? wh : 0)) * p.in_c;
             const __nv_bfloat16* p3 = img + (static_cast<int64_t>(b_ok && l_ok ? hh : 0) * p.in_w + (b_ok && l_ok ? wl : 0)) * p.in_c;
             const __nv_bfloat16* p4 = img + (static_cast<int64_t>(b_ok && r_ok ? hh : 0) * p.in_w + (b_ok && r_ok ? wh : 0)) * p.in_c;
-            const __nv_bfloat16* ws = p.w + static_cast<int64_t>(co) * p.w_ld + tap * p.in_c;
+            const __nv_bfloat16* ws = p.w + static_cast<int64_t>(co) * p.w_ld;
             for (int c = 0; c < p.in_c; ++c) {
                 const float s = w1 * __bfloat162float(p1[c]) + w2 * __bfloat162float(p2[c]) +
                                 w3 * __bfloat162float(p3[c]) + w4 * __bfloat162float(p4[c]);
-                acc = fmaf(__bfloat162float(__float2bfloat16_rn(s)), __bfloat162float(ws[c]), acc);
+                acc = fmaf(__bfloat162float(__float2bfloat16_rn(s)), __bfloat162float(ws[((c >> 6) * 9 + tap) * 64 + (c & 63)]), acc);
             }
         }
         ref_store(p, acc, n, oy, ox, co);

@@ -36,21 +36,28 @@ class DBNetPP(nn.Module):
         return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
 
     def _get_plan(self, x: torch.Tensor, keep_taps: bool = False) -> Plan:
+        u8 = x.dtype == torch.uint8
+        shape = (x.shape[0], x.shape[1], x.shape[2]) if u8 else (x.shape[0], x.shape[2], x.shape[3])
         sig = (x.device, self._signature())
         if self._prepared is None or self._prepared_sig != sig:
             self._prepared = PreparedWeights(self, x.device)
             self._prepared_sig = sig
             self._plans.clear()
-        key = (x.shape[0], x.shape[2], x.shape[3], keep_taps)
+        key = shape + (keep_taps, u8)
         plan = self._plans.get(key)
         if plan is None:
-            plan = Plan(self._prepared, x.shape[0], x.shape[2], x.shape[3], keep_taps=keep_taps)
+            plan = Plan(self._prepared, *shape, keep_taps=keep_taps, input_u8=u8)
             self._plans[key] = plan
         return plan
 
     def _check_input(self, x):
-        if not isinstance(x, torch.Tensor) or x.dim() != 4 or x.shape[1] != 3:
-            raise ValueError("DBNetPP.forward expects a (b, 3, H, W) tensor")
+        ok = isinstance(x, torch.Tensor) and x.dim() == 4
+        if ok and x.dtype == torch.uint8:
+            ok = x.shape[3] == 3  # extension: decoded images, uint8 HWC RGB, normalised on the GPU
+        elif ok:
+            ok = x.shape[1] == 3 and x.is_floating_point()
+        if not ok:
+            raise ValueError("DBNetPP.forward expects a float (b, 3, H, W) tensor (or, as an extension, uint8 (b, H, W, 3))")
         if not x.is_cuda:
             raise RuntimeError("B200 DBNet++ path runs on CUDA only: move the model and the input to the GPU "
                                "(there is no CPU fallback)")
@@ -66,7 +73,8 @@ class DBNetPP(nn.Module):
         self._check_input(x)
         with torch.cuda.device(x.device):
             plan = self._get_plan(x)
-            return plan.run(x.float().contiguous(), want=self.output_maps, use_graph=self.use_cuda_graph)
+            xin = x.contiguous() if x.dtype == torch.uint8 else x.float().contiguous()
+            return plan.run(xin, want=self.output_maps, use_graph=self.use_cuda_graph)
 
     @torch.no_grad()
     def forward_with_taps(self, x):

@@ -32,8 +32,8 @@ class PreparedWeights:
         to = lambda t: t.detach().to(device=device, dtype=torch.float32)
         P: Dict[str, tuple] = {}
 
-        def conv_bn(name, conv_w, bn, n_pad=None, conv_bias=None, dcn=False):
-            w = ops.pack_conv_weight(to(conv_w), n_pad, dcn=dcn)
+        def conv_bn(name, conv_w, bn, n_pad=None, conv_bias=None):
+            w = ops.pack_conv_weight(to(conv_w), n_pad)
             s, t = _bn_fold(bn, None if conv_bias is None else to(conv_bias))
             P[name] = (w, ops.pad_vec(to(s), w.shape[0], 1.0), ops.pad_vec(to(t), w.shape[0]))
 
@@ -51,7 +51,7 @@ class PreparedWeights:
                     om = blk.conv2.offset_mask_conv
                     w = ops.pack_conv_weight(to(om.weight), 32)
                     P[p + ".offset"] = (w, torch.ones(32, device=device), ops.pad_vec(to(om.bias), 32))
-                conv_bn(p + ".conv2", blk.conv2.weight, blk.bn2, dcn=self.dcn and li >= 2)
+                conv_bn(p + ".conv2", blk.conv2.weight, blk.bn2)
                 conv_bn(p + ".conv3", blk.conv3.weight, blk.bn3)
                 if blk.downsample is not None:
                     conv_bn(p + ".down", blk.downsample[0].weight, blk.downsample[1])
@@ -85,7 +85,7 @@ class PreparedWeights:
 class Plan:
     """Static launch list + activation buffers for one (batch, H, W)."""
 
-    def __init__(self, W: PreparedWeights, batch: int, H: int, Wd: int, keep_taps: bool = False):
+    def __init__(self, W: PreparedWeights, batch: int, H: int, Wd: int, keep_taps: bool = False, input_u8: bool = False):
         if H % 32 or Wd % 32:
             raise ValueError(f"DBNet++ input sizes must be multiples of 32 (got {H}x{Wd}); see pipeline2.py:33-40")
         dev = W.device
@@ -116,10 +116,14 @@ class Plan:
             return op
 
         # ---- stem: pack -> 7x7 s2 (+BN+ReLU) -> maxpool
-        self.x_in = torch.empty(b, 3, H, Wd, device=dev, dtype=torch.float32)
         packed = bf(b, H // 2 + 3, Wd // 2 + 3, 16)
         stem = bf(b, H // 2, Wd // 2, 64)
-        self.steps.append(lambda: ops.stem_pack(self.x_in, packed)); self.names.append("stem_pack")
+        if input_u8:  # decoded images, uint8 HWC RGB: normalisation fused into the packing kernel
+            self.x_in = torch.empty(b, H, Wd, 3, device=dev, dtype=torch.uint8)
+            self.steps.append(lambda: ops.stem_pack_u8(self.x_in, packed)); self.names.append("stem_pack_u8")
+        else:         # the reference's interface: normalised fp32 NCHW
+            self.x_in = torch.empty(b, 3, H, Wd, device=dev, dtype=torch.float32)
+            self.steps.append(lambda: ops.stem_pack(self.x_in, packed)); self.names.append("stem_pack")
         igemm("stem", ops.IGEMM_STEM, packed, "stem", stem, in_h=H, in_w=Wd, in_c=3, out_c=64, ksize=7, stride=2,
               flags=ops.EPI_RELU)
         h, w = H // 4, Wd // 4

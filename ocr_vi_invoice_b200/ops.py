@@ -16,7 +16,7 @@ from ._lib import (EPI_DCN_COORDS, EPI_OUT_F32, EPI_RELU, EPI_RES, EPI_RES_UP2, 
 
 __all__ = [
     "Igemm", "pack_conv_weight", "pack_stem_weight", "pack_convT_weight", "fold_bn", "pad_vec",
-    "stem_pack", "maxpool3x3s2", "asf_fwd", "asf_combine", "db_head_fwd", "postproc", "ref_conv2d", "ref_dcn2d",
+    "stem_pack", "stem_pack_u8", "maxpool3x3s2", "asf_fwd", "asf_combine", "db_head_fwd", "postproc", "ref_conv2d", "ref_dcn2d",
     "EPI_RELU", "EPI_RES", "EPI_RES_UP2", "EPI_OUT_F32", "EPI_SHUFFLE2", "EPI_DCN_COORDS", "dcn_coords", "IGEMM_CONV", "IGEMM_STEM", "IGEMM_DCN",
 ]
 
@@ -34,23 +34,20 @@ def choose_n_pad(out_c: int) -> int:
     return _round_up(out_c, 256)
 
 
-def pack_conv_weight(w: torch.Tensor, n_pad: Optional[int] = None, dcn: bool = False) -> torch.Tensor:
-    """(O, I, kh, kw) fp32 -> [n_pad][kh*kw*I] bf16 with K ordered (tap, cin).
+def pack_conv_weight(w: torch.Tensor, n_pad: Optional[int] = None) -> torch.Tensor:
+    """(O, I, kh, kw) fp32 -> [n_pad][kh*kw*I] bf16 with K ordered (64-channel chunk, tap, channel in chunk).
 
-    torchvision's deform_conv2d and nn.Conv2d flatten K as (cin, tap) (`weight.flatten(1)`); the NHWC
-    kernels walk K tap-major so a 64-channel slice of one tap is one contiguous 128-byte row.
-    `dcn=True` orders K as (64-channel chunk, tap, 64 channels) instead: the deformable kernel walks all
-    9 taps of one channel chunk back to back so its gathers re-hit the same neighbourhood in L1.
+    torchvision's deform_conv2d and nn.Conv2d flatten K as (cin, tap) (`weight.flatten(1)`).  The NHWC kernels walk
+    all taps of one 64-channel chunk back to back: a (chunk, tap) K-block is one contiguous 128-byte row per pixel, the
+    three taps of a kernel row share one halo row in shared memory, and the deformable gathers of a chunk re-hit the
+    same neighbourhood in L1.  Input channel counts below 64 (none in DBNet++) are not supported.
     """
     o, i, kh, kw = w.shape
+    assert i % 64 == 0, "input channels must be a multiple of 64"
     n_pad = n_pad or choose_n_pad(o)
     out = torch.zeros(n_pad, kh * kw * i, dtype=torch.bfloat16, device=w.device)
-    if dcn:
-        assert i % 64 == 0
-        t = w.reshape(o, i // 64, 64, kh * kw).permute(0, 1, 3, 2)  # (o, chunk, tap, 64)
-        out[:o] = t.reshape(o, kh * kw * i).to(torch.bfloat16)
-    else:
-        out[:o] = w.permute(0, 2, 3, 1).reshape(o, kh * kw * i).to(torch.bfloat16)
+    t = w.reshape(o, i // 64, 64, kh * kw).permute(0, 1, 3, 2)  # (o, chunk, tap, 64)
+    out[:o] = t.reshape(o, kh * kw * i).to(torch.bfloat16)
     return out.contiguous()
 
 
@@ -146,6 +143,19 @@ def stem_pack(img: torch.Tensor, packed: torch.Tensor) -> None:
     b, c, h, w = img.shape
     assert c == 3 and img.dtype == torch.float32 and img.is_contiguous()
     _lib.check(_lib.load().b200_stem_pack(_lib.ptr(img), _lib.ptr(packed), b, h, w, _lib.current_stream()), "stem_pack")
+
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)  # src/pipeline/pipeline2.py:249-250
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def stem_pack_u8(img_hwc: torch.Tensor, packed: torch.Tensor, mean=IMAGENET_MEAN, std=IMAGENET_STD) -> None:
+    b, h, w, c = img_hwc.shape
+    assert c == 3 and img_hwc.dtype == torch.uint8 and img_hwc.is_contiguous()
+    m = (C.c_float * 3)(*mean)
+    s = (C.c_float * 3)(*std)
+    _lib.check(_lib.load().b200_stem_pack_u8(_lib.ptr(img_hwc), _lib.ptr(packed), b, h, w, m, s, _lib.current_stream()),
+               "stem_pack_u8")
 
 
 def maxpool3x3s2(x: torch.Tensor, y: torch.Tensor, batch: int, h: int, w: int, c: int) -> None:

@@ -65,8 +65,8 @@ class Detector:
         if not host.is_pinned():
             host = host.pin_memory()
         buf = self._dev_buf[slot]
-        if buf is None or buf.shape != host.shape:
-            buf = torch.empty(host.shape, dtype=torch.float32, device=self.device)
+        if buf is None or buf.shape != host.shape or buf.dtype != host.dtype:
+            buf = torch.empty(host.shape, dtype=host.dtype, device=self.device)
             self._dev_buf[slot] = buf
         ready = torch.cuda.Event()
         with torch.cuda.stream(self._copy_stream):

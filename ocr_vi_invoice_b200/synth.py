@@ -51,3 +51,8 @@ def normalize(img_u8: np.ndarray) -> np.ndarray:
 def synthetic_batch(batch: int, h: int, w: int, seed: int = 0) -> np.ndarray:
     """(batch, 3, h, w) float32 normalised batch of distinct synthetic invoices."""
     return np.stack([normalize(synthetic_invoice(h, w, seed * 1000 + i)[0]) for i in range(batch)])
+
+
+def synthetic_batch_u8(batch: int, h: int, w: int, seed: int = 0) -> np.ndarray:
+    """(batch, h, w, 3) uint8 RGB batch of the same synthetic invoices (the decoded-image interface)."""
+    return np.stack([synthetic_invoice(h, w, seed * 1000 + i)[0] for i in range(batch)])

@@ -56,6 +56,10 @@ CONV_CASES = [
     (1, 64, 48, 256, 256, 1, 1, "up2"),
     (2, 10, 6, 256, 1024, 1, 1, "res+relu"),
     (1, 128, 128, 64, 64, 1, 1, "relu"),
+    (1, 6, 128, 64, 64, 3, 1, "relu"),          # 128x1 tiles
+    (2, 5, 200, 256, 256, 3, 1, ""),            # ragged second tile, 4 channel chunks
+    (1, 9, 256, 128, 27, 3, 1, "f32"),          # 128x1 tiles with the direct fp32 epilogue
+    (1, 4, 130, 256, 128, 3, 1, "res+relu"),    # 128x1 tiles + residual
 ]
 
 
@@ -209,8 +213,8 @@ def test_dcn_igemm(case):
     mask = torch.sigmoid(om[..., 18:27]).permute(0, 3, 1, 2).contiguous()
     ref = tvops.deform_conv2d(xb, offset, wb, None, stride=s, padding=1, mask=mask)
     ref = (ref * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)).relu()
-    wp = ops.pack_conv_weight(wt, ops.choose_n_pad(co), dcn=True)   # K = (chunk, tap, 64) for the tcgen05 DCN kernel
-    wp_ref = ops.pack_conv_weight(wt, ops.choose_n_pad(co))         # K = (tap, cin) for the cross-check kernel
+    wp = ops.pack_conv_weight(wt, ops.choose_n_pad(co))   # K = (chunk, tap, 64), same for both kernels
+    wp_ref = wp
     n_pad = wp.shape[0]
     sc, sh = ops.pad_vec(scale, n_pad, 1.0), ops.pad_vec(shift, n_pad)
     y = torch.full((b, oh, ow, co), float("nan"), device=dev, dtype=torch.bfloat16)

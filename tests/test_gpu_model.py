@@ -292,3 +292,17 @@ def test_detector_stream_matches_direct_calls():
             assert all(np.array_equal(x, y) for x, y in zip(ba, bb))
     m.use_cuda_graph = False
     m.output_maps = ("binary", "thresh", "thresh_binary", "bin_logits", "thresh_logits")
+
+
+def test_uint8_input_matches_host_normalisation():
+    """uint8 HWC batch normalised on the GPU == the reference's host normalisation (pipeline2.py:312-314) + fp32 NCHW."""
+    from ocr_vi_invoice_b200.synth import synthetic_batch, synthetic_batch_u8
+    m, _ = _model(4, offset_px=0.5)
+    u8 = torch.from_numpy(synthetic_batch_u8(2, 96, 128, seed=3))
+    f32 = torch.from_numpy(synthetic_batch(2, 96, 128, seed=3))
+    a = m(u8.cuda())
+    b = m(f32.cuda())
+    torch.cuda.synchronize()
+    # same bf16 stem input up to an ulp of the normalisation arithmetic -> logits agree to bf16 noise
+    assert rel_rms(a["bin_logits"], b["bin_logits"]) < 2e-2
+    assert a["binary"].shape == (2, 1, 96, 128)

@@ -59,11 +59,12 @@ def test_dcn_false_constructs():
     assert len(m.state_dict()) == 754 - 2 * 2 * 13
 
 
-def test_pack_conv_weight_is_tap_major():
-    w = torch.randn(5, 64, 3, 3)
+def test_pack_conv_weight_is_chunk_then_tap_major():
+    w = torch.randn(5, 128, 3, 3)
     p = ops.pack_conv_weight(w, 32).float()
-    assert p.shape == (32, 576) and p[5:].abs().sum() == 0
-    torch.testing.assert_close(p[2, 4 * 64 + 7], w[2, 7, 1, 1].to(torch.bfloat16).float())
+    assert p.shape == (32, 1152) and p[5:].abs().sum() == 0
+    # channel 71 = chunk 1, lane 7; tap (1, 1) = 4  ->  K index (1 * 9 + 4) * 64 + 7
+    torch.testing.assert_close(p[2, (1 * 9 + 4) * 64 + 7], w[2, 71, 1, 1].to(torch.bfloat16).float())
 
 
 def test_pack_stem_weight_equals_conv7x7():
