@@ -303,6 +303,20 @@ def main():
                     "achieved": round(dcn_tf, 2), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                     "frac": round(dcn_tf / pk["tf_sustained"], 4), "share_of_step": round(dcn["ms"] / tot_ms, 4),
                     "algorithmic_gflop_per_step": round(dcn["flops"] / 1e9, 1)}
+        # ncu DRAM traffic of the heaviest launch of the dominant kernel (committed capture; null if absent)
+        traffic = None
+        tfile = ROOT / "profiles" / "ncu_traffic.json"
+        top_conv = max((l for l in launches if l[1] == "conv"), key=lambda l: l[2])
+        if tfile.exists():
+            tj = json.loads(tfile.read_text()).get("launches", {})
+            if top_conv[0] in tj:
+                traffic = tj[top_conv[0]]["dram_bytes"]
+        roofline["traffic"] = traffic
+        roofline["top_launch"] = {"name": top_conv[0], "ms": round(top_conv[2], 4),
+                                  "achieved": round(top_conv[3] / (top_conv[2] * 1e-3) / 1e12, 1),
+                                  "frac": round(top_conv[3] / (top_conv[2] * 1e-3) / 1e12 / pk["tf_sustained"], 4),
+                                  "algorithmic_bytes": 2 * b * (H // 4) * (W // 4) * 256 * 2 if top_conv[0] == "smooth0" else None,
+                                  "traffic_is_for": "this launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)"}
         shares = {k: round(v["ms"] / tot_ms, 4) for k, v in by_kind.items()}
         if args.dump_launches:
             with open(args.dump_launches, "w") as f:

@@ -59,6 +59,7 @@ struct IgemmParams {
     int epi_bufs;          // 16 KB epilogue buffers (residual lands in them, the result is written in place, TMA stores it)
     int ss_shared;         // one scale/shift copy for the CTA (single n-block) instead of one per group
     int res_bytes;         // bytes of one residual box (16 KB, or 4 KB for the half-resolution RES_UP2 box)
+    int b_resident;        // the whole weight matrix stays in shared memory for the CTA's lifetime (small N x K)
     const __nv_bfloat16* x;
     const float* scale;
     const float* shift;
@@ -86,6 +87,7 @@ struct SmemLayout {
     uint64_t* res_full;   // [kMaxEpiBufs] residual box landed in the buffer
     uint64_t* slot_free;  // [kMaxEpiBufs] the store that used the buffer has read it (layers without residual)
     uint64_t* out_ready;  // [kMaxEpiBufs] the epilogue group has written its result
+    uint64_t* b_ready;    // resident weights have landed
     uint32_t* tmem_slot;
 };
 
@@ -96,7 +98,7 @@ __device__ __forceinline__ SmemLayout carve(uint8_t* raw, const IgemmParams& p) 
     SmemLayout s;
     s.a = base;
     s.b = s.a + p.stages * kABytes;
-    s.epi = s.b + p.stages * p.block_n * 128;
+    s.epi = s.b + (p.b_resident ? p.k_blocks : p.stages) * p.block_n * 128;
     uint8_t* rest = s.epi + p.epi_bufs * kABytes;
     s.ss = reinterpret_cast<float*>(rest);
     uint8_t* bars = rest + (p.ss_shared ? 1 : G) * 2048;
@@ -107,7 +109,8 @@ __device__ __forceinline__ SmemLayout carve(uint8_t* raw, const IgemmParams& p) 
     s.res_full = s.tempty + 2;
     s.slot_free = s.res_full + kMaxEpiBufs;
     s.out_ready = s.slot_free + kMaxEpiBufs;
-    s.tmem_slot = reinterpret_cast<uint32_t*>(s.out_ready + kMaxEpiBufs);
+    s.b_ready = s.out_ready + kMaxEpiBufs;
+    s.tmem_slot = reinterpret_cast<uint32_t*>(s.b_ready + 1);
     return s;
 }
 
@@ -298,6 +301,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                 mbar_init(&sm.tfull[a], 1);
                 mbar_init(&sm.tempty[a], 4 * G);
             }
+            mbar_init(sm.b_ready, 1);
             for (int a = 0; a < kMaxEpiBufs; ++a) {
                 mbar_init(&sm.res_full[a], 1);
                 mbar_init(&sm.slot_free[a], 1);
@@ -326,12 +330,17 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
             int s = 0;
             uint32_t ph = 0;
             const int taps = p.k_blocks / p.cchunks;  // K is ordered (64-channel chunk, tap)
+            if (p.b_resident) {  // small weight matrix: fetch it once, every tile multiplies against the same copy
+                mbar_arrive_expect_tx(sm.b_ready, p.k_blocks * b_bytes);
+                for (int kb = 0; kb < p.k_blocks; ++kb)
+                    tma_load_2d(sm.b + kb * b_bytes, &tm.b, sm.b_ready, kb * kBlockK, 0);
+            }
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const TileCoord t = decode_tile(p, tile);
                 int tap = 0, c0 = 0;
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
                     mbar_wait(&sm.empty[s], ph ^ 1);
-                    mbar_arrive_expect_tx(&sm.full[s], (kGather ? 0 : kABytes) + b_bytes);
+                    mbar_arrive_expect_tx(&sm.full[s], (kGather ? 0 : kABytes) + (p.b_resident ? 0 : b_bytes));
                     if (!kGather) {
                         int ax = t.x0, ay = t.y0;
                         const CUtensorMap* ma = &tm.a[0];
@@ -351,7 +360,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                         }
                         tma_load_4d(sm.a + s * kABytes, ma, &sm.full[s], c0, ax, ay, t.n);
                     }
-                    tma_load_2d(sm.b + s * b_bytes, &tm.b, &sm.full[s], kb * kBlockK, t.nb * p.block_n);
+                    if (!p.b_resident) tma_load_2d(sm.b + s * b_bytes, &tm.b, &sm.full[s], kb * kBlockK, t.nb * p.block_n);
                     if (++s == stages) { s = 0; ph ^= 1; }
                     if (++tap == taps) { tap = 0; c0 += kBlockK; }
                 }
@@ -361,6 +370,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
         // ===================================================================== MMA issuer
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16(static_cast<uint32_t>(p.block_n));
+            if (p.b_resident) mbar_wait(sm.b_ready, 0);
             int s = 0;
             uint32_t ph = 0;
             int it = 0;
@@ -374,7 +384,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                     mbar_wait(&sm.full[s], ph);
                     tc_fence_after();
                     const uint64_t da = umma_desc_sw128(smem_u32(sm.a + s * kABytes));
-                    const uint64_t db = umma_desc_sw128(smem_u32(sm.b + s * b_bytes));
+                    const uint64_t db = umma_desc_sw128(smem_u32(sm.b + (p.b_resident ? kb : s) * b_bytes));
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
                         // +32 bytes per UMMA_K step inside the 128B swizzle atom (encoded >> 4)
@@ -872,9 +882,13 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
 
     const int G = epi_groups(op->gather);
     const int b_bytes = block_n * 128;
-    const int stage_bytes = kABytes + b_bytes;
+    // Small weight matrices (stem, layer1, ConvT, ...) live in shared memory for the whole launch: no per-tile weight
+    // TMA traffic, the ring carries activations only.
+    p.b_resident = (p.num_n_blocks == 1 && p.k_blocks * b_bytes <= 72 * 1024 && d->mode != B200_IGEMM_DCN) ? 1 : 0;
+    const int stage_bytes = p.b_resident ? kABytes : kABytes + b_bytes;
     p.ss_shared = (p.num_n_blocks == 1) ? 1 : 0;
-    const int fixed = 1024 /*alignment*/ + 1024 /*barriers*/ + (p.ss_shared ? 1 : G) * 2048 /*scale+shift*/;
+    const int fixed = 1024 /*alignment*/ + 1024 /*barriers*/ + (p.ss_shared ? 1 : G) * 2048 /*scale+shift*/ +
+                      (p.b_resident ? p.k_blocks * b_bytes : 0);
     // The DCN gather lives on L1 hits (K ordered chunk-major), so it keeps its carve-out <= 132 KB and leaves the
     // rest of the 256 KB to L1; everything else may use the full 227 KB opt-in.
     const int cap = (d->mode == B200_IGEMM_DCN) ? 131 * 1024 : kMaxSmem;

@@ -31,6 +31,22 @@ def run(name, b, h, w, ci, co, k, s, flags, res=False, shuf=0, iters=20):
     byts = x.numel() * 2 + y.numel() * 2 + (r.numel() * 2 if res else 0)
     print(f"{name:28s} {ms:7.3f} ms  {byts / ms / 1e9:7.2f} TB/s  {op.flops / ms / 1e9:8.1f} TF/s  dbg={os.environ.get('B200_DEBUG_EPI','0')}", flush=True)
 
+if __name__ == "__main__" and os.environ.get("EPI_SET") == "gemm":
+    for n in (64, 128, 256):
+        run(f"1x1 K=2048 N={n} 32x32", 16, 32, 32, 2048, n, 1, 1, 0, iters=50)
+    for n in (64, 256):
+        run(f"1x1 K=2048 N={n} 8x128", 16, 8, 128, 2048, n, 1, 1, 0, iters=50)
+    for n in (64, 256):
+        run(f"1x1 K=512 N={n} 64x64", 16, 64, 64, 512, n, 1, 1, 0, iters=50)
+    sys.exit(0)
+if __name__ == "__main__" and os.environ.get("EPI_SET") == "conv2":
+    run("layer1.conv2 3x3 64->64", 16, 256, 256, 64, 64, 3, 1, ops.EPI_RELU)
+    run("conv 3x3 64->64 no-relu", 16, 256, 256, 64, 64, 3, 1, 0)
+    run("stem-like 1x1 k=4 256->64", 16, 512, 512, 256, 64, 1, 1, ops.EPI_RELU)
+    run("3x3 64->128", 16, 256, 256, 64, 128, 3, 1, ops.EPI_RELU)
+    run("3x3 64->256", 16, 256, 256, 64, 256, 3, 1, ops.EPI_RELU)
+    run("3x3 128->64", 16, 256, 256, 128, 64, 3, 1, ops.EPI_RELU)
+    sys.exit(0)
 if __name__ == "__main__":
     run("layer1.conv3 64->256 res", 16, 256, 256, 64, 256, 1, 1, ops.EPI_RELU, res=True)
     run("layer1.conv3 no-res", 16, 256, 256, 64, 256, 1, 1, ops.EPI_RELU)
