@@ -9,7 +9,7 @@
 
 namespace b200 {
 
-constexpr int kChunk = 4096;  // pixels per scan chunk (256 threads x 16)
+constexpr int kChunkWords = 128;  // 32-pixel words per scan chunk (one block of 256 threads)
 
 struct CompRec {  // per-component accumulator, 32 B
     int minx, miny, maxx, maxy;
@@ -19,9 +19,11 @@ struct CompRec {  // per-component accumulator, 32 B
 
 struct PP {
     const float* prob;
-    int* L;       // union-find parent per pixel (global pixel index), -1 = background
-    int* R;       // canonical rank, valid at root pixels
-    int* labels;  // output label map (may be null)
+    uint32_t* mask;      // foreground bitmask, one 32-pixel word per (row, word) -- rows are padded to whole words
+    uint32_t* rootmask;  // bit set where the pixel is the root (= first pixel in raster order) of its component
+    int* L;              // union-find parent per FOREGROUND pixel (global pixel index); background entries are never touched
+    int* R;              // canonical rank, valid at root pixels
+    int* labels;         // output label map (may be null)
     int* chunk_cnt;
     int* ncomp;
     CompRec* rec;
@@ -40,10 +42,17 @@ __device__ __forceinline__ int uf_find(const int* L, int a) {
     }
     return a;
 }
+// find with path compression: re-point the start at the root it found (any ancestor is a valid parent, and parents
+// only ever decrease, so a racing writer can at worst store another valid ancestor)
+__device__ __forceinline__ int uf_find_compress(int* L, int a) {
+    const int r = uf_find(L, a);
+    if (r != a && L[a] > r) L[a] = r;
+    return r;
+}
 __device__ __forceinline__ void uf_union(int* L, int a, int b) {
     while (true) {
-        a = uf_find(L, a);
-        b = uf_find(L, b);
+        a = uf_find_compress(L, a);
+        b = uf_find_compress(L, b);
         if (a == b) return;
         if (a < b) {
             const int t = a;
@@ -56,77 +65,106 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
     }
 }
 
-// One warp = 32 consecutive pixels of a row.  L[p] = index of the first pixel of p's run inside this word.
+// One warp = 4 consecutive words (4 loads in flight per lane).  Writes the foreground bitmask and, for foreground
+// pixels only, L[p] = index of the first pixel of p's run inside its word.
 __global__ void pp_init_kernel(const PP p) {
     const int lane = threadIdx.x & 31;
-    const int64_t nwords = static_cast<int64_t>(p.batch) * p.h * p.wpr;
-    for (int64_t wd = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5; wd < nwords;
-         wd += (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5) {
-        const int wx = static_cast<int>(wd % p.wpr);
-        const int64_t row = wd / p.wpr;  // n*h + y
-        const int x = wx * 32 + lane;
-        const int64_t g = row * p.w + x;
-        const bool fg = (x < p.w) && (p.prob[g] > p.thresh);
-        const uint32_t m = __ballot_sync(0xffffffffu, fg);
-        if (fg) {
-            // zeros strictly below this lane; the run starts right above the highest of them
-            const uint32_t z = ~m & ((1u << lane) - 1u);
-            const int start = z ? (32 - __clz(z)) : 0;
-            p.L[g] = static_cast<int>(g) - (lane - start);
-        } else if (x < p.w) {
-            p.L[g] = -1;
+    // all indices fit 32 bits (batch*h*w < 2^31 is checked by the host): no 64-bit divisions in the loops
+    const uint32_t nwords = static_cast<uint32_t>(p.batch) * p.h * p.wpr;
+    const uint32_t nquads = (nwords + 3) >> 2;
+    for (uint32_t wq = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wq < nquads; wq += (gridDim.x * blockDim.x) >> 5) {
+        float v[4];
+        uint32_t g[4];
+        bool in[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t wd = wq * 4 + j;
+            const uint32_t row = wd / p.wpr;  // n*h + y
+            const int wx = static_cast<int>(wd - row * p.wpr);
+            const int x = wx * 32 + lane;
+            in[j] = (wd < nwords) && (x < p.w);
+            g[j] = row * p.w + x;
+            v[j] = in[j] ? __ldg(p.prob + g[j]) : 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t wd = wq * 4 + j;
+            const bool fg = in[j] && (v[j] > p.thresh);
+            const uint32_t m = __ballot_sync(0xffffffffu, fg);
+            if (wd < nwords && lane == 0) p.mask[wd] = m;
+            if (fg) {
+                // zeros strictly below this lane; the run starts right above the highest of them
+                const uint32_t z = ~m & ((1u << lane) - 1u);
+                const int start = z ? (32 - __clz(z)) : 0;
+                p.L[g[j]] = static_cast<int>(g[j]) - (lane - start);
+            }
         }
     }
 }
 
-// Merge runs across word boundaries and with the row above (8-connectivity), skipping unions that a
-// horizontally adjacent pixel is guaranteed to perform.
+// Merge runs across word boundaries and with the row above (8-connectivity).  Which unions are needed is decided
+// from six bitmask words per warp, skipping the ones a horizontally adjacent pixel is guaranteed to perform.
 __global__ void pp_merge_kernel(const PP p) {
-    const int64_t total = static_cast<int64_t>(p.batch) * p.h * p.w;
-    for (int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; g < total;
-         g += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        if (p.L[g] < 0) continue;
-        const int x = static_cast<int>(g % p.w);
-        const int y = static_cast<int>((g / p.w) % p.h);
-        const bool left = (x > 0) && (p.L[g - 1] >= 0);
-        if (left && (x & 31) == 0) uf_union(p.L, static_cast<int>(g), static_cast<int>(g - 1));
-        if (y == 0) continue;
-        const int64_t u = g - p.w;
-        const bool up = p.L[u] >= 0;
-        const bool ul = (x > 0) && (p.L[u - 1] >= 0);
-        if (up) {
-            if (!(left && ul)) uf_union(p.L, static_cast<int>(g), static_cast<int>(u));
-        } else {
-            if (ul && !left) uf_union(p.L, static_cast<int>(g), static_cast<int>(u - 1));
-            const bool ur = (x + 1 < p.w) && (p.L[u + 1] >= 0);
-            const bool right = (x + 1 < p.w) && (p.L[g + 1] >= 0);
-            if (ur && !right) uf_union(p.L, static_cast<int>(g), static_cast<int>(u + 1));
-        }
+    const int lane = threadIdx.x & 31;
+    const uint32_t nwords = static_cast<uint32_t>(p.batch) * p.h * p.wpr;
+    for (uint32_t wd = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wd < nwords; wd += (gridDim.x * blockDim.x) >> 5) {
+        const uint32_t m = p.mask[wd];
+        if (m == 0) continue;
+        const uint32_t row = wd / p.wpr;
+        const int wx = static_cast<int>(wd - row * p.wpr);
+        const int y = static_cast<int>(row % p.h);
+        const bool has_l = wx > 0, has_r = wx + 1 < p.wpr, has_u = y > 0;
+        const uint32_t ml = has_l ? p.mask[wd - 1] : 0u, mr = has_r ? p.mask[wd + 1] : 0u;
+        const uint32_t u = has_u ? p.mask[wd - p.wpr] : 0u;
+        const uint32_t ul = (has_u && has_l) ? p.mask[wd - p.wpr - 1] : 0u, ur = (has_u && has_r) ? p.mask[wd - p.wpr + 1] : 0u;
+        const uint32_t left = (m << 1) | (ml >> 31);    // bit i: pixel i-1 of this row is foreground
+        const uint32_t right = (m >> 1) | (mr << 31);   // bit i: pixel i+1
+        const uint32_t upl = (u << 1) | (ul >> 31), upr = (u >> 1) | (ur << 31);
+        const uint32_t do_word = m & 1u & (ml >> 31);            // run continues from the previous word
+        const uint32_t do_up = m & u & ~(left & upl);            // the left pair has not linked these two runs yet
+        const uint32_t do_ul = m & ~u & upl & ~left;
+        const uint32_t do_ur = m & ~u & upr & ~right;
+        const uint32_t g = row * p.w + wx * 32 + lane;
+        const uint32_t bit = 1u << lane;
+        if (do_word & bit) uf_union(p.L, static_cast<int>(g), static_cast<int>(g - 1));
+        if (do_up & bit) uf_union(p.L, static_cast<int>(g), static_cast<int>(g - p.w));
+        if (do_ul & bit) uf_union(p.L, static_cast<int>(g), static_cast<int>(g - p.w - 1));
+        if (do_ur & bit) uf_union(p.L, static_cast<int>(g), static_cast<int>(g - p.w + 1));
     }
 }
 
-// Flatten to roots and count roots per chunk.  grid = batch * nchunks blocks of 256 threads.
+// Flatten to roots, publish the per-word root bitmask and count roots per chunk.
+// grid = batch * nchunks blocks of 256 threads; a chunk = 128 consecutive words of one image (raster order).
 __global__ void __launch_bounds__(256) pp_flatten_count_kernel(const PP p) {
     __shared__ int s_cnt;
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
     const int n = blockIdx.x / p.nchunks, ck = blockIdx.x % p.nchunks;
-    const int npx = p.h * p.w;
-    const int64_t base = static_cast<int64_t>(n) * npx;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wimg = p.h * p.wpr;
     int cnt = 0;
-    for (int i = threadIdx.x; i < kChunk; i += 256) {
-        const int l = ck * kChunk + i;
-        if (l >= npx) break;
-        const int64_t g = base + l;
-        if (p.L[g] >= 0) {
-            const int r = uf_find(p.L, static_cast<int>(g));
-            p.L[g] = r;  // only ever shortens paths; roots are stable after the merge kernel
-            cnt += (r == static_cast<int>(g));
+    for (int i = warp; i < kChunkWords; i += 8) {
+        const int wl = ck * kChunkWords + i;
+        if (wl >= wimg) break;
+        const uint32_t wd = static_cast<uint32_t>(n) * wimg + wl;
+        const uint32_t m = p.mask[wd];
+        uint32_t rm = 0;
+        if (m) {
+            const uint32_t g = (wd / p.wpr) * p.w + (wl % p.wpr) * 32 + lane;
+            bool root = false;
+            if ((m >> lane) & 1u) {
+                const int r = uf_find(p.L, static_cast<int>(g));
+                p.L[g] = r;  // only ever shortens paths; roots are stable after the merge kernel
+                root = (r == static_cast<int>(g));
+            }
+            rm = __ballot_sync(0xffffffffu, root);
+        }
+        if (lane == 0) {
+            p.rootmask[wd] = rm;
+            cnt += __popc(rm);
         }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_cnt, cnt);
+    if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
     __syncthreads();
     if (threadIdx.x == 0) p.chunk_cnt[blockIdx.x] = s_cnt;
 }
@@ -163,58 +201,75 @@ __global__ void __launch_bounds__(256) pp_scan_kernel(const PP p) {
     }
 }
 
-// Rank roots: R[root] = 1 + (#roots before it in raster order).  Same grid as flatten_count.
+// Rank roots: R[root] = 1 + (#roots before it in raster order), from the root bitmasks alone.  Same grid as above.
 __global__ void __launch_bounds__(256) pp_rank_kernel(const PP p) {
-    __shared__ int s_warp[8];
+    __shared__ int s_pre[kChunkWords];
     const int n = blockIdx.x / p.nchunks, ck = blockIdx.x % p.nchunks;
-    const int npx = p.h * p.w;
-    const int64_t base = static_cast<int64_t>(n) * npx;
-    int running = p.chunk_cnt[blockIdx.x];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i0 = 0; i0 < kChunk; i0 += 256) {  // raster order: pass i0 covers 256 consecutive pixels
-        const int l = ck * kChunk + i0 + threadIdx.x;
-        const int64_t g = base + l;
-        const bool root = (l < npx) && (p.L[g] == static_cast<int>(g));
-        const uint32_t m = __ballot_sync(0xffffffffu, root);
-        if (lane == 0) s_warp[warp] = __popc(m);
+    const int wimg = p.h * p.wpr;
+    const uint32_t wbase = static_cast<uint32_t>(n) * wimg + static_cast<uint32_t>(ck) * kChunkWords;
+    // inclusive scan of the 128 per-word root counts (threads 0..127, Hillis-Steele in shared memory)
+    int c = 0;
+    if (threadIdx.x < kChunkWords && ck * kChunkWords + static_cast<int>(threadIdx.x) < wimg) c = __popc(p.rootmask[wbase + threadIdx.x]);
+    if (threadIdx.x < kChunkWords) s_pre[threadIdx.x] = c;
+    __syncthreads();
+    for (int o = 1; o < kChunkWords; o <<= 1) {
+        int t = 0;
+        if (threadIdx.x < kChunkWords && static_cast<int>(threadIdx.x) >= o) t = s_pre[threadIdx.x - o];
         __syncthreads();
-        int before = 0, tot = 0;
-#pragma unroll
-        for (int wq = 0; wq < 8; ++wq) {
-            const int c = s_warp[wq];
-            before += (wq < warp) ? c : 0;
-            tot += c;
+        if (threadIdx.x < kChunkWords) s_pre[threadIdx.x] += t;
+        __syncthreads();
+    }
+    const int base = p.chunk_cnt[blockIdx.x];
+    for (int i = warp; i < kChunkWords; i += 8) {
+        const int wl = ck * kChunkWords + i;
+        if (wl >= wimg) break;
+        const uint32_t rm = p.rootmask[wbase + i];
+        if ((rm >> lane) & 1u) {
+            const uint32_t g = ((wbase + i) / p.wpr) * p.w + (wl % p.wpr) * 32 + lane;
+            const int before = (i ? s_pre[i - 1] : 0) + __popc(rm & ((1u << lane) - 1u));
+            p.R[g] = base + before + 1;
         }
-        if (root) p.R[g] = running + before + __popc(m & ((1u << lane) - 1u)) + 1;
-        running += tot;
-        __syncthreads();
     }
 }
 
-// Write the canonical label map and accumulate per-component statistics.  One warp = one 32-pixel word.
-__global__ void pp_stats_kernel(const PP p) {
-    const int lane = threadIdx.x & 31;
-    const int64_t nwords = static_cast<int64_t>(p.batch) * p.h * p.wpr;
-    for (int64_t wd = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5; wd < nwords;
-         wd += (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5) {
-        const int wx = static_cast<int>(wd % p.wpr);
-        const int64_t row = wd / p.wpr;
+// Write the canonical label map and accumulate per-component statistics.  One warp = one 32-pixel word; empty words
+// cost one 4-byte load (plus the zero labels, when a label map is requested).  Blocks walk contiguous word ranges and
+// keep ONE component record in shared memory (the first one they meet): a page-sized component then costs shared-memory
+// atomics plus one global flush per block instead of six same-address global atomics per run.
+__global__ void __launch_bounds__(256) pp_stats_kernel(const PP p) {
+    __shared__ int s_key;  // image * maxc + (label - 1) of the cached record, -1 = none yet
+    __shared__ int s_minx, s_miny, s_maxx, s_maxy, s_npix;
+    __shared__ unsigned long long s_qsum;
+    if (threadIdx.x == 0) {
+        s_key = -1; s_minx = 0x7fffffff; s_miny = 0x7fffffff; s_maxx = -1; s_maxy = -1; s_npix = 0; s_qsum = 0ull;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nwords = static_cast<uint32_t>(p.batch) * p.h * p.wpr;
+    const uint32_t per_block = (nwords + gridDim.x - 1) / gridDim.x;
+    const uint32_t w_begin = blockIdx.x * per_block;
+    const uint32_t w_end = (w_begin + per_block < nwords) ? w_begin + per_block : nwords;
+    for (uint32_t wd = w_begin + warp; wd < w_end; wd += 8) {
+        const uint32_t m = p.mask[wd];
+        if (m == 0 && !p.labels) continue;
+        const uint32_t row = wd / p.wpr;
+        const int wx = static_cast<int>(wd - row * p.wpr);
+        const int x = wx * 32 + lane;
+        const uint32_t g = row * p.w + x;
+        if (m == 0) {
+            if (x < p.w) p.labels[g] = 0;
+            continue;
+        }
         const int y = static_cast<int>(row % p.h);
         const int n = static_cast<int>(row / p.h);
-        const int x = wx * 32 + lane;
-        const int64_t g = row * p.w + x;
         int lab = 0;
         uint32_t q = 0;
-        if (x < p.w) {
-            const int root = p.L[g];
-            if (root >= 0) {
-                lab = p.R[root];
-                q = __float2uint_rn(p.prob[g] * 16777216.0f);
-            }
-            if (p.labels) p.labels[g] = lab;
+        if ((m >> lane) & 1u) {
+            lab = p.R[p.L[g]];
+            q = __float2uint_rn(p.prob[g] * 16777216.0f);
         }
-        const uint32_t m = __ballot_sync(0xffffffffu, lab != 0);
-        if (m == 0) continue;
+        if (p.labels && x < p.w) p.labels[g] = lab;
         const uint32_t zabove = ~m & ~((2u << lane) - 1u);  // background lanes strictly above this lane
         const int end = zabove ? (__ffs(zabove) - 1) : 32;   // exclusive end of this lane's run
 #pragma unroll
@@ -224,14 +279,36 @@ __global__ void pp_stats_kernel(const PP p) {
         }
         const bool head = (lab != 0) && (lane == 0 || !((m >> (lane - 1)) & 1u));
         if (head && lab <= p.maxc) {
-            CompRec* r = p.rec + static_cast<int64_t>(n) * p.maxc + (lab - 1);
-            atomicMin(&r->minx, x);
-            atomicMax(&r->maxx, x + (end - lane) - 1);
-            atomicMin(&r->miny, y);
-            atomicMax(&r->maxy, y);
-            atomicAdd(&r->npix, end - lane);
-            atomicAdd(&r->qsum, static_cast<unsigned long long>(q));
+            const int key = n * p.maxc + (lab - 1);
+            int cur = s_key;
+            if (cur == -1) cur = atomicCAS(&s_key, -1, key), cur = (cur == -1) ? key : cur;
+            if (cur == key) {
+                atomicMin(&s_minx, x);
+                atomicMax(&s_maxx, x + (end - lane) - 1);
+                atomicMin(&s_miny, y);
+                atomicMax(&s_maxy, y);
+                atomicAdd(&s_npix, end - lane);
+                atomicAdd(&s_qsum, static_cast<unsigned long long>(q));
+            } else {
+                CompRec* r = p.rec + key;
+                atomicMin(&r->minx, x);
+                atomicMax(&r->maxx, x + (end - lane) - 1);
+                atomicMin(&r->miny, y);
+                atomicMax(&r->maxy, y);
+                atomicAdd(&r->npix, end - lane);
+                atomicAdd(&r->qsum, static_cast<unsigned long long>(q));
+            }
         }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_key >= 0) {
+        CompRec* r = p.rec + s_key;
+        atomicMin(&r->minx, s_minx);
+        atomicMax(&r->maxx, s_maxx);
+        atomicMin(&r->miny, s_miny);
+        atomicMax(&r->maxy, s_maxy);
+        atomicAdd(&r->npix, s_npix);
+        atomicAdd(&r->qsum, s_qsum);
     }
 }
 
@@ -297,8 +374,9 @@ using namespace b200;
 extern "C" int64_t b200_postproc_workspace_bytes(int batch, int h, int w, int max_candidates) {
     if (batch <= 0 || h <= 0 || w <= 0 || max_candidates <= 0) return -1;
     const int64_t npx = static_cast<int64_t>(batch) * h * w;
-    const int64_t nchunks = (static_cast<int64_t>(h) * w + kChunk - 1) / kChunk;
-    return 2 * align256(npx * 4) + align256(batch * nchunks * 4) + align256(batch * 4) +
+    const int64_t wimg = static_cast<int64_t>(h) * ((w + 31) / 32);
+    const int64_t nchunks = (wimg + kChunkWords - 1) / kChunkWords;
+    return 2 * align256(npx * 4) + 2 * align256(batch * wimg * 4) + align256(batch * nchunks * 4) + align256(batch * 4) +
            align256(static_cast<int64_t>(batch) * max_candidates * sizeof(CompRec));
 }
 
@@ -320,7 +398,8 @@ extern "C" int b200_postproc(const float* prob, int32_t* labels, b200_box* boxes
     p.counts = counts;
     p.batch = batch; p.h = h; p.w = w;
     p.wpr = (w + 31) / 32;
-    p.nchunks = static_cast<int>((static_cast<int64_t>(h) * w + kChunk - 1) / kChunk);
+    const int64_t wimg = static_cast<int64_t>(h) * p.wpr;
+    p.nchunks = static_cast<int>((wimg + kChunkWords - 1) / kChunkWords);
     p.maxc = max_candidates;
     p.min_area = min_area;
     p.thresh = static_cast<float>(thresh);
@@ -329,16 +408,19 @@ extern "C" int b200_postproc(const float* prob, int32_t* labels, b200_box* boxes
     char* ws = reinterpret_cast<char*>(workspace);
     p.L = reinterpret_cast<int*>(ws); ws += align256(npx * 4);
     p.R = reinterpret_cast<int*>(ws); ws += align256(npx * 4);
+    p.mask = reinterpret_cast<uint32_t*>(ws); ws += align256(batch * wimg * 4);
+    p.rootmask = reinterpret_cast<uint32_t*>(ws); ws += align256(batch * wimg * 4);
     p.chunk_cnt = reinterpret_cast<int*>(ws); ws += align256(static_cast<int64_t>(batch) * p.nchunks * 4);
     int* ncomp_ws = reinterpret_cast<int*>(ws); ws += align256(batch * 4);
     p.rec = reinterpret_cast<CompRec*>(ws);
     p.ncomp = ncomp ? ncomp : ncomp_ws;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const int64_t nwords = static_cast<int64_t>(batch) * h * p.wpr;
-    const int wblocks = static_cast<int>(((nwords + 7) / 8 < 148 * 32) ? (nwords + 7) / 8 : 148 * 32);
-    const int pblocks = static_cast<int>(((npx + 255) / 256 < 148 * 32) ? (npx + 255) / 256 : 148 * 32);
-    pp_init_kernel<<<wblocks, 256, 0, st>>>(p);
-    pp_merge_kernel<<<pblocks, 256, 0, st>>>(p);
+    const int64_t nwords = static_cast<int64_t>(batch) * wimg;
+    const int cap = 148 * 8;  // 8 resident 256-thread blocks per SM
+    const int qblocks = static_cast<int>(((nwords + 31) / 32 < cap) ? (nwords + 31) / 32 : cap);
+    const int wblocks = static_cast<int>(((nwords + 7) / 8 < cap) ? (nwords + 7) / 8 : cap);
+    pp_init_kernel<<<qblocks, 256, 0, st>>>(p);
+    pp_merge_kernel<<<wblocks, 256, 0, st>>>(p);
     pp_flatten_count_kernel<<<batch * p.nchunks, 256, 0, st>>>(p);
     pp_scan_kernel<<<batch, 256, 0, st>>>(p);
     pp_rank_kernel<<<batch * p.nchunks, 256, 0, st>>>(p);
