@@ -359,67 +359,97 @@ struct HeadParams {
 constexpr int kHeadPix = 128;       // pixels (threads) per block
 constexpr int kHeadRowBytes = 144;  // 128 B of channels + 16 B pad: conflict-free 16-byte row reads
 
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // Last ConvTranspose2d(64 -> 1, k2 s2) of both branches + sigmoid + DB step (model/det/head.py:15,23,28-48).
-// Stage 128 pixels x 64 channels of each branch into shared memory with coalesced 16-byte loads, then
-// one thread per input pixel produces its 2x2 output patch of all five maps (8-byte coalesced stores).
+// Persistent blocks: while one 128-pixel tile (2 x 128 x 64 channels) is reduced from shared memory -- one thread per
+// input pixel, its 2x2 output patch of all requested maps, 8-byte coalesced stores -- the next tile streams in with
+// cp.async (coalesced 16-byte copies, no register staging).
 __global__ void __launch_bounds__(kHeadPix) db_head_kernel(const HeadParams p) {
-    __shared__ __align__(16) uint8_t sb[2][kHeadPix * kHeadRowBytes];
+    extern __shared__ __align__(16) uint8_t sb_raw[];  // [2 buffers][2 branches][kHeadPix * kHeadRowBytes]
     __shared__ float sw[2][256];
     for (int t = threadIdx.x; t < 256; t += kHeadPix) {
         sw[0][t] = p.w2_bin[t];
         sw[1][t] = p.w2_thr[t];
     }
     const int64_t total = static_cast<int64_t>(p.batch) * p.h * p.w;
-    const int64_t pix0 = static_cast<int64_t>(blockIdx.x) * kHeadPix;
-    const int npx = static_cast<int>(min(static_cast<int64_t>(kHeadPix), total - pix0));
-    // 128 pixels * 8 chunks of 16 B per branch
-    for (int t = threadIdx.x; t < kHeadPix * 8; t += kHeadPix) {
-        const int px = t >> 3, ch = t & 7;
-        if (px < npx) {
-            *reinterpret_cast<uint4*>(&sb[0][px * kHeadRowBytes + ch * 16]) = ldg128(p.t_bin + (pix0 + px) * p.ld + ch * 8);
-            *reinterpret_cast<uint4*>(&sb[1][px * kHeadRowBytes + ch * 16]) = ldg128(p.t_thr + (pix0 + px) * p.ld + ch * 8);
-        }
-    }
-    __syncthreads();
-    const int px = threadIdx.x;
-    if (px >= npx) return;
-    float acc[2][4];
-#pragma unroll
-    for (int br = 0; br < 2; ++br) {
-        acc[br][0] = acc[br][1] = acc[br][2] = acc[br][3] = 0.0f;
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-            float f[8];
-            unpack8(*reinterpret_cast<const uint4*>(&sb[br][px * kHeadRowBytes + ch * 16]), f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 wv = *reinterpret_cast<const float4*>(&sw[br][(ch * 8 + j) * 4]);
-                acc[br][0] = fmaf(f[j], wv.x, acc[br][0]);
-                acc[br][1] = fmaf(f[j], wv.y, acc[br][1]);
-                acc[br][2] = fmaf(f[j], wv.z, acc[br][2]);
-                acc[br][3] = fmaf(f[j], wv.w, acc[br][3]);
+    const int64_t ntiles = (total + kHeadPix - 1) / kHeadPix;
+    constexpr int kBranch = kHeadPix * kHeadRowBytes;
+    auto fetch = [&](int64_t tile, int buf) {
+        const int64_t pix0 = tile * kHeadPix;
+        const int npx = static_cast<int>(min(static_cast<int64_t>(kHeadPix), total - pix0));
+        uint8_t* dst = sb_raw + buf * 2 * kBranch;
+        for (int t = threadIdx.x; t < kHeadPix * 8; t += kHeadPix) {  // 128 pixels x 8 chunks of 16 B per branch
+            const int px = t >> 3, ch = t & 7;
+            if (px < npx) {
+                cp_async16(dst + px * kHeadRowBytes + ch * 16, p.t_bin + (pix0 + px) * p.ld + ch * 8);
+                cp_async16(dst + kBranch + px * kHeadRowBytes + ch * 16, p.t_thr + (pix0 + px) * p.ld + ch * 8);
             }
         }
-    }
-    const int64_t pix = pix0 + px;
-    const int x = static_cast<int>(pix % p.w);
-    int64_t r = pix / p.w;
-    const int y = static_cast<int>(r % p.h);
-    const int n = static_cast<int>(r / p.h);
-    const int ow = 2 * p.w;
+        cp_async_commit();
+    };
+    int buf = 0;
+    if (static_cast<int64_t>(blockIdx.x) < ntiles) fetch(blockIdx.x, 0);
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+        const int64_t next = tile + gridDim.x;
+        if (next < ntiles) {
+            fetch(next, buf ^ 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const int64_t pix0 = tile * kHeadPix;
+        const int px = threadIdx.x;
+        if (pix0 + px < total) {
+            const uint8_t* src = sb_raw + buf * 2 * kBranch;
+            float acc[2][4];
 #pragma unroll
-    for (int dy = 0; dy < 2; ++dy) {
-        const float bl0 = acc[0][dy * 2 + 0] + p.b2_bin, bl1 = acc[0][dy * 2 + 1] + p.b2_bin;
-        const float tl0 = acc[1][dy * 2 + 0] + p.b2_thr, tl1 = acc[1][dy * 2 + 1] + p.b2_thr;
-        const float bp0 = 1.0f / (1.0f + expf(-bl0)), bp1 = 1.0f / (1.0f + expf(-bl1));
-        const float tp0 = 1.0f / (1.0f + expf(-tl0)), tp1 = 1.0f / (1.0f + expf(-tl1));
-        const float tb0 = 1.0f / (1.0f + expf(-p.k * (bp0 - tp0))), tb1 = 1.0f / (1.0f + expf(-p.k * (bp1 - tp1)));
-        const int64_t o = (static_cast<int64_t>(n) * (2 * p.h) + (2 * y + dy)) * ow + 2 * x;
-        if (p.binary) *reinterpret_cast<float2*>(p.binary + o) = make_float2(bp0, bp1);
-        if (p.thresh) *reinterpret_cast<float2*>(p.thresh + o) = make_float2(tp0, tp1);
-        if (p.thresh_binary) *reinterpret_cast<float2*>(p.thresh_binary + o) = make_float2(tb0, tb1);
-        if (p.bin_logits) *reinterpret_cast<float2*>(p.bin_logits + o) = make_float2(bl0, bl1);
-        if (p.thresh_logits) *reinterpret_cast<float2*>(p.thresh_logits + o) = make_float2(tl0, tl1);
+            for (int br = 0; br < 2; ++br) {
+                acc[br][0] = acc[br][1] = acc[br][2] = acc[br][3] = 0.0f;
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                    float f[8];
+                    unpack8(*reinterpret_cast<const uint4*>(src + br * kBranch + px * kHeadRowBytes + ch * 16), f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 wv = *reinterpret_cast<const float4*>(&sw[br][(ch * 8 + j) * 4]);
+                        acc[br][0] = fmaf(f[j], wv.x, acc[br][0]);
+                        acc[br][1] = fmaf(f[j], wv.y, acc[br][1]);
+                        acc[br][2] = fmaf(f[j], wv.z, acc[br][2]);
+                        acc[br][3] = fmaf(f[j], wv.w, acc[br][3]);
+                    }
+                }
+            }
+            const int64_t pix = pix0 + px;
+            const int x = static_cast<int>(pix % p.w);
+            const int64_t r = pix / p.w;
+            const int y = static_cast<int>(r % p.h);
+            const int n = static_cast<int>(r / p.h);
+            const int ow = 2 * p.w;
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+                const float bl0 = acc[0][dy * 2 + 0] + p.b2_bin, bl1 = acc[0][dy * 2 + 1] + p.b2_bin;
+                const float tl0 = acc[1][dy * 2 + 0] + p.b2_thr, tl1 = acc[1][dy * 2 + 1] + p.b2_thr;
+                const float bp0 = 1.0f / (1.0f + expf(-bl0)), bp1 = 1.0f / (1.0f + expf(-bl1));
+                const float tp0 = 1.0f / (1.0f + expf(-tl0)), tp1 = 1.0f / (1.0f + expf(-tl1));
+                const int64_t o = (static_cast<int64_t>(n) * (2 * p.h) + (2 * y + dy)) * ow + 2 * x;
+                if (p.binary) *reinterpret_cast<float2*>(p.binary + o) = make_float2(bp0, bp1);
+                if (p.thresh) *reinterpret_cast<float2*>(p.thresh + o) = make_float2(tp0, tp1);
+                if (p.thresh_binary) {
+                    const float tb0 = 1.0f / (1.0f + expf(-p.k * (bp0 - tp0))), tb1 = 1.0f / (1.0f + expf(-p.k * (bp1 - tp1)));
+                    *reinterpret_cast<float2*>(p.thresh_binary + o) = make_float2(tb0, tb1);
+                }
+                if (p.bin_logits) *reinterpret_cast<float2*>(p.bin_logits + o) = make_float2(bl0, bl1);
+                if (p.thresh_logits) *reinterpret_cast<float2*>(p.thresh_logits + o) = make_float2(tl0, tl1);
+            }
+        }
+        __syncthreads();  // everyone is done with `buf` before the next iteration's fetch overwrites it
     }
 }
 
@@ -518,8 +548,11 @@ extern "C" int b200_db_head_fwd(const void* t_bin, const void* t_thr, const floa
     p.bin_logits = bin_logits; p.thresh_logits = thresh_logits;
     p.batch = batch; p.h = h; p.w = w; p.ld = ld;
     const int64_t total = static_cast<int64_t>(batch) * h * w;
-    const int64_t blocks = (total + kHeadPix - 1) / kHeadPix;
-    if (blocks > 0x7fffffff) return set_error("b200_db_head_fwd: too many pixels");
-    db_head_kernel<<<static_cast<int>(blocks), kHeadPix, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    const int64_t ntiles = (total + kHeadPix - 1) / kHeadPix;
+    const int smem = 4 * kHeadPix * kHeadRowBytes;  // 2 buffers x 2 branches = 72 KB -> 3 blocks per SM
+    cudaError_t e = cudaFuncSetAttribute(db_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return check_cuda(e, "b200_db_head_fwd attribute");
+    const int blocks = static_cast<int>(ntiles < 148 * 3 ? ntiles : 148 * 3);
+    db_head_kernel<<<blocks, kHeadPix, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     return check_cuda(cudaGetLastError(), "b200_db_head_fwd launch");
 }
