@@ -293,13 +293,13 @@ def main():
         conv, dcn = by_kind.get("conv", {"ms": 1e-9, "flops": 0, "n": 0}), by_kind.get("dcn", {"ms": 1e-9, "flops": 0, "n": 0})
         conv_tf = conv["flops"] / (conv["ms"] * 1e-3) / 1e12
         dcn_tf = dcn["flops"] / (dcn["ms"] * 1e-3) / 1e12
-        roofline = {"kernel": "igemm_kernel<false> (TMA-fed tcgen05 conv, %d launches/step)" % conv["n"], "bound": "tensor",
+        roofline = {"kernel": "igemm_kernel<0|2> (TMA-fed tcgen05 conv, %d launches/step)" % conv["n"], "bound": "tensor",
                     "achieved": round(conv_tf, 2), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                     "frac": round(conv_tf / pk["tf_sustained"], 4), "traffic": None,
                     "peak_source": pk["source"] + " sustained (kernel timed inside a long step)",
                     "share_of_step": round(conv["ms"] / tot_ms, 4),
                     "algorithmic_gflop_per_step": round(conv["flops"] / 1e9, 1)}
-        dcn_line = {"kernel": "igemm_kernel<true> (fused sampling + tcgen05 DCN, %d launches/step)" % dcn["n"],
+        dcn_line = {"kernel": "igemm_kernel<1> (fused sampling + tcgen05 DCN, %d launches/step)" % dcn["n"],
                     "achieved": round(dcn_tf, 2), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                     "frac": round(dcn_tf / pk["tf_sustained"], 4), "share_of_step": round(dcn["ms"] / tot_ms, 4),
                     "algorithmic_gflop_per_step": round(dcn["flops"] / 1e9, 1)}

@@ -43,7 +43,7 @@ constexpr int kMaxEpiBufs = 12;
 // their epilogue math is latency-bound with one warp per scheduler.  The gather kernel keeps one group (its threads
 // go to the producers).  Warp 2 is the epilogue DMA warp: it alone issues the residual loads and the output stores.
 __host__ __device__ constexpr int epi_groups(bool gather) { return gather ? 1 : 4; }
-__host__ __device__ constexpr int kEpiWarp0 = 3;
+constexpr int kEpiWarp0 = 4;  // warps: 0 = A producer (TMA), 1 = MMA issuer, 2 = epilogue DMA, 3 = B producer (TMA)
 __host__ __device__ constexpr int base_warps(bool gather) { return kEpiWarp0 + 4 * epi_groups(gather); }
 
 struct IgemmParams {
@@ -51,7 +51,8 @@ struct IgemmParams {
     int ksize, stride, flags, block_n;
     int tile_w, tile_h, tiles_x, tiles_y;
     int num_n_blocks, num_tiles, k_blocks, cchunks;
-    int out_ld, res_ld, shuf_c, stages;
+    int out_ld, res_ld, shuf_c;
+    int a_stages;  // depth of the A ring
     int pk_h, pk_w;        // STEM: rows / columns of the packed space-to-depth buffer
     int x_ld;              // elements between consecutive input pixels
     int epi_tma, res_tma;  // epilogue stores through TMA / residual prefetched through TMA
@@ -60,12 +61,18 @@ struct IgemmParams {
     int ss_shared;         // one scale/shift copy for the CTA (single n-block) instead of one per group
     int res_bytes;         // bytes of one residual box (16 KB, or 4 KB for the half-resolution RES_UP2 box)
     int b_resident;        // the whole weight matrix stays in shared memory for the CTA's lifetime (small N x K)
+    int dbg;               // development probes (B200_DEBUG): 1 = no MMA issue, 2 = no A loads, 4 = no epilogue math
     const __nv_bfloat16* x;
     const float* scale;
     const float* shift;
     const __nv_bfloat16* residual;
     void* y;
     const void* offsets;
+    int b_stages;  // depth of the B ring (share mode)
+    int a_kb;      // k-blocks one A stage serves: 3 = a (tile_h+2)-row box of one (chunk, kx) feeds the taps ky = 0..2
+    int a_bytes;   // bytes of one A stage
+    int a_shift;   // share mode: bytes between the A tiles of consecutive ky inside the box (tile_w * 128)
+    int b_kb;      // k-blocks of weights per B stage
 };
 
 struct TmapPack {
@@ -80,8 +87,10 @@ struct SmemLayout {
     uint8_t* b;
     uint8_t* epi;  // epi_bufs x 16 KB
     float* ss;     // scale[256] then shift[256] of the current n-block (one copy, or one per epilogue group)
-    uint64_t* full;
-    uint64_t* empty;
+    uint64_t* a_full;
+    uint64_t* a_empty;
+    uint64_t* b_full;
+    uint64_t* b_empty;
     uint64_t* tfull;
     uint64_t* tempty;
     uint64_t* res_full;   // [kMaxEpiBufs] residual box landed in the buffer
@@ -97,14 +106,16 @@ __device__ __forceinline__ SmemLayout carve(uint8_t* raw, const IgemmParams& p) 
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
     SmemLayout s;
     s.a = base;
-    s.b = s.a + p.stages * kABytes;
-    s.epi = s.b + (p.b_resident ? p.k_blocks : p.stages) * p.block_n * 128;
+    s.b = s.a + p.a_stages * p.a_bytes;
+    s.epi = s.b + (p.b_resident ? p.k_blocks : (p.a_kb == 3 ? p.b_stages * 3 : p.a_stages)) * p.block_n * 128;
     uint8_t* rest = s.epi + p.epi_bufs * kABytes;
     s.ss = reinterpret_cast<float*>(rest);
     uint8_t* bars = rest + (p.ss_shared ? 1 : G) * 2048;
-    s.full = reinterpret_cast<uint64_t*>(bars);
-    s.empty = s.full + kMaxStages;
-    s.tfull = s.empty + kMaxStages;
+    s.a_full = reinterpret_cast<uint64_t*>(bars);
+    s.a_empty = s.a_full + kMaxStages;
+    s.b_full = s.a_empty + kMaxStages;
+    s.b_empty = s.b_full + kMaxStages;
+    s.tfull = s.b_empty + kMaxStages;
     s.tempty = s.tfull + 2;
     s.res_full = s.tempty + 2;
     s.slot_free = s.res_full + kMaxEpiBufs;
@@ -113,6 +124,23 @@ __device__ __forceinline__ SmemLayout carve(uint8_t* raw, const IgemmParams& p) 
     s.tmem_slot = reinterpret_cast<uint32_t*>(s.b_ready + 1);
     return s;
 }
+
+// Development counters (B200_DEBUG & 16): cycles block 0 spends in each wait, read with b200_igemm_debug_counters().
+__device__ unsigned long long g_prof[16];
+#ifdef B200_PROF
+#define B200_TIMED_WAIT(slot, stmt)                                                     \
+    do {                                                                                \
+        if (p.dbg & 16) {                                                               \
+            const long long t_ = clock64();                                             \
+            stmt;                                                                       \
+            if (blockIdx.x == 0 && lane == 0) g_prof[slot] += clock64() - t_;           \
+        } else {                                                                        \
+            stmt;                                                                       \
+        }                                                                               \
+    } while (0)
+#else
+#define B200_TIMED_WAIT(slot, stmt) do { stmt; } while (0)
+#endif
 
 struct TileCoord {
     int n, y0, x0, nb;
@@ -265,17 +293,22 @@ __device__ __forceinline__ void epilogue_direct32(const IgemmParams& p, const ui
 }
 
 // ------------------------------------------------------------------------------------------ kernel
-template <bool kGather>
-__global__ void __launch_bounds__((base_warps(kGather) + (kGather ? kGatherWarps : 0)) * 32, 1)
+// kVariant: 0 = TMA-fed conv (one A tile + one weight k-block per stage), 1 = gather producers (DCN / stem fallback),
+// 2 = TMA-fed 3x3 stride-1 conv in share mode.  Separate instantiations: the loops of one variant must not cost the
+// others registers or instructions (the MMA warp and the epilogue warps are latency-critical).
+template <int kVariant>
+__global__ void __launch_bounds__((base_warps(kVariant == 1) + (kVariant == 1 ? kGatherWarps : 0)) * 32, 1)
 igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
     extern __shared__ uint8_t smem_raw[];
+    constexpr bool kGather = (kVariant == 1);
+    constexpr bool kShare = (kVariant == 2);
     constexpr int kBaseWarps = base_warps(kGather);
     constexpr int G = epi_groups(kGather);
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int b_bytes = p.block_n * 128;
     const SmemLayout sm = carve<kGather>(smem_raw, p);
-    const int stages = p.stages;
+    const int stages = p.a_stages;  // A ring depth (the gather producers fill it too)
     const uint32_t tmem_cols = (2 * p.block_n < 32) ? 32u : static_cast<uint32_t>(2 * p.block_n);
 
     if (warp == 0 && lane == 0) {
@@ -294,8 +327,14 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < stages; ++s) {
-                mbar_init(&sm.full[s], kGather ? 1 + kGatherWarps : 1);
-                mbar_init(&sm.empty[s], 1);
+                mbar_init(&sm.a_full[s], kGather ? 1 + kGatherWarps : 1);
+                mbar_init(&sm.a_empty[s], 1);
+            }
+            if constexpr (kShare) {
+                for (int s = 0; s < p.b_stages; ++s) {
+                    mbar_init(&sm.b_full[s], 1);
+                    mbar_init(&sm.b_empty[s], 1);
+                }
             }
             for (int a = 0; a < 2; ++a) {
                 mbar_init(&sm.tfull[a], 1);
@@ -323,27 +362,53 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *sm.tmem_slot;
+#ifdef B200_PROF
+    const long long prof_t0 = (p.dbg & 16) ? clock64() : 0;
+#endif
 
     if (warp == 0) {
         // ===================================================================== TMA producer
-        if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 0;
-            const int taps = p.k_blocks / p.cchunks;  // K is ordered (64-channel chunk, tap)
-            if (p.b_resident) {  // small weight matrix: fetch it once, every tile multiplies against the same copy
+        // (converged warp, one elected lane issues -- see the MMA warp)
+        if (p.b_resident) {  // small weight matrix: fetch it once, every tile multiplies against the same copy
+            if (elect_one()) {
                 mbar_arrive_expect_tx(sm.b_ready, p.k_blocks * b_bytes);
                 for (int kb = 0; kb < p.k_blocks; ++kb)
                     tma_load_2d(sm.b + kb * b_bytes, &tm.b, sm.b_ready, kb * kBlockK, 0);
             }
+            __syncwarp();
+        }
+        int s = 0;
+        uint32_t ph = 0;
+        if constexpr (kShare) {
+            // Share mode: one box of tile_h+2 rows per (chunk, kx); the MMA warp reads the taps ky = 0..2 out of it at
+            // row offsets, so a 3x3 stride-1 conv pulls 3*(tile_h+2)/tile_h tiles per chunk through L2 instead of 9 and
+            // pays one barrier round trip per 3 k-blocks.  The weights travel on their own ring (warp 3).
+            const uint32_t tx_bytes = (p.dbg & 2) ? 0u : static_cast<uint32_t>(p.a_bytes);
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const TileCoord t = decode_tile(p, tile);
+                for (int c0 = 0; c0 < p.in_c; c0 += kBlockK) {
+                    for (int kx = 0; kx < 3; ++kx) {
+                        B200_TIMED_WAIT(0, mbar_wait(&sm.a_empty[s], ph ^ 1));
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(&sm.a_full[s], tx_bytes);
+                            if (!(p.dbg & 2))
+                                tma_load_4d(sm.a + s * p.a_bytes, &tm.a[0], &sm.a_full[s], c0, t.x0 + kx - 1, t.y0 - 1, t.n);
+                        }
+                        __syncwarp();
+                        if (++s == stages) { s = 0; ph ^= 1; }
+                    }
+                }
+            }
+        } else {
+            // One 128-pixel A tile and one weight k-block per stage, both landing on the stage's barrier.
+            const int taps = p.k_blocks / p.cchunks;  // K is ordered (64-channel chunk, tap)
+            const uint32_t tx_bytes = ((kGather || (p.dbg & 2)) ? 0 : kABytes) + (p.b_resident ? 0 : b_bytes);
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const TileCoord t = decode_tile(p, tile);
                 int tap = 0, c0 = 0;
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
-                    mbar_wait(&sm.empty[s], ph ^ 1);
-                    mbar_arrive_expect_tx(&sm.full[s], (kGather ? 0 : kABytes) + (p.b_resident ? 0 : b_bytes));
+                    int ax = t.x0, ay = t.y0, view = 0;
                     if (!kGather) {
-                        int ax = t.x0, ay = t.y0;
-                        const CUtensorMap* ma = &tm.a[0];
                         if (p.mode == B200_IGEMM_STEM) {
                             ay += tap;  // tap = block row of the 4x4 window; the view's rows overlap by 3 blocks
                         } else if (p.ksize == 3) {
@@ -353,14 +418,21 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                                 ay += ky - 1;
                             } else {
                                 // input pixel (2*oy + ky - 1, 2*ox + kx - 1) on the (row parity, column parity) view
-                                ma = &tm.a[(((ky + 1) & 1) << 1) | ((kx + 1) & 1)];
+                                view = (((ky + 1) & 1) << 1) | ((kx + 1) & 1);
                                 ax += (kx == 0) ? -1 : 0;
                                 ay += (ky == 0) ? -1 : 0;
                             }
                         }
-                        tma_load_4d(sm.a + s * kABytes, ma, &sm.full[s], c0, ax, ay, t.n);
                     }
-                    if (!p.b_resident) tma_load_2d(sm.b + s * b_bytes, &tm.b, &sm.full[s], kb * kBlockK, t.nb * p.block_n);
+                    B200_TIMED_WAIT(0, mbar_wait(&sm.a_empty[s], ph ^ 1));
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&sm.a_full[s], tx_bytes);
+                        if (!kGather && !(p.dbg & 2))
+                            tma_load_4d(sm.a + s * kABytes, &tm.a[view], &sm.a_full[s], c0, ax, ay, t.n);
+                        if (!p.b_resident)
+                            tma_load_2d(sm.b + s * b_bytes, &tm.b, &sm.a_full[s], kb * kBlockK, t.nb * p.block_n);
+                    }
+                    __syncwarp();
                     if (++s == stages) { s = 0; ph ^= 1; }
                     if (++tap == taps) { tap = 0; c0 += kBlockK; }
                 }
@@ -368,49 +440,105 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
         }
     } else if (warp == 1) {
         // ===================================================================== MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(static_cast<uint32_t>(p.block_n));
-            if (p.b_resident) mbar_wait(sm.b_ready, 0);
-            int s = 0;
-            uint32_t ph = 0;
-            int it = 0;
+        // The whole warp runs the loop converged and one elected lane issues: every operand of UTCHMMA / UTCBAR then
+        // lives in uniform registers.  (Inside an `if (lane == 0)` region ptxas wraps each uniform-datapath
+        // instruction in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop, ~80 cycles per MMA: small-N layers were bound by
+        // this thread, not by the tensor pipe.)
+        // UTCHMMA back-pressures this thread (the tensor-core queue holds only a few instructions), so whatever the loop
+        // spends between MMAs is tensor-pipe idle time whenever a k-block is short: each mode gets its own lean loop.
+        const uint32_t idesc = umma_idesc_bf16(static_cast<uint32_t>(p.block_n));
+        if (p.b_resident) mbar_wait(sm.b_ready, 0);
+        const uint32_t a0 = smem_u32(sm.a), b0 = smem_u32(sm.b);
+        int s = 0;
+        uint32_t ph = 0;
+        int it = 0;
+        if constexpr (kShare) {
+            // share mode: one A stage (and one weight stage, unless the weights are resident) = 3 k-blocks = 12 MMAs
+            const bool b_ring = !p.b_resident;
+            const int bst = p.b_stages, a_per_tile = p.k_blocks / 3;
+            const uint32_t sh = static_cast<uint32_t>(p.a_shift) >> 4, be = static_cast<uint32_t>(b_bytes) >> 4;
+            int bs = 0;
+            uint32_t bph = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-                const int as = it & 1;
-                const uint32_t aph = (it >> 1) & 1;
-                mbar_wait(&sm.tempty[as], aph ^ 1);
+                const int acc = it & 1;
+                B200_TIMED_WAIT(2, mbar_wait(&sm.tempty[acc], ((it >> 1) & 1) ^ 1));
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.block_n);
-                for (int kb = 0; kb < p.k_blocks; ++kb) {
-                    mbar_wait(&sm.full[s], ph);
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.block_n);
+                int wbase = 0, kx = 0;  // resident weights: k-block of (chunk, ky = 0, kx)
+                for (int ai = 0; ai < a_per_tile; ++ai) {
+                    B200_TIMED_WAIT(3, mbar_wait(&sm.a_full[s], ph));
+                    if (b_ring) B200_TIMED_WAIT(4, mbar_wait(&sm.b_full[bs], bph));
                     tc_fence_after();
-                    const uint64_t da = umma_desc_sw128(smem_u32(sm.a + s * kABytes));
-                    const uint64_t db = umma_desc_sw128(smem_u32(sm.b + (p.b_resident ? kb : s) * b_bytes));
+                    const uint64_t da = umma_desc_sw128(a0 + s * p.a_bytes);
+                    const uint64_t db = umma_desc_sw128(b0 + (b_ring ? bs * 3 : wbase) * b_bytes);
+                    if (elect_one()) {
+                        if (!(p.dbg & 1)) {
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
-                        // +32 bytes per UMMA_K step inside the 128B swizzle atom (encoded >> 4)
-                        umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                            for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+                                for (int k = 0; k < kBlockK / 16; ++k)
+                                    umma_bf16(d_tmem, da + ky * sh + 2 * k, db + ky * (b_ring ? be : 3 * be) + 2 * k, idesc,
+                                              (ai | ky | k) ? 1u : 0u);
+                            }
+                        }
+                        umma_commit(&sm.a_empty[s]);
+                        if (b_ring) umma_commit(&sm.b_empty[bs]);
                     }
-                    umma_commit(&sm.empty[s]);
+                    __syncwarp();
+                    if (++s == stages) { s = 0; ph ^= 1; }
+                    if (b_ring && ++bs == bst) { bs = 0; bph ^= 1; }
+                    if (++kx == 3) { kx = 0; wbase += 7; } else { ++wbase; }
+                }
+                if (elect_one()) umma_commit(&sm.tfull[acc]);
+                __syncwarp();
+            }
+        } else {
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                B200_TIMED_WAIT(2, mbar_wait(&sm.tempty[acc], ((it >> 1) & 1) ^ 1));
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.block_n);
+                for (int kb = 0; kb < p.k_blocks; ++kb) {
+                    B200_TIMED_WAIT(3, mbar_wait(&sm.a_full[s], ph));
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_sw128(a0 + s * kABytes);
+                    const uint64_t db = umma_desc_sw128(b0 + (p.b_resident ? kb : s) * b_bytes);
+                    if (elect_one()) {
+                        if (!(p.dbg & 1)) {
+#pragma unroll
+                            for (int k = 0; k < kBlockK / 16; ++k) {
+                                // +32 bytes per UMMA_K step inside the 128B swizzle atom (encoded >> 4)
+                                umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                            }
+                        }
+                        umma_commit(&sm.a_empty[s]);
+                    }
+                    __syncwarp();
                     if (++s == stages) { s = 0; ph ^= 1; }
                 }
-                umma_commit(&sm.tfull[as]);
+                if (elect_one()) umma_commit(&sm.tfull[acc]);
+                __syncwarp();
             }
         }
     } else if (warp == 2) {
         // ===================================================================== epilogue DMA warp
-        // One thread owns every epilogue TMA transfer.  Chunk g (CTA-wide order) uses buffer g % B.  After the store of
-        // chunk g is queued, the store of chunk g-1 has surely read its buffer (wait_group.read 1), so that buffer
-        // is recycled: the residual box of chunk g-1+B is loaded into it (B-1 chunks of prefetch), or it is marked free.
-        if (lane == 0 && p.epi_tma) {
+        // One elected lane owns every epilogue TMA transfer (the warp runs converged).  Chunk g (CTA-wide order) uses
+        // buffer g % B.  After the store of chunk g is queued, the store of chunk g-1 has surely read its buffer
+        // (wait_group.read 1), so that buffer is recycled: the residual box of chunk g-1+B is loaded into it (B-1 chunks
+        // of prefetch), or it is marked free.
+        if (p.epi_tma) {
             const int B = p.epi_bufs, L = (B > 1) ? 1 : 0;
             const bool up2 = (p.flags & B200_EPI_RES_UP2) != 0;
             int ld_tile = blockIdx.x, ld_chunk = 0;
             auto issue_load = [&](int slot) {
                 if (ld_tile >= p.num_tiles) return;
                 const TileCoord t = decode_tile(p, ld_tile);
-                mbar_arrive_expect_tx(&sm.res_full[slot], p.res_bytes);
-                tma_load_4d(sm.epi + slot * kABytes, &tm.res, &sm.res_full[slot], t.nb * p.block_n + ld_chunk * 64,
-                            up2 ? (t.x0 >> 1) : t.x0, up2 ? (t.y0 >> 1) : t.y0, t.n);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&sm.res_full[slot], p.res_bytes);
+                    tma_load_4d(sm.epi + slot * kABytes, &tm.res, &sm.res_full[slot], t.nb * p.block_n + ld_chunk * 64,
+                                up2 ? (t.x0 >> 1) : t.x0, up2 ? (t.y0 >> 1) : t.y0, t.n);
+                }
+                __syncwarp();
                 if (++ld_chunk == chunks_of(p, t.nb)) { ld_chunk = 0; ld_tile += gridDim.x; }
             };
             if (p.res_tma)
@@ -421,24 +549,55 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                 const TileCoord t = decode_tile(p, tile);
                 const int nchunks = chunks_of(p, t.nb);
                 for (int c = 0; c < nchunks; ++c, ++g) {
-                    mbar_wait(&sm.out_ready[slot], par);
-                    const int col0 = t.nb * p.block_n + c * 64;
+                    B200_TIMED_WAIT(5, mbar_wait(&sm.out_ready[slot], par));
+                    int col0 = t.nb * p.block_n + c * 64, view = 0;
                     if (p.flags & B200_EPI_SHUFFLE2) {
-                        const int sub = col0 / p.shuf_c;
-                        tma_store_4d(&tm.out[sub], sm.epi + slot * kABytes, col0 - sub * p.shuf_c, t.x0, t.y0, t.n);
-                    } else {
-                        tma_store_4d(&tm.out[0], sm.epi + slot * kABytes, col0, t.x0, t.y0, t.n);
+                        view = col0 / p.shuf_c;
+                        col0 -= view * p.shuf_c;
                     }
-                    bulk_commit();
+                    if (elect_one()) {
+                        tma_store_4d(&tm.out[view], sm.epi + slot * kABytes, col0, t.x0, t.y0, t.n);
+                        bulk_commit();
+                        if (g >= L) {
+                            B200_TIMED_WAIT(6, if (L) bulk_wait_read1(); else bulk_wait_read0());
+                            if (!p.res_tma) mbar_arrive(&sm.slot_free[rslot]);
+                        }
+                    }
+                    __syncwarp();
                     if (g >= L) {
-                        if (L) bulk_wait_read1(); else bulk_wait_read0();
-                        if (p.res_tma) issue_load(rslot); else mbar_arrive(&sm.slot_free[rslot]);
+                        if (p.res_tma) issue_load(rslot);
                         if (++rslot == B) rslot = 0;
                     }
                     if (++slot == B) { slot = 0; par ^= 1; }
                 }
             }
-            bulk_wait_all();
+            if (elect_one()) bulk_wait_all();
+            __syncwarp();
+        }
+    } else if (warp < kEpiWarp0) {
+        // ===================================================================== weight producer of the share mode (warp 3)
+        // One stage = the three weight k-blocks (ky = 0..2) of one (chunk, kx); the matrix itself stays (chunk, ky, kx).
+        if constexpr (kShare) if (!p.b_resident) {
+            int s = 0;
+            uint32_t ph = 0;
+            const int bst = p.b_stages;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int n0 = (tile % p.num_n_blocks) * p.block_n;
+                for (int kb9 = 0; kb9 < p.k_blocks; kb9 += 9) {
+                    for (int kx = 0; kx < 3; ++kx) {
+                        B200_TIMED_WAIT(1, mbar_wait(&sm.b_empty[s], ph ^ 1));
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(&sm.b_full[s], 3 * b_bytes);
+#pragma unroll
+                            for (int ky = 0; ky < 3; ++ky)
+                                tma_load_2d(sm.b + (s * 3 + ky) * b_bytes, &tm.b, &sm.b_full[s],
+                                            (kb9 + ky * 3 + kx) * kBlockK, n0);
+                        }
+                        __syncwarp();
+                        if (++s == bst) { s = 0; ph ^= 1; }
+                    }
+                }
+            }
         }
     } else if (warp < kBaseWarps) {
         // ===================================================================== epilogue (G groups of 4 warps)
@@ -467,7 +626,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
             const uint32_t aph = (it >> 1) & 1;
             const int oy = t.y0 + ty, ox = t.x0 + tx;
             const bool valid = (oy < p.out_h) && (ox < p.out_w);
-            mbar_wait(&sm.tfull[as], aph);
+            B200_TIMED_WAIT(7, mbar_wait(&sm.tfull[as], aph));
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                    static_cast<uint32_t>(as * p.block_n);
@@ -497,8 +656,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                     const uint32_t buf = smem_u32(sm.epi) + static_cast<uint32_t>(slot) * kABytes;
                     const uint32_t mine = buf + static_cast<uint32_t>(row) * 128;
                     const uint32_t rsd = buf + static_cast<uint32_t>(rrow) * 128;
-                    if (p.res_tma) mbar_wait(&sm.res_full[slot], par);
-                    else mbar_wait(&sm.slot_free[slot], par ^ 1);
+                    B200_TIMED_WAIT(8, if (p.res_tma) mbar_wait(&sm.res_full[slot], par); else mbar_wait(&sm.slot_free[slot], par ^ 1));
                     uint4 rup[8];
                     if (up2) {  // the 4 KB half-resolution box is shared by four pixels: read it before anyone overwrites
 #pragma unroll
@@ -506,6 +664,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                             rup[i] = lds128(rsd + ((static_cast<uint32_t>(i) ^ rswz) << 4));
                         named_bar_sync(1 + eg, kEpiThreads);
                     }
+                    if (!(p.dbg & 4))
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {  // two 32-column halves (register-lean: 19-23 warps per CTA)
                         uint32_t v[32];
@@ -594,13 +753,13 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                         if (valid[q])
                             u[q] = ldg128(img + (static_cast<int64_t>(oy[q] + kb) * p.pk_w + ox[q]) * 16 + l8 * 8);
                     }
-                    mbar_wait(&sm.empty[s], ph ^ 1);
+                    mbar_wait(&sm.a_empty[s], ph ^ 1);
                     uint8_t* a = sm.a + s * kABytes;
 #pragma unroll
                     for (int q = 0; q < kPasses; ++q) *reinterpret_cast<uint4*>(a + soff[q]) = u[q];
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&sm.full[s]);
+                    if (lane == 0) mbar_arrive(&sm.a_full[s]);
                     if (++s == stages) { s = 0; ph ^= 1; }
                 }
             } else {
@@ -670,12 +829,12 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                         res.z = B200_BLEND2(z);
                         res.w = B200_BLEND2(w);
 #undef B200_BLEND2
-                        if (q == 0) mbar_wait(&sm.empty[s], ph ^ 1);
+                        if (q == 0) mbar_wait(&sm.a_empty[s], ph ^ 1);
                         sts128(a_base + static_cast<uint32_t>(s) * kABytes + soff[q], res);
                         if (q == 1) {
                             fence_proxy_async_smem();
                             __syncwarp();
-                            if (lane == 0) mbar_arrive(&sm.full[s]);
+                            if (lane == 0) mbar_arrive(&sm.a_full[s]);
                             if (++s == stages) { s = 0; ph ^= 1; }
                         }
                     }
@@ -688,6 +847,9 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
 
     tc_fence_before();
     __syncthreads();
+#ifdef B200_PROF
+    if ((p.dbg & 16) && blockIdx.x == 0 && threadIdx.x == 0) g_prof[9] += clock64() - prof_t0;
+#endif
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, tmem_cols);
@@ -831,9 +993,23 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     p.stride = d->stride;
     p.flags = d->flags;
     p.block_n = block_n;
+    // 3x3 stride-1 convs share one (tile_h+2)-row activation box between the taps ky = 0..2 of a kernel column
+    // ("share mode"): tall tiles (8 rows x 16 pixels) make that 2.4x less L2->SM traffic and a third of the barrier
+    // round trips (a hand-shake costs ~380 cycles whatever it carries, a 128 x N x 64 MMA block only 2*N).
+    // Only narrow GEMMs (N <= 128) take it: at N = 256 a k-block is 512 MMA cycles and hides everything already.
+    const bool share = (d->mode == B200_IGEMM_CONV && d->ksize == 3 && d->stride == 1 && block_n <= 128 &&
+                        !getenv("B200_NO_SHARE"));
     // RES_UP2 reads a half-resolution residual box: the tile needs at least two rows
-    p.tile_w = pick_tile_w(p.out_h, p.out_w, (d->flags & B200_EPI_RES_UP2) ? 64 : 128);
+    int max_tw = (d->flags & B200_EPI_RES_UP2) ? 64 : 128;
+    if (share) max_tw = 16;
+    if (const char* e = getenv("B200_CONV_TW")) { if (atoi(e) >= 8 && (share || atoi(e) < max_tw)) max_tw = atoi(e); }
+    if (const char* e = getenv("B200_DEBUG")) p.dbg = atoi(e);
+    p.tile_w = pick_tile_w(p.out_h, p.out_w, max_tw);
     p.tile_h = kBlockM / p.tile_w;
+    p.a_kb = share ? 3 : 1;
+    p.a_bytes = share ? (p.tile_h + 2) * p.tile_w * 128 : kABytes;
+    p.a_shift = share ? p.tile_w * 128 : 0;
+    p.b_kb = 1;
     p.tiles_x = (p.out_w + p.tile_w - 1) / p.tile_w;
     p.tiles_y = (p.out_h + p.tile_h - 1) / p.tile_h;
     p.num_n_blocks = d->n_pad / block_n;
@@ -885,16 +1061,42 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     // Small weight matrices (stem, layer1, ConvT, ...) live in shared memory for the whole launch: no per-tile weight
     // TMA traffic, the ring carries activations only.
     p.b_resident = (p.num_n_blocks == 1 && p.k_blocks * b_bytes <= 72 * 1024 && d->mode != B200_IGEMM_DCN) ? 1 : 0;
-    const int stage_bytes = p.b_resident ? kABytes : kABytes + b_bytes;
     p.ss_shared = (p.num_n_blocks == 1) ? 1 : 0;
     const int fixed = 1024 /*alignment*/ + 1024 /*barriers*/ + (p.ss_shared ? 1 : G) * 2048 /*scale+shift*/ +
                       (p.b_resident ? p.k_blocks * b_bytes : 0);
     // The DCN gather lives on L1 hits (K ordered chunk-major), so it keeps its carve-out <= 132 KB and leaves the
     // rest of the 256 KB to L1; everything else may use the full 227 KB opt-in.
     const int cap = (d->mode == B200_IGEMM_DCN) ? 131 * 1024 : kMaxSmem;
-    int stages, bufs = 0, ga = 1;
+    const int a_bytes = p.a_bytes;
+    int max_stages = kMaxStages;
+    if (const char* e = getenv("B200_STAGES")) { if (atoi(e) >= 2 && atoi(e) < max_stages) max_stages = atoi(e); }
+    // Ring depths for `avail` bytes; returns false if the minimum does not fit.
+    int a_st = 0, b_st = 0, b_kb = 1;
+    auto rings = [&](int avail) -> bool {
+        b_kb = 1;
+        if (p.b_resident) {
+            a_st = avail / a_bytes;
+            b_st = 0;
+            if (a_st > max_stages) a_st = max_stages;
+            return a_st >= 2;
+        }
+        if (!share) {  // one A tile and one weight k-block per stage, rings of equal depth
+            a_st = b_st = avail / (a_bytes + b_bytes);
+            if (a_st > max_stages) a_st = b_st = max_stages;
+            return a_st >= 2;
+        }
+        // share mode: an A stage feeds three k-blocks and so does a weight stage (three k-blocks of block_n rows)
+        const int n = avail / (a_bytes + 3 * b_bytes);
+        if (n < 2) return false;
+        b_kb = 3;
+        a_st = b_st = (n > max_stages) ? max_stages : n;
+        if (avail - a_st * (a_bytes + 3 * b_bytes) >= a_bytes && a_st < max_stages) ++a_st;
+        return true;
+    };
+    int bufs = 0, ga = 1;
+    bool ok;
     if (!p.epi_tma) {
-        stages = (cap - fixed) / stage_bytes;
+        ok = rings(cap - fixed);
     } else {
         // Split the shared memory between mainloop stages and epilogue buffers by where the time goes:
         // mainloop ~ k_blocks * 2 * block_n cycles per tile (tcgen05 issue rate), epilogue ~ 1600 cycles per 64-column
@@ -905,16 +1107,16 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
         ga = (epi_clk + main_clk - 1) / main_clk;
         if (ga > G) ga = G;
         if (ga < 1) ga = 1;
-        const int min_stages = p.k_blocks >= 4 ? 3 : 2;
         bufs = (ga == 1 && !p.res_tma) ? 1 : ga + 1 + (p.res_tma ? 2 : 0);
-        stages = (cap - fixed - bufs * kABytes) / stage_bytes;
-        while (stages < min_stages && bufs > 1) {
+        ok = rings(cap - fixed - bufs * kABytes);
+        const int want = (p.k_blocks >= 4 && !share) ? 3 : 2;
+        while ((!ok || a_st < want) && bufs > 1) {
             --bufs;
-            stages = (cap - fixed - bufs * kABytes) / stage_bytes;
+            ok = rings(cap - fixed - bufs * kABytes);
         }
-        if (stages > kMaxStages) stages = kMaxStages;
-        if (stages >= 2) {
-            bufs = (cap - fixed - stages * stage_bytes) / kABytes;  // leftovers deepen the residual prefetch
+        if (ok) {  // leftovers deepen the residual prefetch
+            const int used = a_st * a_bytes + (p.b_resident ? 0 : (share ? b_st * 3 : a_st) * b_bytes);
+            bufs = (cap - fixed - used) / kABytes;
             if (bufs > kMaxEpiBufs) bufs = kMaxEpiBufs;
         }
         if (bufs < 1) {
@@ -923,17 +1125,22 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
         }
         if (ga > bufs - 1) ga = bufs > 1 ? bufs - 1 : 1;
     }
-    if (stages > kMaxStages) stages = kMaxStages;
-    if (stages < 2) {
+    if (!ok) {
         delete op;
         return set_error("igemm: not enough shared memory for two pipeline stages");
     }
-    p.stages = stages;
+    p.a_stages = a_st;
+    p.b_stages = b_st;
+    p.b_kb = b_kb;
     p.epi_bufs = bufs;
     p.epi_active = ga;
-    op->smem_bytes = fixed + stages * stage_bytes + bufs * kABytes;
+    op->smem_bytes = fixed + a_st * a_bytes + (p.b_resident ? 0 : (share ? b_st * 3 : a_st) * b_bytes) + bufs * kABytes;
 
     op->threads = (base_warps(op->gather) + (op->gather ? kGatherWarps : 0)) * 32;
+    if (getenv("B200_VERBOSE"))
+        fprintf(stderr, "igemm plan: mode %d k %d s %d N %d kb %d tile %dx%d share %d resident %d a_stages %d (x %d B) b_stages %d bufs %d ga %d smem %d\n",
+                p.mode, p.ksize, p.stride, p.block_n, p.k_blocks, p.tile_w, p.tile_h, p.a_kb == 3, p.b_resident, p.a_stages,
+                p.a_bytes, p.b_stages, p.epi_bufs, p.epi_active, op->smem_bytes);
 
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess ||
@@ -955,7 +1162,8 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     if (!err && !op->gather && d->mode != B200_IGEMM_STEM) {
         const uint64_t C = d->in_c, W = d->in_w, H = d->in_h, LD = x_ld;
         if (d->stride == 1) {
-            err |= encode_nhwc(&op->tm.a[0], d->x, C, W, H, d->batch, LD, 1, 1, W, H * W, p.tile_w, p.tile_h, "activations");
+            err |= encode_nhwc(&op->tm.a[0], d->x, C, W, H, d->batch, LD, 1, 1, W, H * W, p.tile_w,
+                               share ? p.tile_h + 2 : p.tile_h, "activations");
         } else {
             // stride 2: four (row parity, column parity) strided views of the NHWC tensor
             const int nviews = (d->ksize == 3) ? 4 : 1;
@@ -995,11 +1203,13 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
         return 1;
     }
     // the attribute is per kernel function, not per op: always raise it to the full 227 KB opt-in
-    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e == cudaSuccess)  // let the gather kernel's L1 have what its launches do not ask for as shared memory
-        e = cudaFuncSetAttribute(igemm_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+        e = cudaFuncSetAttribute(igemm_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+        e = cudaFuncSetAttribute(igemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(igemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) {
         delete op;
         return set_error("igemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -1012,12 +1222,21 @@ extern "C" int b200_igemm_launch(const b200_igemm* op, void* stream) {
     if (!op) return set_error("b200_igemm_launch: null op");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (op->gather)
-        igemm_kernel<true><<<op->grid, op->threads, op->smem_bytes, st>>>(op->tm, op->p);
+        igemm_kernel<1><<<op->grid, op->threads, op->smem_bytes, st>>>(op->tm, op->p);
+    else if (op->p.a_kb == 3)
+        igemm_kernel<2><<<op->grid, op->threads, op->smem_bytes, st>>>(op->tm, op->p);
     else
-        igemm_kernel<false><<<op->grid, op->threads, op->smem_bytes, st>>>(op->tm, op->p);
+        igemm_kernel<0><<<op->grid, op->threads, op->smem_bytes, st>>>(op->tm, op->p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("igemm launch failed: %s", cudaGetErrorString(e));
     return 0;
+}
+
+// development aid (not declared in the public header): read and clear the B200_DEBUG & 16 counters
+extern "C" int b200_igemm_debug_counters(unsigned long long* out) {
+    unsigned long long zero[16] = {0};
+    if (cudaMemcpyFromSymbol(out, b200::g_prof, sizeof(zero)) != cudaSuccess) return 1;
+    return cudaMemcpyToSymbol(b200::g_prof, zero, sizeof(zero)) != cudaSuccess;
 }
 
 extern "C" int b200_igemm_destroy(b200_igemm* op) {

@@ -29,7 +29,16 @@ def run(name, b, h, w, ci, co, k, s, flags, res=False, shuf=0, iters=20):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     byts = x.numel() * 2 + y.numel() * 2 + (r.numel() * 2 if res else 0)
-    print(f"{name:28s} {ms:7.3f} ms  {byts / ms / 1e9:7.2f} TB/s  {op.flops / ms / 1e9:8.1f} TF/s  dbg={os.environ.get('B200_DEBUG_EPI','0')}", flush=True)
+    if int(os.environ.get("B200_DEBUG", "0")) & 16:
+        import ctypes as C
+        from ocr_vi_invoice_b200 import _lib
+        buf = (C.c_ulonglong * 16)()
+        _lib.load().b200_igemm_debug_counters(buf)   # clear
+        op(); torch.cuda.synchronize()
+        _lib.load().b200_igemm_debug_counters(buf)
+        names = ["A.empty", "B.empty", "mma.tempty", "mma.a_full", "mma.b_full", "dma.out_ready", "dma.wait_read", "epi.tfull", "epi.slot", "total"]
+        print("   " + "  ".join(f"{n}={buf[i]}" for i, n in enumerate(names)))
+    print(f"{name:28s} {ms:7.3f} ms  {byts / ms / 1e9:7.2f} TB/s  {op.flops / ms / 1e9:8.1f} TF/s  {op.info()}", flush=True)
 
 if __name__ == "__main__" and os.environ.get("EPI_SET") == "gemm":
     for n in (64, 128, 256):
