@@ -107,7 +107,7 @@ __device__ __forceinline__ SmemLayout carve(uint8_t* raw, const IgemmParams& p) 
     SmemLayout s;
     s.a = base;
     s.b = s.a + p.a_stages * p.a_bytes;
-    s.epi = s.b + (p.b_resident ? p.k_blocks : (p.a_kb == 3 ? p.b_stages * 3 : p.a_stages)) * p.block_n * 128;
+    s.epi = s.b + (p.b_resident ? p.k_blocks : (p.a_kb > 1 ? p.b_stages * 3 : p.a_stages)) * p.block_n * 128;
     uint8_t* rest = s.epi + p.epi_bufs * kABytes;
     s.ss = reinterpret_cast<float*>(rest);
     uint8_t* bars = rest + (p.ss_shared ? 1 : G) * 2048;
@@ -384,8 +384,19 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
             // row offsets, so a 3x3 stride-1 conv pulls 3*(tile_h+2)/tile_h tiles per chunk through L2 instead of 9 and
             // pays one barrier round trip per 3 k-blocks.  The weights travel on their own ring (warp 3).
             const uint32_t tx_bytes = (p.dbg & 2) ? 0u : static_cast<uint32_t>(p.a_bytes);
+            const bool stem = (p.mode == B200_IGEMM_STEM);  // one box per tile: rows y0 .. y0+tile_h+2 of the view
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const TileCoord t = decode_tile(p, tile);
+                if (stem) {
+                    B200_TIMED_WAIT(0, mbar_wait(&sm.a_empty[s], ph ^ 1));
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&sm.a_full[s], tx_bytes);
+                        if (!(p.dbg & 2)) tma_load_4d(sm.a + s * p.a_bytes, &tm.a[0], &sm.a_full[s], 0, t.x0, t.y0, t.n);
+                    }
+                    __syncwarp();
+                    if (++s == stages) { s = 0; ph ^= 1; }
+                    continue;
+                }
                 for (int c0 = 0; c0 < p.in_c; c0 += kBlockK) {
                     for (int kx = 0; kx < 3; ++kx) {
                         B200_TIMED_WAIT(0, mbar_wait(&sm.a_empty[s], ph ^ 1));
@@ -455,8 +466,11 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
         if constexpr (kShare) {
             // share mode: one A stage (and one weight stage, unless the weights are resident) = 3 k-blocks = 12 MMAs
             const bool b_ring = !p.b_resident;
-            const int bst = p.b_stages, a_per_tile = p.k_blocks / 3;
+            const int bst = p.b_stages, akb = p.a_kb, a_per_tile = p.k_blocks / akb;
             const uint32_t sh = static_cast<uint32_t>(p.a_shift) >> 4, be = static_cast<uint32_t>(b_bytes) >> 4;
+            // weight k-blocks between the sub-tiles of a stage: ring stage = 3 consecutive k-blocks; resident 3x3 weights are
+            // (chunk, ky, kx) so ky steps by 3; the stem's four window rows are consecutive
+            const uint32_t wstep = (b_ring || akb == 4) ? be : 3 * be;
             int bs = 0;
             uint32_t bph = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -477,8 +491,12 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                             for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
                                 for (int k = 0; k < kBlockK / 16; ++k)
-                                    umma_bf16(d_tmem, da + ky * sh + 2 * k, db + ky * (b_ring ? be : 3 * be) + 2 * k, idesc,
-                                              (ai | ky | k) ? 1u : 0u);
+                                    umma_bf16(d_tmem, da + ky * sh + 2 * k, db + ky * wstep + 2 * k, idesc, (ai | ky | k) ? 1u : 0u);
+                            }
+                            if (akb == 4) {
+#pragma unroll
+                                for (int k = 0; k < kBlockK / 16; ++k)
+                                    umma_bf16(d_tmem, da + 3 * sh + 2 * k, db + 3 * wstep + 2 * k, idesc, 1u);
                             }
                         }
                         umma_commit(&sm.a_empty[s]);
@@ -1000,15 +1018,18 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     const bool share = (d->mode == B200_IGEMM_CONV && d->ksize == 3 && d->stride == 1 && block_n <= 128 &&
                         !getenv("B200_NO_SHARE"));
     // RES_UP2 reads a half-resolution residual box: the tile needs at least two rows
+    // The stem (4x4 window over the space-to-depth buffer) works the same way: the four window rows of a tile are
+    // tile_h+3 consecutive rows of the overlapping-stride view, one box and one barrier round trip per tile.
+    bool stem_share = (d->mode == B200_IGEMM_STEM && !getenv("B200_STEM_GATHER") && !getenv("B200_NO_SHARE"));
     int max_tw = (d->flags & B200_EPI_RES_UP2) ? 64 : 128;
-    if (share) max_tw = 16;
-    if (const char* e = getenv("B200_CONV_TW")) { if (atoi(e) >= 8 && (share || atoi(e) < max_tw)) max_tw = atoi(e); }
+    if (share || stem_share) max_tw = 16;
+    if (const char* e = getenv("B200_CONV_TW")) { if (atoi(e) >= 8 && (share || stem_share || atoi(e) < max_tw)) max_tw = atoi(e); }
     if (const char* e = getenv("B200_DEBUG")) p.dbg = atoi(e);
     p.tile_w = pick_tile_w(p.out_h, p.out_w, max_tw);
     p.tile_h = kBlockM / p.tile_w;
-    p.a_kb = share ? 3 : 1;
-    p.a_bytes = share ? (p.tile_h + 2) * p.tile_w * 128 : kABytes;
-    p.a_shift = share ? p.tile_w * 128 : 0;
+    p.a_kb = share ? 3 : (stem_share ? 4 : 1);
+    p.a_bytes = share ? (p.tile_h + 2) * p.tile_w * 128 : (stem_share ? (p.tile_h + 3) * p.tile_w * 128 : kABytes);
+    p.a_shift = (share || stem_share) ? p.tile_w * 128 : 0;
     p.b_kb = 1;
     p.tiles_x = (p.out_w + p.tile_w - 1) / p.tile_w;
     p.tiles_y = (p.out_h + p.tile_h - 1) / p.tile_h;
@@ -1036,11 +1057,17 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
         const uint64_t dims[4] = {64, (uint64_t)(d->in_w / 2), (uint64_t)(d->in_h / 2 + 3), (uint64_t)d->batch};
         const uint64_t pkw = d->in_w / 2 + 3, pkh = d->in_h / 2 + 3;
         const uint64_t str[3] = {32, pkw * 32, pkh * pkw * 32};
-        const int tw = pick_tile_w(d->in_h / 2, d->in_w / 2, 128);
-        const uint32_t box[4] = {64u, (uint32_t)tw, (uint32_t)(kBlockM / tw), 1u};
-        if (!getenv("B200_STEM_GATHER") && encode_map(&op->tm.a[0], d->x, 4, dims, str, box, "overlapping stem view") == 0)
+        const uint32_t box[4] = {64u, (uint32_t)p.tile_w, (uint32_t)(stem_share ? p.tile_h + 3 : p.tile_h), 1u};
+        if (!getenv("B200_STEM_GATHER") && encode_map(&op->tm.a[0], d->x, 4, dims, str, box, "overlapping stem view") == 0) {
             op->gather = 0;
+        } else {
+            stem_share = false;
+            p.a_kb = 1;
+            p.a_bytes = kABytes;
+            p.a_shift = 0;
+        }
     }
+    const bool fat = p.a_kb > 1;  // an A stage carries several k-blocks (share variant of the kernel)
 
     // bf16 outputs whose channel count is a multiple of 64 go out through swizzled staging + TMA stores
     p.epi_tma = !(d->flags & (B200_EPI_OUT_F32 | B200_EPI_DCN_COORDS)) && (d->out_c % 64) == 0 &&
@@ -1080,7 +1107,7 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
             if (a_st > max_stages) a_st = max_stages;
             return a_st >= 2;
         }
-        if (!share) {  // one A tile and one weight k-block per stage, rings of equal depth
+        if (!fat) {  // one A tile and one weight k-block per stage, rings of equal depth
             a_st = b_st = avail / (a_bytes + b_bytes);
             if (a_st > max_stages) a_st = b_st = max_stages;
             return a_st >= 2;
@@ -1109,13 +1136,13 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
         if (ga < 1) ga = 1;
         bufs = (ga == 1 && !p.res_tma) ? 1 : ga + 1 + (p.res_tma ? 2 : 0);
         ok = rings(cap - fixed - bufs * kABytes);
-        const int want = (p.k_blocks >= 4 && !share) ? 3 : 2;
+        const int want = (p.k_blocks >= 4 && !fat) ? 3 : 2;
         while ((!ok || a_st < want) && bufs > 1) {
             --bufs;
             ok = rings(cap - fixed - bufs * kABytes);
         }
         if (ok) {  // leftovers deepen the residual prefetch
-            const int used = a_st * a_bytes + (p.b_resident ? 0 : (share ? b_st * 3 : a_st) * b_bytes);
+            const int used = a_st * a_bytes + (p.b_resident ? 0 : (fat ? b_st * 3 : a_st) * b_bytes);
             bufs = (cap - fixed - used) / kABytes;
             if (bufs > kMaxEpiBufs) bufs = kMaxEpiBufs;
         }
@@ -1134,12 +1161,12 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     p.b_kb = b_kb;
     p.epi_bufs = bufs;
     p.epi_active = ga;
-    op->smem_bytes = fixed + a_st * a_bytes + (p.b_resident ? 0 : (share ? b_st * 3 : a_st) * b_bytes) + bufs * kABytes;
+    op->smem_bytes = fixed + a_st * a_bytes + (p.b_resident ? 0 : (fat ? b_st * 3 : a_st) * b_bytes) + bufs * kABytes;
 
     op->threads = (base_warps(op->gather) + (op->gather ? kGatherWarps : 0)) * 32;
     if (getenv("B200_VERBOSE"))
         fprintf(stderr, "igemm plan: mode %d k %d s %d N %d kb %d tile %dx%d share %d resident %d a_stages %d (x %d B) b_stages %d bufs %d ga %d smem %d\n",
-                p.mode, p.ksize, p.stride, p.block_n, p.k_blocks, p.tile_w, p.tile_h, p.a_kb == 3, p.b_resident, p.a_stages,
+                p.mode, p.ksize, p.stride, p.block_n, p.k_blocks, p.tile_w, p.tile_h, p.a_kb, p.b_resident, p.a_stages,
                 p.a_bytes, p.b_stages, p.epi_bufs, p.epi_active, op->smem_bytes);
 
     int dev = 0, sms = 0;
@@ -1223,7 +1250,7 @@ extern "C" int b200_igemm_launch(const b200_igemm* op, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (op->gather)
         igemm_kernel<1><<<op->grid, op->threads, op->smem_bytes, st>>>(op->tm, op->p);
-    else if (op->p.a_kb == 3)
+    else if (op->p.a_kb > 1)
         igemm_kernel<2><<<op->grid, op->threads, op->smem_bytes, st>>>(op->tm, op->p);
     else
         igemm_kernel<0><<<op->grid, op->threads, op->smem_bytes, st>>>(op->tm, op->p);
