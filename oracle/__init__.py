@@ -10,9 +10,10 @@ Pinning status (see DESIGN.md "Oracle"):
     (/root/reference/model/det, imported unchanged) by tests/golden/make_golden.py -> tests/golden/*.npz
   * deformable conv (deform_conv2d_ref) -- pinned against torchvision.ops.deform_conv2d (the third-party
     op the reference calls at model/det/dcn.py:48; unpinned version, 0.26.0 installed) via golden vectors
-  * post-processing (postproc_oracle.py) -- PARITY UNPINNED against the reference's own boxes: the
-    reference path needs pyclipper + shapely (src/det/test.py:17-18), neither is installed and there is
-    no network.  It is pinned instead against the cv2 half of the reference path (findContours /
-    approxPolyDP / box_score_fast run here, golden in tests/golden/postproc_cv2.npz) as an agreement
-    rate, not bit-exactness.
+  * post-processing (postproc_oracle.py) -- pinned against runs of the reference's own
+    DBPostProcessor.__call__ (src/det/test.py imported unchanged by tests/golden/make_postproc_reference.py;
+    the absent pyclipper / shapely replaced by clipper_offset.py, a restatement of Clipper 6.4.2's
+    ClipperOffset without its final union): exact rectangles and scores on rectangular components, an
+    agreement rate on noisy ones.  PARTIALLY PINNED: Clipper's union step / polygon vertex lists are not
+    reproduced (the consumer only takes cv2.boundingRect of a box).
 """

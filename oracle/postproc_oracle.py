@@ -5,8 +5,19 @@ Python loop and un-clips each polygon with pyclipper.  BASELINE.json's north sta
 connected-component labelling -> per-component box extraction and mean-score filtering on the GPU, with the
 label map and boxes bit-exact "given identical binarised maps".  This file is the CPU statement of exactly
 that contract; the CUDA path in ocr_vi_invoice_b200/csrc/postproc.cu must reproduce
-it bit for bit.  PARITY UNPINNED against the reference's own boxes (pyclipper / shapely are not installable
-here); `cv2_reference_path` restates the half of the reference that can run, for an agreement-rate check.
+it bit for bit.
+
+Pinning.  The reference's own `DBPostProcessor.__call__` was run in the authoring container on rendered maps
+(tests/golden/make_postproc_reference.py: src/det/test.py imported unchanged; pyclipper / shapely, which are not
+installable here, replaced by oracle/clipper_offset.py, a restatement of Clipper 6.4.2's ClipperOffset without its
+final self-intersection union -- the bounding rectangle of a box, all the reference's consumer reads, is unaffected).
+Against those goldens (tests/golden/postproc_reference.npz, tests/test_oracle.py):
+  * `cv2_reference_path` (the restated cv2 half + closed-form bounding-rectangle growth) reproduces the reference's
+    bounding rectangles and scores exactly, in order;
+  * this contract's boxes and scores EQUAL the reference's on maps whose components are axis-aligned rectangles;
+  * on noisy maps with holes / diagonal touches they agree for > 90 % of the boxes (IoU >= 0.8) -- the documented
+    differences: hole contours (RETR_LIST), polygon-mask mean vs component-pixel mean, approxPolyDP corners.
+PARITY PARTIALLY PINNED: Clipper's union step and the many-vertex polygon outputs are not reproduced.
 
 Contract
   1. foreground = prob > float32(thresh)                                   (test.py:57)

@@ -109,3 +109,24 @@ def test_reference_call_signature_and_cv2_agreement():
         # torch CUDA input, batched API
         res = pp.batch(torch.from_numpy(prob).cuda()[None, None])
         assert len(res) == 1 and len(res[0][0]) == len(boxes)
+
+
+def test_gpu_boxes_equal_reference_code_on_rectangular_components():
+    """GPU box rectangles == cv2.boundingRect of the boxes returned by the reference's own DBPostProcessor.__call__
+    (golden: tests/golden/postproc_reference.npz) for maps whose components are axis-aligned rectangles."""
+    g = np.load(GOLD / "postproc_reference.npz")
+    checked = 0
+    for i in range(int(g["n_maps"])):
+        th, bt, ratio, min_area, clean = g[f"params_{i}"]
+        if not clean:
+            continue
+        ref = sorted((int(x), int(y), int(x + w - 1), int(y + h - 1)) for x, y, w, h in g[f"rects_{i}"])
+        _, _, recs, pp = _run(g[f"prob_{i}"], thresh=float(th), box_thresh=float(bt), unclip_ratio=float(ratio),
+                              min_area=int(min_area))
+        boxes, scores = pp.records_to_boxes(recs[0])
+        import cv2
+        ours = sorted((x, y, x + w - 1, y + h - 1) for x, y, w, h in (cv2.boundingRect(b.astype(np.int32)) for b in boxes))
+        assert ours == ref
+        assert np.allclose(sorted(scores), sorted(g[f"scores_{i}"]), rtol=0, atol=2.0 ** -23)
+        checked += 1
+    assert checked >= 2

@@ -130,3 +130,70 @@ def test_boxes_agree_with_cv2_half_of_reference():
         assert all(b.shape == (4, 2) and b.dtype == np.int64 and b.flags.writeable for b in boxes)
         assert all(0.5 <= s <= 1.0 for s in scores)
     assert min(rates) >= 0.9, rates
+
+
+# ----------------------------------------------------------------------------- reference's own post-processor
+def _reference_goldens():
+    g = np.load(GOLD / "postproc_reference.npz")
+    for i in range(int(g["n_maps"])):
+        th, bt, ratio, min_area, clean = g[f"params_{i}"]
+        rects = [(int(x), int(y), int(x + w - 1), int(y + h - 1)) for x, y, w, h in g[f"rects_{i}"]]
+        yield g[f"prob_{i}"], float(th), float(bt), float(ratio), int(min_area), bool(clean), rects, g[f"scores_{i}"]
+
+
+def test_clipper_offset_known_answers():
+    """ClipperOffset restatement (oracle/clipper_offset.py) on cases with closed-form answers."""
+    from oracle.clipper_offset import ET_CLOSEDPOLYGON, JT_ROUND, Polygon, PyclipperOffset
+    rect = [[10, 20], [110, 20], [110, 50], [10, 50]]
+    poly = Polygon(rect)
+    assert poly.area == 3000.0 and poly.length == 260.0
+    for order in (rect, rect[::-1]):                      # either orientation grows outward (FixOrientations)
+        off = PyclipperOffset()
+        off.AddPath(order, JT_ROUND, ET_CLOSEDPOLYGON)
+        (path,) = off.Execute(7.3)
+        p = np.array(path)
+        assert (p[:, 0].min(), p[:, 1].min(), p[:, 0].max(), p[:, 1].max()) == (3, 13, 117, 57)  # Round(10 - 7.3) = 3 ...
+        # every offset vertex is within delta (+ rounding) of the rectangle and at least delta - arc tolerance away
+        dx = np.maximum(np.maximum(10 - p[:, 0], p[:, 0] - 110), 0)
+        dy = np.maximum(np.maximum(20 - p[:, 1], p[:, 1] - 50), 0)
+        dist = np.hypot(dx, dy)
+        assert dist.max() <= 7.3 + 0.71 and dist.min() >= 7.3 - 0.25 - 0.71
+    off = PyclipperOffset()
+    off.AddPath(rect + [rect[0]], JT_ROUND, ET_CLOSEDPOLYGON)  # duplicated closing vertex is stripped
+    assert len(off.Execute(7.3)[0]) == len(path)
+    # a concave (L-shaped) polygon: the reflex vertex emits the 3-point notch Clipper's union later removes
+    ell = [[0, 0], [40, 0], [40, 20], [20, 20], [20, 40], [0, 40]]
+    off = PyclipperOffset()
+    off.AddPath(ell, JT_ROUND, ET_CLOSEDPOLYGON)
+    q = np.array(off.Execute(5.0)[0])
+    assert [20, 20] in q.tolist() and (q[:, 0].min(), q[:, 1].min(), q[:, 0].max(), q[:, 1].max()) == (-5, -5, 45, 45)
+
+
+def test_cv2_restatement_equals_reference_code():
+    """oracle.postproc_oracle.cv2_reference_path == bounding rectangles of the boxes the reference's own
+    DBPostProcessor.__call__ returned (tests/golden/make_postproc_reference.py), in the reference's order."""
+    for prob, th, bt, ratio, min_area, _clean, rects, scores in _reference_goldens():
+        got, got_scores = ppo.cv2_reference_path(prob, th, bt, 1000, ratio, min_area)
+        assert got == rects
+        assert np.allclose(got_scores, scores, rtol=0, atol=1e-12)
+
+
+def test_contract_boxes_equal_reference_boxes_on_rectangular_components():
+    """For axis-aligned rectangular components the contract (component box + closed-form un-clip) and the reference
+    (contour -> approxPolyDP -> Clipper round offset -> cv2.boundingRect in the consumer) give identical rectangles
+    and scores; on noisy / nested / diagonally-touching components they agree for > 90 % at IoU 0.8."""
+    n_clean = 0
+    for prob, th, bt, ratio, min_area, clean, rects, scores in _reference_goldens():
+        _, _, recs = ppo.postprocess(prob, th, bt, 1000, ratio, min_area)
+        ours = [(int(r["x0"]), int(r["y0"]), int(r["x1"]), int(r["y1"])) for r in recs]
+        _, our_scores = ppo.records_to_boxes(recs)
+        if clean:
+            n_clean += 1
+            assert sorted(ours) == sorted(rects)
+            assert np.allclose(sorted(our_scores), sorted(scores), rtol=0, atol=2.0 ** -23)
+            # the reference lists contours bottom-up (reverse raster order); ours is raster order of the first pixel
+            assert ours == [r for r in sorted(rects, key=lambda r: (min(r[1], r[3]), r[0]))] or sorted(ours) == sorted(rects)
+        else:
+            assert ppo.match_rate(ours, rects, 0.8) >= 0.9
+            assert sum(1 for r in rects if r in ours) >= 0.85 * len(rects)
+    assert n_clean >= 2
