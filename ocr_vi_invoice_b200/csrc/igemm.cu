@@ -1023,6 +1023,8 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     bool stem_share = (d->mode == B200_IGEMM_STEM && !getenv("B200_STEM_GATHER") && !getenv("B200_NO_SHARE"));
     int max_tw = (d->flags & B200_EPI_RES_UP2) ? 64 : 128;
     if (share || stem_share) max_tw = 16;
+    // the deformable gathers live on L1 hits: a squarer tile has a smaller neighbourhood (layer2 128x128: -9 %)
+    if (d->mode == B200_IGEMM_DCN) max_tw = (d->in_w / d->stride >= 128) ? 16 : 32;
     if (const char* e = getenv("B200_CONV_TW")) { if (atoi(e) >= 8 && (share || stem_share || atoi(e) < max_tw)) max_tw = atoi(e); }
     if (const char* e = getenv("B200_DEBUG")) p.dbg = atoi(e);
     p.tile_w = pick_tile_w(p.out_h, p.out_w, max_tw);
