@@ -73,6 +73,8 @@ struct IgemmParams {
     int a_bytes;   // bytes of one A stage
     int a_shift;   // share mode: bytes between the A tiles of consecutive ky inside the box (tile_w * 128)
     int b_kb;      // k-blocks of weights per B stage
+    int ss_half;   // floats between the scale and the shift copy in shared memory (256, or 512 for block_n = 512)
+    int nacc;      // TMEM accumulators: 2 (tile i+1's MMAs overlap tile i's epilogue) or 1 (block_n = 512 fills TMEM)
 };
 
 struct TmapPack {
@@ -110,7 +112,7 @@ __device__ __forceinline__ SmemLayout carve(uint8_t* raw, const IgemmParams& p) 
     s.epi = s.b + (p.b_resident ? p.k_blocks : (p.a_kb > 1 ? p.b_stages * 3 : p.a_stages)) * p.block_n * 128;
     uint8_t* rest = s.epi + p.epi_bufs * kABytes;
     s.ss = reinterpret_cast<float*>(rest);
-    uint8_t* bars = rest + (p.ss_shared ? 1 : G) * 2048;
+    uint8_t* bars = rest + (p.ss_shared ? 1 : G) * 8 * p.ss_half;
     s.a_full = reinterpret_cast<uint64_t*>(bars);
     s.a_empty = s.a_full + kMaxStages;
     s.b_full = s.a_empty + kMaxStages;
@@ -309,7 +311,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
     const int b_bytes = p.block_n * 128;
     const SmemLayout sm = carve<kGather>(smem_raw, p);
     const int stages = p.a_stages;  // A ring depth (the gather producers fill it too)
-    const uint32_t tmem_cols = (2 * p.block_n < 32) ? 32u : static_cast<uint32_t>(2 * p.block_n);
+    const uint32_t tmem_cols = (p.nacc * p.block_n < 32) ? 32u : static_cast<uint32_t>(p.nacc * p.block_n);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm.b);
@@ -355,7 +357,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
     if (p.epi_tma && p.ss_shared) {  // single n-block: stage its scale / shift once for every epilogue group
         for (int i = threadIdx.x; i < p.block_n; i += blockDim.x) {
             sm.ss[i] = __ldg(p.scale + i);
-            sm.ss[256 + i] = __ldg(p.shift + i);
+            sm.ss[p.ss_half + i] = __ldg(p.shift + i);
         }
     }
     tc_fence_before();
@@ -440,8 +442,12 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                         mbar_arrive_expect_tx(&sm.a_full[s], tx_bytes);
                         if (!kGather && !(p.dbg & 2))
                             tma_load_4d(sm.a + s * kABytes, &tm.a[view], &sm.a_full[s], c0, ax, ay, t.n);
-                        if (!p.b_resident)
+                        if (!p.b_resident) {
                             tma_load_2d(sm.b + s * b_bytes, &tm.b, &sm.a_full[s], kb * kBlockK, t.nb * p.block_n);
+                            if (kGather && p.block_n > 256)  // a weight box holds at most 256 rows
+                                tma_load_2d(sm.b + s * b_bytes + 256 * 128, &tm.b, &sm.a_full[s], kb * kBlockK,
+                                            t.nb * p.block_n + 256);
+                        }
                     }
                     __syncwarp();
                     if (++s == stages) { s = 0; ph ^= 1; }
@@ -511,9 +517,14 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                 __syncwarp();
             }
         } else {
+            // N = 512 (gather variant only): two N = 256 instructions per K step, one accumulator
+            const bool wide = kGather && p.block_n > 256;
+            const int nacc = kGather ? p.nacc : 2;
+            const uint32_t idesc_l = wide ? umma_idesc_bf16(256u) : idesc;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-                const int acc = it & 1;
-                B200_TIMED_WAIT(2, mbar_wait(&sm.tempty[acc], ((it >> 1) & 1) ^ 1));
+                const int acc = (nacc == 2) ? (it & 1) : 0;
+                const uint32_t tph = (nacc == 2) ? ((it >> 1) & 1) : (it & 1);
+                B200_TIMED_WAIT(2, mbar_wait(&sm.tempty[acc], tph ^ 1));
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.block_n);
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
@@ -526,7 +537,8 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
 #pragma unroll
                             for (int k = 0; k < kBlockK / 16; ++k) {
                                 // +32 bytes per UMMA_K step inside the 128B swizzle atom (encoded >> 4)
-                                umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                                umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc_l, (kb | k) ? 1u : 0u);
+                                if (wide) umma_bf16(d_tmem + 256, da + 2 * k, db + (256 * 128 >> 4) + 2 * k, idesc_l, (kb | k) ? 1u : 0u);
                             }
                         }
                         umma_commit(&sm.a_empty[s]);
@@ -627,7 +639,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
         const int tx = row - ty * p.tile_w;
         const uint32_t swz = static_cast<uint32_t>(row & 7);
         const int GA = p.epi_active, B = p.epi_bufs;
-        float* const ss = sm.ss + (p.ss_shared ? 0 : eg * 512);
+        float* const ss = sm.ss + (p.ss_shared ? 0 : eg * 2 * p.ss_half);
         // residual row this thread reads: its own pixel, or (y>>1, x>>1) of the half-resolution RES_UP2 box
         const bool up2 = (p.flags & B200_EPI_RES_UP2) != 0;
         const int rrow = up2 ? ((ty >> 1) * (p.tile_w >> 1) + (tx >> 1)) : row;
@@ -640,8 +652,8 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
         int ss_nb = p.ss_shared ? 0 : -1;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const TileCoord t = decode_tile(p, tile);
-            const int as = it & 1;
-            const uint32_t aph = (it >> 1) & 1;
+            const int as = (!kGather || p.nacc == 2) ? (it & 1) : 0;
+            const uint32_t aph = (!kGather || p.nacc == 2) ? ((it >> 1) & 1) : (it & 1);
             const int oy = t.y0 + ty, ox = t.x0 + tx;
             const bool valid = (oy < p.out_h) && (ox < p.out_w);
             B200_TIMED_WAIT(7, mbar_wait(&sm.tfull[as], aph));
@@ -663,7 +675,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                     named_bar_sync(1 + eg, kEpiThreads);  // nobody still reads the old copy
                     for (int i = et; i < p.block_n; i += kEpiThreads) {
                         ss[i] = __ldg(p.scale + t.nb * p.block_n + i);
-                        ss[256 + i] = __ldg(p.shift + t.nb * p.block_n + i);
+                        ss[p.ss_half + i] = __ldg(p.shift + t.nb * p.block_n + i);
                     }
                     named_bar_sync(1 + eg, kEpiThreads);
                     ss_nb = t.nb;
@@ -695,8 +707,8 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                             float f[8];
                             const float4 sc0 = *reinterpret_cast<const float4*>(ss + c * 64 + piece * 8);
                             const float4 sc1 = *reinterpret_cast<const float4*>(ss + c * 64 + piece * 8 + 4);
-                            const float4 sh0 = *reinterpret_cast<const float4*>(ss + 256 + c * 64 + piece * 8);
-                            const float4 sh1 = *reinterpret_cast<const float4*>(ss + 256 + c * 64 + piece * 8 + 4);
+                            const float4 sh0 = *reinterpret_cast<const float4*>(ss + p.ss_half + c * 64 + piece * 8);
+                            const float4 sh1 = *reinterpret_cast<const float4*>(ss + p.ss_half + c * 64 + piece * 8 + 4);
                             f[0] = fmaf(__uint_as_float(v[j * 8 + 0]), sc0.x, sh0.x);
                             f[1] = fmaf(__uint_as_float(v[j * 8 + 1]), sc0.y, sh0.y);
                             f[2] = fmaf(__uint_as_float(v[j * 8 + 2]), sc0.z, sh0.z);
@@ -981,8 +993,11 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
         while (block_n > 32 && block_n / 2 >= d->n_pad) block_n >>= 1;
         if (d->n_pad % block_n) block_n = 32;
     }
-    if (block_n != 32 && block_n != 64 && block_n != 128 && block_n != 256)
-        return set_error("igemm: block_n must be 32, 64, 128 or 256");
+    // DCN with 512 output channels: one 128 x 512 tile fills TMEM (single accumulator) but every pixel is gathered
+    // once instead of once per 256-column block -- the gather, not the MMA, is what this kernel is short of
+    if (d->block_n == 0 && d->mode == B200_IGEMM_DCN && d->n_pad == 512 && !getenv("B200_DCN_N256")) block_n = 512;
+    if (block_n != 32 && block_n != 64 && block_n != 128 && block_n != 256 && !(block_n == 512 && d->mode == B200_IGEMM_DCN))
+        return set_error("igemm: block_n must be 32, 64, 128 or 256 (512 for DCN)");
     if (d->n_pad <= 0 || (d->n_pad % block_n) != 0) return set_error("igemm: n_pad must be a multiple of block_n");
     if (d->out_c > d->n_pad) return set_error("igemm: out_c > n_pad");
     if ((d->flags & B200_EPI_SHUFFLE2) && (d->shuf_c <= 0 || d->shuf_c % 32 != 0 || d->out_c != 4 * d->shuf_c))
@@ -1011,6 +1026,8 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     p.stride = d->stride;
     p.flags = d->flags;
     p.block_n = block_n;
+    p.ss_half = block_n > 256 ? 512 : 256;
+    p.nacc = block_n > 256 ? 1 : 2;
     // 3x3 stride-1 convs share one (tile_h+2)-row activation box between the taps ky = 0..2 of a kernel column
     // ("share mode"): tall tiles (8 rows x 16 pixels) make that 2.4x less L2->SM traffic and a third of the barrier
     // round trips (a hand-shake costs ~380 cycles whatever it carries, a 128 x N x 64 MMA block only 2*N).
@@ -1091,11 +1108,12 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     // TMA traffic, the ring carries activations only.
     p.b_resident = (p.num_n_blocks == 1 && p.k_blocks * b_bytes <= 72 * 1024 && d->mode != B200_IGEMM_DCN) ? 1 : 0;
     p.ss_shared = (p.num_n_blocks == 1) ? 1 : 0;
-    const int fixed = 1024 /*alignment*/ + 1024 /*barriers*/ + (p.ss_shared ? 1 : G) * 2048 /*scale+shift*/ +
+    const int fixed = 1024 /*alignment*/ + 1024 /*barriers*/ + (p.ss_shared ? 1 : G) * 8 * p.ss_half /*scale+shift*/ +
                       (p.b_resident ? p.k_blocks * b_bytes : 0);
     // The DCN gather lives on L1 hits (K ordered chunk-major), so it keeps its carve-out <= 132 KB and leaves the
     // rest of the 256 KB to L1; everything else may use the full 227 KB opt-in.
-    const int cap = (d->mode == B200_IGEMM_DCN) ? 131 * 1024 : kMaxSmem;
+    int cap = (d->mode == B200_IGEMM_DCN) ? (block_n > 256 ? 227 : 131) * 1024 : kMaxSmem;
+    if (const char* e = getenv("B200_DCN_CAP")) { if (d->mode == B200_IGEMM_DCN && atoi(e) >= 100 && atoi(e) <= 227) cap = atoi(e) * 1024; }
     const int a_bytes = p.a_bytes;
     int max_stages = kMaxStages;
     if (const char* e = getenv("B200_STAGES")) { if (atoi(e) >= 2 && atoi(e) < max_stages) max_stages = atoi(e); }
@@ -1185,7 +1203,7 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     {
         const uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)d->n_pad};
         const uint64_t str[1] = {(uint64_t)ktot * 2};
-        const uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)block_n};
+        const uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)(block_n > 256 ? 256 : block_n)};
         err |= encode_map(&op->tm.b, d->w, 2, dims, str, box, "weights");
     }
     if (!err && !op->gather && d->mode != B200_IGEMM_STEM) {
