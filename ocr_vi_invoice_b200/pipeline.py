@@ -81,13 +81,16 @@ class Detector:
         return next(self.detect_stream([host_batch]))
 
     def detect_stream(self, batches: Iterable[torch.Tensor]) -> Iterator[List[Result]]:
-        """Yields per-batch results; the H2D copy of batch i+1 overlaps the kernels of batch i."""
+        """Yields per-batch results.  The H2D copy of batch i+1 overlaps the kernels of batch i, and the host only
+        waits for the box records of batch i after the forward of batch i+1 is queued, so the GPU never idles on the
+        host (stream order: fwd(i), post(i), D2H(i) | fwd(i+1), post(i+1), ...)."""
         it = iter(batches)
         try:
             cur = self._stage(next(it), 0)
         except StopIteration:
             return
         slot = 0
+        pending = None  # post-processing buffers of the previous batch, D2H queued
         with torch.cuda.device(self.device):
             main = torch.cuda.current_stream(self.device)
             while cur is not None:
@@ -102,5 +105,10 @@ class Detector:
                     slot ^= 1
                 except StopIteration:
                     cur = None
-                recs, _ = self.post.fetch(self.post.run_device(out["binary"][:, 0], want_labels=False))
+                if pending is not None:  # the previous batch's records: its kernels ran before this forward
+                    recs, _ = self.post.fetch_wait(pending)
+                    yield [self.post.records_to_boxes(r) for r in recs]
+                pending = self.post.fetch_async(self.post.run_device(out["binary"][:, 0], want_labels=False))
+            if pending is not None:
+                recs, _ = self.post.fetch_wait(pending)
                 yield [self.post.records_to_boxes(r) for r in recs]

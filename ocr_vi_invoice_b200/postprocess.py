@@ -68,18 +68,32 @@ class DBPostProcessor:
         buf["prob_ref"] = prob  # keep alive until the stream has consumed it
         return buf
 
-    def fetch(self, buf) -> Tuple[List[np.ndarray], np.ndarray]:
-        """D2H of the box records only (48 B per kept box).  Returns (records per image, ncomp)."""
+    def fetch_async(self, buf):
+        """Queues the D2H of the box records (48 B per slot) behind the kernels of `run_device` and records an event;
+        the caller may queue more GPU work before `fetch_wait`."""
         b = buf["counts"].numel()
-        mc = int(self.max_candidates)
         hc = buf["host_counts"]
         hc[:b].copy_(buf["counts"], non_blocking=True)
         hc[b:].copy_(buf["ncomp"], non_blocking=True)
         buf["host_boxes"].copy_(buf["boxes"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        buf["fetch_event"] = ev
+        return buf
+
+    def fetch_wait(self, buf) -> Tuple[List[np.ndarray], np.ndarray]:
+        """Waits for `fetch_async` and returns (records per image, ncomp)."""
+        buf["fetch_event"].synchronize()
+        b = buf["counts"].numel()
+        mc = int(self.max_candidates)
+        hc = buf["host_counts"]
         counts = hc[:b].numpy()
         recs_all = buf["host_boxes"].numpy().view(_BOX_DTYPE).reshape(b, mc)
         return [recs_all[i, :counts[i]].copy() for i in range(b)], hc[b:].numpy().copy()
+
+    def fetch(self, buf) -> Tuple[List[np.ndarray], np.ndarray]:
+        """D2H of the box records only (48 B per kept box).  Returns (records per image, ncomp)."""
+        return self.fetch_wait(self.fetch_async(buf))
 
     @staticmethod
     def records_to_boxes(recs) -> Tuple[List[np.ndarray], List[float]]:
