@@ -306,3 +306,55 @@ def test_uint8_input_matches_host_normalisation():
     # same bf16 stem input up to an ulp of the normalisation arithmetic -> logits agree to bf16 noise
     assert rel_rms(a["bin_logits"], b["bin_logits"]) < 2e-2
     assert a["binary"].shape == (2, 1, 96, 128)
+
+
+def test_config1_640_batch1_vs_oracle():
+    """BASELINE configs[0]: one 640x640 image, batch 1, against the fp32 oracle run on the CPU (same weights, same input)."""
+    from oracle import dbnet_oracle as dbo
+    from ocr_vi_invoice_b200.synth import synthetic_batch
+    m, sd = _model(5, offset_px=0.25)
+    x = torch.from_numpy(synthetic_batch(1, 640, 640, seed=2))
+    ref_taps = {}
+    ref_out = dbo.dbnet_forward(sd, x, taps=ref_taps)
+    out, taps = m.forward_with_taps(x.cuda())
+    torch.cuda.synchronize()
+    # stage errors stay at the tight bf16 level; single pixels of the probability maps may flip (random weights give
+    # logits of magnitude ~100 on the high-contrast synthetic invoice), so only their mean error is bounded
+    fails = _check_against(out, taps, ref_out, ref_taps, sd, TOL_TIGHT, prob_mean=0.015, prob_max=1.01)
+    assert not fails, fails
+
+
+def test_config2_full_size_properties():
+    """BASELINE configs[1] (batch 16 at 1024x1024) through size-independent properties: (a) every image of the batch
+    gives bit-identical maps when run alone (tile schedule, CTA assignment and n-block order change; the arithmetic per
+    output must not), (b) graph replay == eager launches, (c) the boxes of every image are the oracle's boxes for that
+    image's map, bit for bit, (d) maps are finite probabilities."""
+    from oracle import postproc_oracle as ppo
+    from ocr_vi_invoice_b200.postprocess import DBPostProcessor
+    from ocr_vi_invoice_b200.synth import synthetic_batch
+    m, _ = _model(9, offset_px=1.0)
+    x = torch.from_numpy(synthetic_batch(16, 1024, 1024, seed=4)).cuda()
+    out = {k: v.clone() for k, v in m(x).items()}
+    torch.cuda.synchronize()
+    for k, v in out.items():
+        assert v.shape == (16, 1, 1024, 1024) and torch.isfinite(v).all()
+    assert 0.0 <= out["binary"].min().item() and out["binary"].max().item() <= 1.0
+    m.use_cuda_graph = True
+    rep = m(x)
+    rep = m(x)
+    torch.cuda.synchronize()
+    for k in out:
+        assert torch.equal(out[k], rep[k]), f"graph replay differs in {k}"
+    m.use_cuda_graph = False
+    for i in (0, 7, 15):
+        alone = m(x[i:i + 1].contiguous())
+        torch.cuda.synchronize()
+        for k in out:
+            assert torch.equal(alone[k][0], out[k][i]), f"image {i} alone differs from its batch-16 result in {k}"
+    post = DBPostProcessor(thresh=0.3, box_thresh=0.5, unclip_ratio=1.6)
+    recs, ncomp = post.fetch(post.run_device(out["binary"][:, 0], want_labels=False))
+    for i in (0, 7, 15):
+        _, n, ref = ppo.postprocess(out["binary"][i, 0].cpu().numpy(), 0.3, 0.5, 1000, 1.6, 10)
+        assert n == int(ncomp[i]) and len(ref) == len(recs[i])
+        for f in ref.dtype.names:
+            assert np.array_equal(recs[i][f], ref[f])
