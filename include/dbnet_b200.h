@@ -118,6 +118,11 @@ int b200_stem_pack(const float* img, void* packed, int batch, int h, int w, void
  * HOST pointers to 3 floats). */
 int b200_stem_pack_u8(const void* img_hwc, void* packed, int batch, int h, int w, const float* mean3,
                       const float* std3, void* stream);
+/* cv2.resize(img, (dst_w, dst_h)) with the default INTER_LINEAR for an 8-bit 3-channel HWC image, bit for bit (OpenCV's
+ * fixed-point path): replaces the host resize of resize_image_for_det (src/pipeline/pipeline2.py:34-40) and resize_image
+ * (src/det/test.py:108-121).  Pitches are bytes per row; dst may be one slot of a batch buffer. */
+int b200_resize_u8_linear(const void* src_hwc, int src_h, int src_w, int src_pitch, void* dst_hwc, int dst_h, int dst_w,
+                          int dst_pitch, void* stream);
 /* MaxPool2d(3, stride 2, pad 1) on NHWC bf16 (torchvision resnet.py:200). */
 int b200_maxpool3x3s2(const void* x, void* y, int batch, int h, int w, int c, void* stream);
 /* ScaleFeatureSelection.forward (model/det/neck.py:57-79): bilinear(align_corners=True) upsample of

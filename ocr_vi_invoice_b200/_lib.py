@@ -51,6 +51,7 @@ SYMBOLS = {
     "b200_igemm_info": (_i, [_p] + [C.POINTER(C.c_int32)] * 7),
     "b200_stem_pack": (_i, [_p, _p, _i, _i, _i, _p]),
     "b200_stem_pack_u8": (_i, [_p, _p, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _p]),
+    "b200_resize_u8_linear": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _p]),
     "b200_maxpool3x3s2": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "b200_asf_fwd": (_i, [_p] * 7 + [_i] * 9 + [_p]),
     "b200_asf_combine": (_i, [_p] * 8 + [_i] + [_p, _p] + [_i] * 9 + [_p]),

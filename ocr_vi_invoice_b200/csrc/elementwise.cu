@@ -341,6 +341,49 @@ __global__ void __launch_bounds__(256, 3) asf_combine_kernel(const AsfParams P) 
     }
 }
 
+// ------------------------------------------------------------------------------------------ image resize
+// cv2.resize(img, (dst_w, dst_h)) for 8-bit images with the default INTER_LINEAR (the reference's resize_image_for_det,
+// src/pipeline/pipeline2.py:34-40, and resize_image, src/det/test.py:108-121), bit for bit: OpenCV's fixed-point path
+// (imgproc/resize.cpp: 11-bit coefficients, horizontal pass in int, vertical pass ((b * (S >> 4)) >> 16), + 2 >> 2).
+// x: fx = float((dx + 0.5) * scale_x - 0.5), sx = floor(fx), fx -= sx, clamped at both borders (fx = 0);
+// y: NOT clamped -- the two source rows are clipped into the image instead, so a border row is blended with itself by
+// two separately truncated products.
+__device__ __forceinline__ void resize_coef(int d, double scale, int src, bool clamp_frac, int& s0, int& s1, int& a0, int& a1) {
+    float f = static_cast<float>((d + 0.5) * scale - 0.5);
+    int s = static_cast<int>(floorf(f));
+    f -= static_cast<float>(s);
+    if (clamp_frac) {
+        if (s < 0) { f = 0.0f; s = 0; }
+        if (s >= src - 1) { f = 0.0f; s = src - 1; }
+    }
+    a0 = __float2int_rn((1.0f - f) * 2048.0f);  // saturate_cast<short>(float) = round half to even
+    a1 = __float2int_rn(f * 2048.0f);
+    s0 = min(max(s, 0), src - 1);
+    s1 = min(max(s + 1, 0), src - 1);
+}
+
+__global__ void resize_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int sh, int sw, int dh, int dw,
+                                 int src_pitch, int dst_pitch, double scale_x, double scale_y) {
+    const int64_t total = static_cast<int64_t>(dh) * dw;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int dx = static_cast<int>(i % dw), dy = static_cast<int>(i / dw);
+        int x0, x1, a0, a1, y0, y1, b0, b1;
+        resize_coef(dx, scale_x, sw, true, x0, x1, a0, a1);
+        resize_coef(dy, scale_y, sh, false, y0, y1, b0, b1);
+        const uint8_t* r0 = src + static_cast<int64_t>(y0) * src_pitch;
+        const uint8_t* r1 = src + static_cast<int64_t>(y1) * src_pitch;
+        uint8_t* o = dst + static_cast<int64_t>(dy) * dst_pitch + dx * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int s0 = r0[x0 * 3 + c] * a0 + r0[x1 * 3 + c] * a1;
+            const int s1 = r1[x0 * 3 + c] * a0 + r1[x1 * 3 + c] * a1;
+            const int v = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2;
+            o[c] = static_cast<uint8_t>(min(max(v, 0), 255));
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ DB head tail
 struct HeadParams {
     const __nv_bfloat16* t_bin;
@@ -484,6 +527,20 @@ extern "C" int b200_stem_pack_u8(const void* img_hwc, void* packed, int batch, i
         reinterpret_cast<const uint8_t*>(img_hwc), reinterpret_cast<uint4*>(packed), batch, h, w, mean3[0], mean3[1], mean3[2],
         1.0f / std3[0], 1.0f / std3[1], 1.0f / std3[2]);
     return check_cuda(cudaGetLastError(), "b200_stem_pack_u8 launch");
+}
+
+extern "C" int b200_resize_u8_linear(const void* src_hwc, int src_h, int src_w, int src_pitch, void* dst_hwc, int dst_h,
+                                     int dst_w, int dst_pitch, void* stream) {
+    if (!src_hwc || !dst_hwc) return set_error("b200_resize_u8_linear: null pointer");
+    if (src_h <= 0 || src_w <= 0 || dst_h <= 0 || dst_w <= 0 || src_pitch < 3 * src_w || dst_pitch < 3 * dst_w)
+        return set_error("b200_resize_u8_linear: bad shape");
+    // cv::resize: inv_scale = dsize / (double)ssize; scale = 1. / inv_scale
+    const double scale_x = 1.0 / (dst_w / static_cast<double>(src_w)), scale_y = 1.0 / (dst_h / static_cast<double>(src_h));
+    const int64_t total = static_cast<int64_t>(dst_h) * dst_w;
+    resize_u8_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const uint8_t*>(src_hwc), reinterpret_cast<uint8_t*>(dst_hwc), src_h, src_w, dst_h, dst_w, src_pitch,
+        dst_pitch, scale_x, scale_y);
+    return check_cuda(cudaGetLastError(), "b200_resize_u8_linear launch");
 }
 
 extern "C" int b200_maxpool3x3s2(const void* x, void* y, int batch, int h, int w, int c, void* stream) {

@@ -16,7 +16,7 @@ from ._lib import (EPI_DCN_COORDS, EPI_OUT_F32, EPI_RELU, EPI_RES, EPI_RES_UP2, 
 
 __all__ = [
     "Igemm", "pack_conv_weight", "pack_stem_weight", "pack_convT_weight", "fold_bn", "pad_vec",
-    "stem_pack", "stem_pack_u8", "maxpool3x3s2", "asf_fwd", "asf_combine", "db_head_fwd", "postproc", "ref_conv2d", "ref_dcn2d",
+    "stem_pack", "stem_pack_u8", "resize_u8_linear", "maxpool3x3s2", "asf_fwd", "asf_combine", "db_head_fwd", "postproc", "ref_conv2d", "ref_dcn2d",
     "EPI_RELU", "EPI_RES", "EPI_RES_UP2", "EPI_OUT_F32", "EPI_SHUFFLE2", "EPI_DCN_COORDS", "dcn_coords", "IGEMM_CONV", "IGEMM_STEM", "IGEMM_DCN",
 ]
 
@@ -156,6 +156,16 @@ def stem_pack_u8(img_hwc: torch.Tensor, packed: torch.Tensor, mean=IMAGENET_MEAN
     s = (C.c_float * 3)(*std)
     _lib.check(_lib.load().b200_stem_pack_u8(_lib.ptr(img_hwc), _lib.ptr(packed), b, h, w, m, s, _lib.current_stream()),
                "stem_pack_u8")
+
+
+def resize_u8_linear(src: torch.Tensor, dst: torch.Tensor) -> None:
+    """cv2.resize(src, (W2, H2)) (INTER_LINEAR, uint8 HWC, 3 channels) on the GPU, bit-exact; dst may be a view of a batch."""
+    assert src.dtype == torch.uint8 and dst.dtype == torch.uint8 and src.dim() == 3 and dst.dim() == 3
+    assert src.shape[2] == 3 and dst.shape[2] == 3 and src.stride(2) == 1 and dst.stride(2) == 1
+    assert src.stride(1) == 3 and dst.stride(1) == 3, "pixels must be packed RGB"
+    _lib.check(_lib.load().b200_resize_u8_linear(_lib.ptr(src), src.shape[0], src.shape[1], src.stride(0), _lib.ptr(dst),
+                                                 dst.shape[0], dst.shape[1], dst.stride(0), _lib.current_stream()),
+               "resize_u8_linear")
 
 
 def maxpool3x3s2(x: torch.Tensor, y: torch.Tensor, batch: int, h: int, w: int, c: int) -> None:

@@ -358,3 +358,37 @@ def test_config2_full_size_properties():
         assert n == int(ncomp[i]) and len(ref) == len(recs[i])
         for f in ref.dtype.names:
             assert np.array_equal(recs[i][f], ref[f])
+
+
+@pytest.mark.parametrize("case", [(50, 70, 224, 96), (333, 517, 640, 992), (480, 640, 1024, 1024), (1000, 700, 640, 448),
+                                  (7, 9, 64, 32), (1400, 1000, 1024, 736)], ids=lambda c: "%dx%d_to_%dx%d" % c)
+def test_gpu_resize_bit_exact(case):
+    """b200_resize_u8_linear == the cv2.resize restatement (pinned to cv2 goldens), bit for bit."""
+    from oracle import preprocess_oracle as pre
+    from ocr_vi_invoice_b200 import ops
+    h, w, dh, dw = case
+    rng = np.random.default_rng(h * 7 + w)
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    dst = torch.empty(dh, dw, 3, dtype=torch.uint8, device="cuda")
+    ops.resize_u8_linear(torch.from_numpy(img).cuda(), dst)
+    torch.cuda.synchronize()
+    assert np.array_equal(dst.cpu().numpy(), pre.resize_u8_linear(img, dw, dh))
+
+
+def test_gpu_preprocess_drop_in():
+    """resize_image_for_det on the GPU + uint8 forward == the reference's host pre-processing fed as fp32."""
+    from oracle import preprocess_oracle as pre
+    from ocr_vi_invoice_b200 import preprocess
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (300, 420, 3), dtype=np.uint8)
+    resized, scales = preprocess.resize_image_for_det(torch.from_numpy(img).cuda(), 256)
+    ref_resized, ref_scales = pre.resize_image_for_det(img, 256)
+    assert scales == ref_scales and np.array_equal(resized.cpu().numpy(), ref_resized)
+    with pytest.raises(RuntimeError):
+        preprocess.resize_image_for_det(torch.from_numpy(img), 256)
+    m, _ = _model(21, offset_px=0.5)
+    out_u8 = {k: v.clone() for k, v in m(resized[None]).items()}
+    out_f32 = m(torch.from_numpy(pre.normalise(ref_resized)).cuda())
+    torch.cuda.synchronize()
+    for k in out_u8:  # same bf16 values after the fused normalisation up to float rounding of (x/255 - mean)/std
+        assert (out_u8[k] - out_f32[k]).abs().mean().item() < 2e-3

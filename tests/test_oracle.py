@@ -197,3 +197,30 @@ def test_contract_boxes_equal_reference_boxes_on_rectangular_components():
             assert ppo.match_rate(ours, rects, 0.8) >= 0.9
             assert sum(1 for r in rects if r in ours) >= 0.85 * len(rects)
     assert n_clean >= 2
+
+
+# ----------------------------------------------------------------------------- pre-processing
+def test_resize_restatement_matches_cv2_golden():
+    from oracle import preprocess_oracle as pre
+    g = np.load(GOLD / "resize_cv2.npz")
+    for i, (h, w, dh, dw) in enumerate(g["cases"]):
+        got = pre.resize_u8_linear(g[f"src_{i}"], int(dw), int(dh))
+        assert np.array_equal(got, g[f"dst_{i}"]), f"case {i}: {h}x{w} -> {dh}x{dw}"
+    try:  # live check against the installed cv2 on more shapes (the golden file is what pins it)
+        import cv2
+    except ImportError:
+        return
+    rng = np.random.default_rng(1)
+    for h, w, dh, dw in [(333, 517, 640, 992), (480, 640, 1024, 1024), (1000, 700, 640, 448), (31, 33, 256, 256)]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        assert np.array_equal(pre.resize_u8_linear(img, dw, dh), cv2.resize(img, (dw, dh)))
+
+
+def test_det_size_matches_reference_formula():
+    from oracle import preprocess_oracle as pre
+    from ocr_vi_invoice_b200 import preprocess
+    for h, w, size in [(1400, 1000, 640), (333, 517, 640), (1000, 1000, 1024), (280, 400, 1280), (997, 1403, 1024)]:
+        assert pre.det_size(h, w, size) == preprocess.det_size(h, w, size)
+        (nh, nw), (sh, sw) = pre.det_size(h, w, size)
+        assert nh % 32 == 0 and nw % 32 == 0 and max(nh, nw) in (size - 16, size, size + 16) or max(nh, nw) % 32 == 0
+        assert sh == nh / h and sw == nw / w
