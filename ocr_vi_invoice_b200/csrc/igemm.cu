@@ -298,7 +298,9 @@ __device__ __forceinline__ void epilogue_direct32(const IgemmParams& p, const ui
 // kVariant: 0 = TMA-fed conv (one A tile + one weight k-block per stage), 1 = gather producers (DCN / stem fallback),
 // 2 = TMA-fed 3x3 stride-1 conv in share mode.  Separate instantiations: the loops of one variant must not cost the
 // others registers or instructions (the MMA warp and the epilogue warps are latency-critical).
-template <int kVariant>
+// kUp2: the epilogue adds a nearest-upsampled half-resolution residual (FPN top-down path); it keeps eight more vector
+// registers alive, so it is its own instantiation and the common epilogue does not pay for it.
+template <int kVariant, bool kUp2 = false>
 __global__ void __launch_bounds__((base_warps(kVariant == 1) + (kVariant == 1 ? kGatherWarps : 0)) * 32, 1)
 igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -558,7 +560,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
         // of prefetch), or it is marked free.
         if (p.epi_tma) {
             const int B = p.epi_bufs, L = (B > 1) ? 1 : 0;
-            const bool up2 = (p.flags & B200_EPI_RES_UP2) != 0;
+            constexpr bool up2 = kUp2;
             int ld_tile = blockIdx.x, ld_chunk = 0;
             auto issue_load = [&](int slot) {
                 if (ld_tile >= p.num_tiles) return;
@@ -641,7 +643,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
         const int GA = p.epi_active, B = p.epi_bufs;
         float* const ss = sm.ss + (p.ss_shared ? 0 : eg * 2 * p.ss_half);
         // residual row this thread reads: its own pixel, or (y>>1, x>>1) of the half-resolution RES_UP2 box
-        const bool up2 = (p.flags & B200_EPI_RES_UP2) != 0;
+        constexpr bool up2 = kUp2;
         const int rrow = up2 ? ((ty >> 1) * (p.tile_w >> 1) + (tx >> 1)) : row;
         const uint32_t rswz = static_cast<uint32_t>(rrow & 7);
         int it = 0;
@@ -687,8 +689,8 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                     const uint32_t mine = buf + static_cast<uint32_t>(row) * 128;
                     const uint32_t rsd = buf + static_cast<uint32_t>(rrow) * 128;
                     B200_TIMED_WAIT(8, if (p.res_tma) mbar_wait(&sm.res_full[slot], par); else mbar_wait(&sm.slot_free[slot], par ^ 1));
-                    uint4 rup[8];
-                    if (up2) {  // the 4 KB half-resolution box is shared by four pixels: read it before anyone overwrites
+                    uint4 rup[kUp2 ? 8 : 1];
+                    if constexpr (up2) {  // the 4 KB half-resolution box is shared by four pixels: read it before anyone overwrites
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
                             rup[i] = lds128(rsd + ((static_cast<uint32_t>(i) ^ rswz) << 4));
@@ -719,7 +721,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                             f[7] = fmaf(__uint_as_float(v[j * 8 + 7]), sc1.w, sh1.w);
                             if (p.res_tma) {
                                 uint4 u;
-                                if (up2) u = rup[piece];
+                                if constexpr (up2) u = rup[piece];
                                 else u = lds128(mine + so);  // residual of this very pixel, in place
                                 f[0] += bf16lo(u.x); f[1] += bf16hi(u.x);
                                 f[2] += bf16lo(u.y); f[3] += bf16hi(u.y);
@@ -1257,6 +1259,8 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
         e = cudaFuncSetAttribute(igemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(igemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(igemm_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) {
         delete op;
         return set_error("igemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -1272,6 +1276,8 @@ extern "C" int b200_igemm_launch(const b200_igemm* op, void* stream) {
         igemm_kernel<1><<<op->grid, op->threads, op->smem_bytes, st>>>(op->tm, op->p);
     else if (op->p.a_kb > 1)
         igemm_kernel<2><<<op->grid, op->threads, op->smem_bytes, st>>>(op->tm, op->p);
+    else if (op->p.flags & B200_EPI_RES_UP2)
+        igemm_kernel<0, true><<<op->grid, op->threads, op->smem_bytes, st>>>(op->tm, op->p);
     else
         igemm_kernel<0><<<op->grid, op->threads, op->smem_bytes, st>>>(op->tm, op->p);
     cudaError_t e = cudaGetLastError();
