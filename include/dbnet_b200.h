@@ -50,6 +50,11 @@ enum {
     B200_EPI_OUT_F32    = 8,  /* store fp32 instead of bf16              (offset/mask conv)      */
     B200_EPI_SHUFFLE2   = 16, /* N = 4*shuf_c, column (dy*2+dx)*shuf_c+co goes to pixel
                                  (2y+dy, 2x+dx), channel co               (ConvTranspose2d 2x2) */
+    B200_EPI_HEAD_DOT   = 64, /* DB head: with SHUFFLE2, shuf_c = 64, out_c = 256.  The 64-channel map of the first
+                               * ConvTranspose2d is not stored; BN + ReLU + bf16 rounding + the LAST
+                               * ConvTranspose2d(64 -> 1, k2 s2) (head.py:15,23) run in the epilogue and y receives
+                               * the fp32 logit map (batch, 4*in_h, 4*in_w).  `offsets` = float[257]: tail weights
+                               * w[c*4 + dy*2+dx], then the bias.                                             */
     B200_EPI_DCN_COORDS = 32  /* offset_mask_conv only (out_c = 32): instead of the raw 27 channels, store
                                  the b200_dcn_coord records of the 9 taps, y = [pixel][9] records, so
                                  the DCN producers do no coordinate arithmetic (dcn.py:44-46 fused)    */
@@ -123,6 +128,11 @@ int b200_stem_pack_u8(const void* img_hwc, void* packed, int batch, int h, int w
  * (src/det/test.py:108-121).  Pitches are bytes per row; dst may be one slot of a batch buffer. */
 int b200_resize_u8_linear(const void* src_hwc, int src_h, int src_w, int src_pitch, void* dst_hwc, int dst_h, int dst_w,
                           int dst_pitch, void* stream);
+/* sigmoid + differentiable-binarisation step (model/det/head.py:28-48) from the two fp32 logit maps (n values each):
+ * binary = sigmoid(bin), thresh = sigmoid(thr), thresh_binary = 1 / (1 + exp(-k (binary - thresh))); NULL outputs are
+ * skipped; bin_logits_out / thresh_logits_out receive copies of the inputs when given. */
+int b200_db_maps(const float* bin_logits, const float* thresh_logits, float k, float* binary, float* thresh,
+                 float* thresh_binary, float* bin_logits_out, float* thresh_logits_out, int64_t n, void* stream);
 /* MaxPool2d(3, stride 2, pad 1) on NHWC bf16 (torchvision resnet.py:200). */
 int b200_maxpool3x3s2(const void* x, void* y, int batch, int h, int w, int c, void* stream);
 /* ScaleFeatureSelection.forward (model/det/neck.py:57-79): bilinear(align_corners=True) upsample of

@@ -13,7 +13,7 @@ from pathlib import Path
 _LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libdbnet_b200.so"
 
 IGEMM_CONV, IGEMM_STEM, IGEMM_DCN = 0, 1, 2
-EPI_RELU, EPI_RES, EPI_RES_UP2, EPI_OUT_F32, EPI_SHUFFLE2, EPI_DCN_COORDS = 1, 2, 4, 8, 16, 32
+EPI_RELU, EPI_RES, EPI_RES_UP2, EPI_OUT_F32, EPI_SHUFFLE2, EPI_DCN_COORDS, EPI_HEAD_DOT = 1, 2, 4, 8, 16, 32, 64
 
 
 class B200Error(RuntimeError):
@@ -51,6 +51,7 @@ SYMBOLS = {
     "b200_igemm_info": (_i, [_p] + [C.POINTER(C.c_int32)] * 7),
     "b200_stem_pack": (_i, [_p, _p, _i, _i, _i, _p]),
     "b200_stem_pack_u8": (_i, [_p, _p, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _p]),
+    "b200_db_maps": (_i, [_p, _p, _f, _p, _p, _p, _p, _p, _i64, _p]),
     "b200_resize_u8_linear": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _p]),
     "b200_maxpool3x3s2": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "b200_asf_fwd": (_i, [_p] * 7 + [_i] * 9 + [_p]),

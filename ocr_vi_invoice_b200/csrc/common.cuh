@@ -202,6 +202,12 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     return v;
 }
 
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {  // explicit ld.shared: a generic float* costs LD.E + R2UR churn
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
 // ---------------------------------------------------------------------------------- small helpers
 __device__ __forceinline__ uint4 ldg128(const void* p) {
     return __ldg(reinterpret_cast<const uint4*>(p));

@@ -496,6 +496,28 @@ __global__ void __launch_bounds__(kHeadPix) db_head_kernel(const HeadParams p) {
     }
 }
 
+// sigmoid + DB step from the logit maps written by the B200_EPI_HEAD_DOT epilogue; same expressions as db_head_kernel.
+__global__ void db_maps_kernel(const float4* __restrict__ bl, const float4* __restrict__ tl, float k, float4* binary,
+                               float4* thresh, float4* thresh_binary, float4* bl_out, float4* tl_out, int64_t n4) {
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const float4 b = __ldg(bl + i), t = __ldg(tl + i);
+        const float bv[4] = {b.x, b.y, b.z, b.w}, tv[4] = {t.x, t.y, t.z, t.w};
+        float bp[4], tp[4], tb[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            bp[j] = 1.0f / (1.0f + expf(-bv[j]));
+            tp[j] = 1.0f / (1.0f + expf(-tv[j]));
+            tb[j] = 1.0f / (1.0f + expf(-k * (bp[j] - tp[j])));
+        }
+        if (binary) binary[i] = make_float4(bp[0], bp[1], bp[2], bp[3]);
+        if (thresh) thresh[i] = make_float4(tp[0], tp[1], tp[2], tp[3]);
+        if (thresh_binary) thresh_binary[i] = make_float4(tb[0], tb[1], tb[2], tb[3]);
+        if (bl_out) bl_out[i] = b;
+        if (tl_out) tl_out[i] = t;
+    }
+}
+
 static int grid_for(int64_t work_items, int threads) {
     int64_t blocks = (work_items + threads - 1) / threads;
     const int64_t cap = 148 * 16;
@@ -541,6 +563,17 @@ extern "C" int b200_resize_u8_linear(const void* src_hwc, int src_h, int src_w, 
         reinterpret_cast<const uint8_t*>(src_hwc), reinterpret_cast<uint8_t*>(dst_hwc), src_h, src_w, dst_h, dst_w, src_pitch,
         dst_pitch, scale_x, scale_y);
     return check_cuda(cudaGetLastError(), "b200_resize_u8_linear launch");
+}
+
+extern "C" int b200_db_maps(const float* bin_logits, const float* thresh_logits, float k, float* binary, float* thresh,
+                            float* thresh_binary, float* bin_logits_out, float* thresh_logits_out, int64_t n, void* stream) {
+    if (!bin_logits || !thresh_logits) return set_error("b200_db_maps: null pointer");
+    if (n <= 0 || (n & 3)) return set_error("b200_db_maps: n must be a positive multiple of 4");
+    db_maps_kernel<<<grid_for(n / 4, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(bin_logits), reinterpret_cast<const float4*>(thresh_logits), k,
+        reinterpret_cast<float4*>(binary), reinterpret_cast<float4*>(thresh), reinterpret_cast<float4*>(thresh_binary),
+        reinterpret_cast<float4*>(bin_logits_out), reinterpret_cast<float4*>(thresh_logits_out), n / 4);
+    return check_cuda(cudaGetLastError(), "b200_db_maps launch");
 }
 
 extern "C" int b200_maxpool3x3s2(const void* x, void* y, int batch, int h, int w, int c, void* stream) {

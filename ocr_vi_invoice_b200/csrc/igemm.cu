@@ -294,18 +294,69 @@ __device__ __forceinline__ void epilogue_direct32(const IgemmParams& p, const ui
     }
 }
 
+// ------------------------------------------------------------------------------------------ head tail epilogue
+// B200_EPI_HEAD_DOT: the tile is ConvTranspose2d(64 -> 64, k2 s2) of one DB-head branch (N = 4 sub-pixels x 64 channels).
+// Instead of storing the 64-channel bf16 map, each thread folds BN + ReLU, rounds to bf16 exactly as the stored map
+// would be, and applies the LAST ConvTranspose2d(64 -> 1, k2 s2) (model/det/head.py:15,23) in registers: four fp32 logits
+// per sub-pixel, i.e. a 4 x 4 patch of the full-resolution logit map per input pixel.  Channel order and fmaf sequence
+// are those of db_head_kernel (elementwise.cu), so the logits are bit-identical to the unfused path.
+// aux = float[257]: w2[c * 4 + (dy2 * 2 + dx2)], then the bias.
+__device__ __forceinline__ void epilogue_head_dot(const IgemmParams& p, uint32_t ss_s, uint32_t taddr, int n, int oy,
+                                                  int ox, bool valid, int sub) {
+    // ss (shared): scale[256] | tail weights w2[64][4] | shift[256]   (staged once per CTA, see the kernel prologue)
+    const uint32_t sc = ss_s + sub * 256, sh = ss_s + 2048 + sub * 256, w2 = ss_s + 1024;
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tmem_ld32(taddr + sub * 64 + half * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            const int c = half * 32 + i;
+            const float4 s4 = lds_f4(sc + c * 4), h4 = lds_f4(sh + c * 4);
+            float t0 = fmaf(__uint_as_float(v[i + 0]), s4.x, h4.x), t1 = fmaf(__uint_as_float(v[i + 1]), s4.y, h4.y);
+            float t2 = fmaf(__uint_as_float(v[i + 2]), s4.z, h4.z), t3 = fmaf(__uint_as_float(v[i + 3]), s4.w, h4.w);
+            if (p.flags & B200_EPI_RELU) {
+                t0 = fmaxf(t0, 0.0f); t1 = fmaxf(t1, 0.0f); t2 = fmaxf(t2, 0.0f); t3 = fmaxf(t3, 0.0f);
+            }
+            const uint32_t p01 = pack_bf16(t0, t1), p23 = pack_bf16(t2, t3);  // the rounding the stored bf16 map had
+            const float r[4] = {bf16lo(p01), bf16hi(p01), bf16lo(p23), bf16hi(p23)};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 w = lds_f4(w2 + (c + j) * 16);
+                acc[0] = fmaf(r[j], w.x, acc[0]);
+                acc[1] = fmaf(r[j], w.y, acc[1]);
+                acc[2] = fmaf(r[j], w.z, acc[2]);
+                acc[3] = fmaf(r[j], w.w, acc[3]);
+            }
+        }
+    }
+    if (valid) {
+        const float bias = __ldg(reinterpret_cast<const float*>(p.offsets) + 256);
+        float* out = reinterpret_cast<float*>(p.y);
+        const int ow = 4 * p.out_w;
+        const int64_t row = (static_cast<int64_t>(n) * (4 * p.out_h) + 4 * oy + 2 * (sub >> 1));
+        float* o = out + row * ow + 4 * ox + 2 * (sub & 1);
+        *reinterpret_cast<float2*>(o) = make_float2(acc[0] + bias, acc[1] + bias);
+        *reinterpret_cast<float2*>(o + ow) = make_float2(acc[2] + bias, acc[3] + bias);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ kernel
 // kVariant: 0 = TMA-fed conv (one A tile + one weight k-block per stage), 1 = gather producers (DCN / stem fallback),
 // 2 = TMA-fed 3x3 stride-1 conv in share mode.  Separate instantiations: the loops of one variant must not cost the
 // others registers or instructions (the MMA warp and the epilogue warps are latency-critical).
-// kUp2: the epilogue adds a nearest-upsampled half-resolution residual (FPN top-down path); it keeps eight more vector
-// registers alive, so it is its own instantiation and the common epilogue does not pay for it.
-template <int kVariant, bool kUp2 = false>
+// kEpi: 0 = common epilogue; 1 = adds a nearest-upsampled half-resolution residual (FPN top-down path, keeps eight more
+// vector registers alive); 2 = DB-head tail folded in (B200_EPI_HEAD_DOT).  Own instantiations: the common epilogue must
+// not pay registers (spills) for the rare ones.
+template <int kVariant, int kEpi = 0>
 __global__ void __launch_bounds__((base_warps(kVariant == 1) + (kVariant == 1 ? kGatherWarps : 0)) * 32, 1)
 igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     constexpr bool kGather = (kVariant == 1);
     constexpr bool kShare = (kVariant == 2);
+    constexpr bool kUp2 = (kEpi == 1);
     constexpr int kBaseWarps = base_warps(kGather);
     constexpr int G = epi_groups(kGather);
     const int warp = threadIdx.x >> 5;
@@ -355,6 +406,13 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
         __syncwarp();
         tmem_alloc(sm.tmem_slot, tmem_cols);
         tmem_relinquish();
+    }
+    if constexpr (kEpi == 2) {  // head tail: scale | w2 | shift (ss_half = 512)
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+            sm.ss[i] = __ldg(p.scale + i);
+            sm.ss[256 + i] = __ldg(reinterpret_cast<const float*>(p.offsets) + i);
+            sm.ss[512 + i] = __ldg(p.shift + i);
+        }
     }
     if (p.epi_tma && p.ss_shared) {  // single n-block: stage its scale / shift once for every epilogue group
         for (int i = threadIdx.x; i < p.block_n; i += blockDim.x) {
@@ -642,6 +700,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
         const uint32_t swz = static_cast<uint32_t>(row & 7);
         const int GA = p.epi_active, B = p.epi_bufs;
         float* const ss = sm.ss + (p.ss_shared ? 0 : eg * 2 * p.ss_half);
+        const uint32_t ss_s = smem_u32(ss), ss_shift = static_cast<uint32_t>(p.ss_half) * 4;
         // residual row this thread reads: its own pixel, or (y>>1, x>>1) of the half-resolution RES_UP2 box
         constexpr bool up2 = kUp2;
         const int rrow = up2 ? ((ty >> 1) * (p.tile_w >> 1) + (tx >> 1)) : row;
@@ -663,7 +722,12 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                    static_cast<uint32_t>(as * p.block_n);
             if (!p.epi_tma) {
-                if ((it % G) == eg) {  // direct stores: the groups take alternate tiles
+                if constexpr (kEpi == 2) {
+                    // every group takes one of the four sub-pixels of every tile (16 warps hide the load latency)
+                    epilogue_head_dot(p, smem_u32(sm.ss), taddr, t.n, oy, ox, valid, eg);
+                } else if ((it % G) != eg) {
+                    // direct stores: the groups take alternate tiles
+                } else {
                     for (int c = 0; c < p.block_n; c += 32) {
                         uint32_t v[32];
                         tmem_ld32(taddr + c, v);
@@ -707,10 +771,9 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                             const int piece = h * 4 + j;
                             const uint32_t so = (static_cast<uint32_t>(piece) ^ swz) << 4;
                             float f[8];
-                            const float4 sc0 = *reinterpret_cast<const float4*>(ss + c * 64 + piece * 8);
-                            const float4 sc1 = *reinterpret_cast<const float4*>(ss + c * 64 + piece * 8 + 4);
-                            const float4 sh0 = *reinterpret_cast<const float4*>(ss + p.ss_half + c * 64 + piece * 8);
-                            const float4 sh1 = *reinterpret_cast<const float4*>(ss + p.ss_half + c * 64 + piece * 8 + 4);
+                            const uint32_t sca = ss_s + static_cast<uint32_t>(c * 64 + piece * 8) * 4;
+                            const float4 sc0 = lds_f4(sca), sc1 = lds_f4(sca + 16);
+                            const float4 sh0 = lds_f4(sca + ss_shift), sh1 = lds_f4(sca + ss_shift + 16);
                             f[0] = fmaf(__uint_as_float(v[j * 8 + 0]), sc0.x, sh0.x);
                             f[1] = fmaf(__uint_as_float(v[j * 8 + 1]), sc0.y, sh0.y);
                             f[2] = fmaf(__uint_as_float(v[j * 8 + 2]), sc0.z, sh0.z);
@@ -987,6 +1050,10 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     if (d->mode != B200_IGEMM_STEM && (x_ld < d->in_c || (x_ld % 8))) return set_error("igemm: bad x_ld");
     if (d->mode == B200_IGEMM_DCN && !d->offsets) return set_error("igemm: DCN needs offsets");
     if ((d->flags & (B200_EPI_RES | B200_EPI_RES_UP2)) && !d->residual) return set_error("igemm: residual missing");
+    if ((d->flags & B200_EPI_HEAD_DOT) &&
+        (!(d->flags & B200_EPI_SHUFFLE2) || d->shuf_c != 64 || d->out_c != 256 || d->mode != B200_IGEMM_CONV || !d->offsets ||
+         (d->flags & (B200_EPI_RES | B200_EPI_RES_UP2 | B200_EPI_OUT_F32))))
+        return set_error("igemm: HEAD_DOT is for the 64 -> 4x64 transposed conv with the 257-float tail weights in `offsets`");
     if ((d->flags & B200_EPI_DCN_COORDS) && (d->out_c != 32 || d->ksize != 3 || d->mode != B200_IGEMM_CONV))
         return set_error("igemm: DCN_COORDS is for the 3x3 offset conv with out_c == 32");
     int block_n = d->block_n;
@@ -1028,7 +1095,7 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     p.stride = d->stride;
     p.flags = d->flags;
     p.block_n = block_n;
-    p.ss_half = block_n > 256 ? 512 : 256;
+    p.ss_half = (block_n > 256 || (d->flags & B200_EPI_HEAD_DOT)) ? 512 : 256;
     p.nacc = block_n > 256 ? 1 : 2;
     // 3x3 stride-1 convs share one (tile_h+2)-row activation box between the taps ky = 0..2 of a kernel column
     // ("share mode"): tall tiles (8 rows x 16 pixels) make that 2.4x less L2->SM traffic and a third of the barrier
@@ -1091,7 +1158,7 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     const bool fat = p.a_kb > 1;  // an A stage carries several k-blocks (share variant of the kernel)
 
     // bf16 outputs whose channel count is a multiple of 64 go out through swizzled staging + TMA stores
-    p.epi_tma = !(d->flags & (B200_EPI_OUT_F32 | B200_EPI_DCN_COORDS)) && (d->out_c % 64) == 0 &&
+    p.epi_tma = !(d->flags & (B200_EPI_OUT_F32 | B200_EPI_DCN_COORDS | B200_EPI_HEAD_DOT)) && (d->out_c % 64) == 0 &&
                 (!(d->flags & B200_EPI_SHUFFLE2) || (d->shuf_c % 64) == 0);
     p.res_tma = p.epi_tma && (d->flags & (B200_EPI_RES | B200_EPI_RES_UP2)) && !(d->flags & B200_EPI_SHUFFLE2);
     if ((d->flags & (B200_EPI_RES | B200_EPI_RES_UP2)) && !p.res_tma && p.epi_tma) {
@@ -1260,7 +1327,9 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(igemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(igemm_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+        e = cudaFuncSetAttribute(igemm_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(igemm_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) {
         delete op;
         return set_error("igemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -1276,8 +1345,10 @@ extern "C" int b200_igemm_launch(const b200_igemm* op, void* stream) {
         igemm_kernel<1><<<op->grid, op->threads, op->smem_bytes, st>>>(op->tm, op->p);
     else if (op->p.a_kb > 1)
         igemm_kernel<2><<<op->grid, op->threads, op->smem_bytes, st>>>(op->tm, op->p);
+    else if (op->p.flags & B200_EPI_HEAD_DOT)
+        igemm_kernel<0, 2><<<op->grid, op->threads, op->smem_bytes, st>>>(op->tm, op->p);
     else if (op->p.flags & B200_EPI_RES_UP2)
-        igemm_kernel<0, true><<<op->grid, op->threads, op->smem_bytes, st>>>(op->tm, op->p);
+        igemm_kernel<0, 1><<<op->grid, op->threads, op->smem_bytes, st>>>(op->tm, op->p);
     else
         igemm_kernel<0><<<op->grid, op->threads, op->smem_bytes, st>>>(op->tm, op->p);
     cudaError_t e = cudaGetLastError();

@@ -201,24 +201,42 @@ class Plan:
         t01 = bf(b, h4, w4, 128)  # [bin 64 | thr 64] channels per pixel
         igemm("head.0", ops.IGEMM_CONV, fused, "head.0", t01, in_h=h4, in_w=w4, in_c=256, out_c=128, ksize=3, stride=1,
               flags=ops.EPI_RELU)
-        for bi_, br in enumerate(("bin", "thr")):
-            u = bf(b, 2 * h4, 2 * w4, 64)
-            igemm(f"head.{br}.1", ops.IGEMM_CONV, t01[..., 64 * bi_:], f"head.{br}.1", u, in_h=h4, in_w=w4, in_c=64,
-                  out_c=256, ksize=1, stride=1, flags=ops.EPI_RELU | ops.EPI_SHUFFLE2, shuf_c=64, x_ld=128)
-            tails[br] = u
-            if keep_taps:
-                self.taps[f"head.{'bin_conv' if br == 'bin' else 'thresh_conv'}.3"] = (u, 64)
-        self.tails = tails
         self.maps: Optional[Dict[str, torch.Tensor]] = None
         self.want = MAP_NAMES
         self.graph = None
+        if keep_taps:
+            # unfused tail (tests read the 64-channel maps): ConvT -> bf16 map -> db_head kernel
+            for bi_, br in enumerate(("bin", "thr")):
+                u = bf(b, 2 * h4, 2 * w4, 64)
+                igemm(f"head.{br}.1", ops.IGEMM_CONV, t01[..., 64 * bi_:], f"head.{br}.1", u, in_h=h4, in_w=w4, in_c=64,
+                      out_c=256, ksize=1, stride=1, flags=ops.EPI_RELU | ops.EPI_SHUFFLE2, shuf_c=64, x_ld=128)
+                tails[br] = u
+                self.taps[f"head.{'bin_conv' if br == 'bin' else 'thresh_conv'}.3"] = (u, 64)
+            self.tails = tails
 
-        def head_tail():
-            (wb, bb_), (wt, bt) = P["head.bin.4"], P["head.thr.4"]
-            ops.db_head_fwd(tails["bin"], tails["thr"], wb, bb_, wt, bt, W.k, self.maps, b, 2 * h4, 2 * w4)
+            def head_tail():
+                (wb, bb_), (wt, bt) = P["head.bin.4"], P["head.thr.4"]
+                ops.db_head_fwd(tails["bin"], tails["thr"], wb, bb_, wt, bt, W.k, self.maps, b, 2 * h4, 2 * w4)
 
-        self.steps.append(head_tail)
-        self.names.append("db_head")
+            self.steps.append(head_tail)
+            self.names.append("db_head")
+        else:
+            # fused tail: the first transposed conv's epilogue applies BN + ReLU + bf16 rounding + the last transposed
+            # conv (64 -> 1) and writes the fp32 logit map; the 64-channel maps (2 x 537 MB at batch 16) never exist.
+            # Bit-identical to the unfused tail (same channel order and fmaf sequence).
+            self.logits = {}
+            self._tail_w = {}
+            for bi_, br in enumerate(("bin", "thr")):
+                w2, b2 = P[f"head.{br}.4"]
+                aux = torch.cat([w2.reshape(-1).float(), torch.tensor([b2], device=dev, dtype=torch.float32)]).contiguous()
+                self._tail_w[br] = aux
+                lg = torch.empty(b, 1, 4 * h4, 4 * w4, device=dev, dtype=torch.float32)
+                self.logits[br] = lg
+                igemm(f"head.{br}.1", ops.IGEMM_CONV, t01[..., 64 * bi_:], f"head.{br}.1", lg, in_h=h4, in_w=w4, in_c=64,
+                      out_c=256, ksize=1, stride=1, flags=ops.EPI_RELU | ops.EPI_SHUFFLE2 | ops.EPI_HEAD_DOT, shuf_c=64,
+                      x_ld=128, offsets=aux)
+            self.steps.append(lambda: ops.db_maps(self.logits["bin"], self.logits["thr"], W.k, self.maps))
+            self.names.append("db_maps")
         self.n_launches = len(self.steps)
 
     def _alloc_maps(self):

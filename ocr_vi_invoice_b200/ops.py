@@ -11,13 +11,13 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (EPI_DCN_COORDS, EPI_OUT_F32, EPI_RELU, EPI_RES, EPI_RES_UP2, EPI_SHUFFLE2, IGEMM_CONV,
+from ._lib import (EPI_DCN_COORDS, EPI_HEAD_DOT, EPI_OUT_F32, EPI_RELU, EPI_RES, EPI_RES_UP2, EPI_SHUFFLE2, IGEMM_CONV,
                    IGEMM_DCN, IGEMM_STEM)
 
 __all__ = [
     "Igemm", "pack_conv_weight", "pack_stem_weight", "pack_convT_weight", "fold_bn", "pad_vec",
     "stem_pack", "stem_pack_u8", "resize_u8_linear", "maxpool3x3s2", "asf_fwd", "asf_combine", "db_head_fwd", "postproc", "ref_conv2d", "ref_dcn2d",
-    "EPI_RELU", "EPI_RES", "EPI_RES_UP2", "EPI_OUT_F32", "EPI_SHUFFLE2", "EPI_DCN_COORDS", "dcn_coords", "IGEMM_CONV", "IGEMM_STEM", "IGEMM_DCN",
+    "EPI_RELU", "EPI_RES", "EPI_RES_UP2", "EPI_OUT_F32", "EPI_SHUFFLE2", "EPI_DCN_COORDS", "EPI_HEAD_DOT", "db_maps", "dcn_coords", "IGEMM_CONV", "IGEMM_STEM", "IGEMM_DCN",
 ]
 
 
@@ -199,6 +199,14 @@ def db_head_fwd(t_bin, t_thr, w2_bin, b2_bin: float, w2_thr, b2_thr: float, k: f
                                             _lib.ptr(w2_thr), b2_thr, k, g("binary"), g("thresh"), g("thresh_binary"),
                                             g("bin_logits"), g("thresh_logits"), batch, h, w, ld, _lib.current_stream()),
                "db_head_fwd")
+
+
+def db_maps(bin_logits: torch.Tensor, thr_logits: torch.Tensor, k: float, maps: dict) -> None:
+    """sigmoid + DB step from the two fp32 logit maps into the requested maps (dict name -> tensor, missing = skipped)."""
+    g = lambda n: _lib.ptr(maps.get(n))
+    _lib.check(_lib.load().b200_db_maps(_lib.ptr(bin_logits), _lib.ptr(thr_logits), float(k), g("binary"), g("thresh"),
+                                        g("thresh_binary"), g("bin_logits"), g("thresh_logits"), bin_logits.numel(),
+                                        _lib.current_stream()), "db_maps")
 
 
 def postproc_workspace_bytes(batch: int, h: int, w: int, max_candidates: int) -> int:

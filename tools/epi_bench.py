@@ -40,6 +40,31 @@ def run(name, b, h, w, ci, co, k, s, flags, res=False, shuf=0, iters=20):
         print("   " + "  ".join(f"{n}={buf[i]}" for i, n in enumerate(names)))
     print(f"{name:28s} {ms:7.3f} ms  {byts / ms / 1e9:7.2f} TB/s  {op.flops / ms / 1e9:8.1f} TF/s  {op.info()}", flush=True)
 
+def run_head_dot(iters=20):
+    dev = "cuda"
+    b, h, w = 16, 256, 256
+    t01 = torch.randn(b, h, w, 128, device=dev).to(torch.bfloat16)
+    wt = (torch.randn(256, 64, device=dev) / 8).to(torch.bfloat16)
+    sc, sh = torch.ones(256, device=dev), torch.zeros(256, device=dev)
+    aux = torch.randn(257, device=dev)
+    y = torch.empty(b, 1, 4 * h, 4 * w, device=dev)
+    op = ops.Igemm(ops.IGEMM_CONV, t01[..., 64:], wt, sc, sh, y, batch=b, in_h=h, in_w=w, in_c=64, out_c=256, ksize=1, stride=1,
+                   flags=ops.EPI_RELU | ops.EPI_SHUFFLE2 | ops.EPI_HEAD_DOT, shuf_c=64, x_ld=128, offsets=aux, name="head-dot")
+    for _ in range(3):
+        op()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        op()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"head-dot convT   {e0.elapsed_time(e1) / iters:7.3f} ms  {op.info()}", flush=True)
+
+
+if __name__ == "__main__" and os.environ.get("EPI_SET") == "head":
+    run_head_dot()
+    sys.exit(0)
 if __name__ == "__main__" and os.environ.get("EPI_SET") == "gemm":
     for n in (64, 128, 256):
         run(f"1x1 K=2048 N={n} 32x32", 16, 32, 32, 2048, n, 1, 1, 0, iters=50)
