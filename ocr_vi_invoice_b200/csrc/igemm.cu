@@ -58,7 +58,7 @@ struct IgemmParams {
     int epi_tma, res_tma;  // epilogue stores through TMA / residual prefetched through TMA
     int epi_active;        // epilogue groups that take chunks (the others only keep the TMEM hand-shake going)
     int epi_bufs;          // 16 KB epilogue buffers (residual lands in them, the result is written in place, TMA stores it)
-    int ss_shared;         // one scale/shift copy for the CTA (single n-block) instead of one per group
+    int ss_shared;         // (always 1) one copy of the layer's whole scale / shift vectors per CTA
     int res_bytes;         // bytes of one residual box (16 KB, or 4 KB for the half-resolution RES_UP2 box)
     int b_resident;        // the whole weight matrix stays in shared memory for the CTA's lifetime (small N x K)
     int dbg;               // development probes (B200_DEBUG): 1 = no MMA issue, 2 = no A loads, 4 = no epilogue math
@@ -73,7 +73,8 @@ struct IgemmParams {
     int a_bytes;   // bytes of one A stage
     int a_shift;   // share mode: bytes between the A tiles of consecutive ky inside the box (tile_w * 128)
     int b_kb;      // k-blocks of weights per B stage
-    int ss_half;   // floats between the scale and the shift copy in shared memory (256, or 512 for block_n = 512)
+    int ss_half;   // floats between the scale and the shift vector in shared memory (n_pad, at least 256)
+    int n_pad;     // GEMM columns of the layer (all n-blocks)
     int nacc;      // TMEM accumulators: 2 (tile i+1's MMAs overlap tile i's epilogue) or 1 (block_n = 512 fills TMEM)
 };
 
@@ -112,7 +113,7 @@ __device__ __forceinline__ SmemLayout carve(uint8_t* raw, const IgemmParams& p) 
     s.epi = s.b + (p.b_resident ? p.k_blocks : (p.a_kb > 1 ? p.b_stages * 3 : p.a_stages)) * p.block_n * 128;
     uint8_t* rest = s.epi + p.epi_bufs * kABytes;
     s.ss = reinterpret_cast<float*>(rest);
-    uint8_t* bars = rest + (p.ss_shared ? 1 : G) * 8 * p.ss_half;
+    uint8_t* bars = rest + 8 * p.ss_half;
     s.a_full = reinterpret_cast<uint64_t*>(bars);
     s.a_empty = s.a_full + kMaxStages;
     s.b_full = s.a_empty + kMaxStages;
@@ -414,8 +415,8 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
             sm.ss[512 + i] = __ldg(p.shift + i);
         }
     }
-    if (p.epi_tma && p.ss_shared) {  // single n-block: stage its scale / shift once for every epilogue group
-        for (int i = threadIdx.x; i < p.block_n; i += blockDim.x) {
+    if (p.epi_tma) {  // the layer's whole scale / shift vectors, staged once (no per-tile reloads, no named barriers)
+        for (int i = threadIdx.x; i < p.n_pad; i += blockDim.x) {
             sm.ss[i] = __ldg(p.scale + i);
             sm.ss[p.ss_half + i] = __ldg(p.shift + i);
         }
@@ -699,8 +700,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
         const int tx = row - ty * p.tile_w;
         const uint32_t swz = static_cast<uint32_t>(row & 7);
         const int GA = p.epi_active, B = p.epi_bufs;
-        float* const ss = sm.ss + (p.ss_shared ? 0 : eg * 2 * p.ss_half);
-        const uint32_t ss_s = smem_u32(ss), ss_shift = static_cast<uint32_t>(p.ss_half) * 4;
+        const uint32_t ss_s0 = smem_u32(sm.ss), ss_shift = static_cast<uint32_t>(p.ss_half) * 4;
         // residual row this thread reads: its own pixel, or (y>>1, x>>1) of the half-resolution RES_UP2 box
         constexpr bool up2 = kUp2;
         const int rrow = up2 ? ((ty >> 1) * (p.tile_w >> 1) + (tx >> 1)) : row;
@@ -710,7 +710,6 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
         int next_mine = eg;  // next chunk index this group takes
         int slot = eg;       // its buffer (g % B) and the parity of that buffer's barriers ((g / B) & 1); GA <= B
         uint32_t par = 0;
-        int ss_nb = p.ss_shared ? 0 : -1;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const TileCoord t = decode_tile(p, tile);
             const int as = (!kGather || p.nacc == 2) ? (it & 1) : 0;
@@ -737,15 +736,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                 }
             } else if (eg < GA) {
                 const int nchunks = chunks_of(p, t.nb);
-                if (ss_nb != t.nb) {  // (re)load this n-block's scale / shift into the group's smem copy
-                    named_bar_sync(1 + eg, kEpiThreads);  // nobody still reads the old copy
-                    for (int i = et; i < p.block_n; i += kEpiThreads) {
-                        ss[i] = __ldg(p.scale + t.nb * p.block_n + i);
-                        ss[p.ss_half + i] = __ldg(p.shift + t.nb * p.block_n + i);
-                    }
-                    named_bar_sync(1 + eg, kEpiThreads);
-                    ss_nb = t.nb;
-                }
+                const uint32_t ss_s = ss_s0 + static_cast<uint32_t>(t.nb * p.block_n) * 4;
                 for (int c = 0; c < nchunks; ++c, ++g) {
                     if (g != next_mine) continue;
                     next_mine += GA;
@@ -1095,7 +1086,8 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     p.stride = d->stride;
     p.flags = d->flags;
     p.block_n = block_n;
-    p.ss_half = (block_n > 256 || (d->flags & B200_EPI_HEAD_DOT)) ? 512 : 256;
+    p.n_pad = d->n_pad;
+    p.ss_half = (d->flags & B200_EPI_HEAD_DOT) ? 512 : (d->n_pad > 256 ? d->n_pad : 256);
     p.nacc = block_n > 256 ? 1 : 2;
     // 3x3 stride-1 convs share one (tile_h+2)-row activation box between the taps ky = 0..2 of a kernel column
     // ("share mode"): tall tiles (8 rows x 16 pixels) make that 2.4x less L2->SM traffic and a third of the barrier
@@ -1176,8 +1168,8 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     // Small weight matrices (stem, layer1, ConvT, ...) live in shared memory for the whole launch: no per-tile weight
     // TMA traffic, the ring carries activations only.
     p.b_resident = (p.num_n_blocks == 1 && p.k_blocks * b_bytes <= 72 * 1024 && d->mode != B200_IGEMM_DCN) ? 1 : 0;
-    p.ss_shared = (p.num_n_blocks == 1) ? 1 : 0;
-    const int fixed = 1024 /*alignment*/ + 1024 /*barriers*/ + (p.ss_shared ? 1 : G) * 8 * p.ss_half /*scale+shift*/ +
+    p.ss_shared = 1;
+    const int fixed = 1024 /*alignment*/ + 1024 /*barriers*/ + 8 * p.ss_half /*scale+shift*/ +
                       (p.b_resident ? p.k_blocks * b_bytes : 0);
     // The DCN gather lives on L1 hits (K ordered chunk-major), so it keeps its carve-out <= 132 KB and leaves the
     // rest of the 256 KB to L1; everything else may use the full 227 KB opt-in.
