@@ -552,6 +552,9 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                     tc_fence_after();
                     const uint64_t da = umma_desc_sw128(a0 + s * p.a_bytes);
                     const uint64_t db = umma_desc_sw128(b0 + (b_ring ? bs * 3 : wbase) * b_bytes);
+#ifdef B200_PROF
+                    const long long ti0 = clock64();
+#endif
                     if (elect_one()) {
                         if (!(p.dbg & 1)) {
 #pragma unroll
@@ -570,6 +573,9 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                         if (b_ring) umma_commit(&sm.b_empty[bs]);
                     }
                     __syncwarp();
+#ifdef B200_PROF
+                    if ((p.dbg & 16) && blockIdx.x == 0 && lane == 0) g_prof[10] += clock64() - ti0;
+#endif
                     if (++s == stages) { s = 0; ph ^= 1; }
                     if (b_ring && ++bs == bst) { bs = 0; bph ^= 1; }
                     if (++kx == 3) { kx = 0; wbase += 7; } else { ++wbase; }

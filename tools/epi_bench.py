@@ -36,7 +36,7 @@ def run(name, b, h, w, ci, co, k, s, flags, res=False, shuf=0, iters=20):
         _lib.load().b200_igemm_debug_counters(buf)   # clear
         op(); torch.cuda.synchronize()
         _lib.load().b200_igemm_debug_counters(buf)
-        names = ["A.empty", "B.empty", "mma.tempty", "mma.a_full", "mma.b_full", "dma.out_ready", "dma.wait_read", "epi.tfull", "epi.slot", "total"]
+        names = ["A.empty", "B.empty", "mma.tempty", "mma.a_full", "mma.b_full", "dma.out_ready", "dma.wait_read", "epi.tfull", "epi.slot", "total", "mma.issue"]
         print("   " + "  ".join(f"{n}={buf[i]}" for i, n in enumerate(names)))
     print(f"{name:28s} {ms:7.3f} ms  {byts / ms / 1e9:7.2f} TB/s  {op.flops / ms / 1e9:8.1f} TF/s  {op.info()}", flush=True)
 
