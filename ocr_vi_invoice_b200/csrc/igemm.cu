@@ -1,24 +1,30 @@
 // Implicit-GEMM convolution family for sm_100a: tcgen05.mma with TMEM accumulators, TMA-fed operands,
 // warp-specialised persistent CTAs.  One kernel template covers
-//   * plain 1x1 / 3x3 convolutions, stride 1 or 2 (A operand = NHWC activations loaded by TMA boxes,
-//     one box per (tap, 64-channel slice); zero padding comes from TMA out-of-bounds fill),
+//   * plain 1x1 / 3x3 convolutions, stride 1 or 2 (A operand = NHWC activations loaded by TMA boxes; zero padding comes
+//     from TMA out-of-bounds fill; stride 2 reads four (row, column)-parity strided views),
+//   * "share mode" for narrow (N <= 128) 3x3 stride-1 convolutions and the 7x7 s2 stem: one box of tile_h+2 (stem:
+//     tile_h+3) rows feeds the three (four) taps of a kernel column at 1024-byte-aligned row offsets, so the MMA warp pays
+//     one barrier round trip per 12-16 MMAs and L2->SM traffic drops 2.4x,
 //   * the modulated deformable conv v2 (A operand gathered by 16 producer warps from pre-computed 16-byte
 //     b200_dcn_coord records: 2x2-block bilinear blend with mask-modulated bf16 weights in packed bf16x2 FMAs,
 //     written straight into the 128B-swizzled UMMA layout; loads software-pipelined one unit ahead, K ordered
-//     (channel chunk, tap) so the gathers hit in L1),
-//   * the 7x7 s2 stem on a space-to-depth buffer (A rows are contiguous 128 B runs, copied by the
-//     producer warps),
+//     (channel chunk, tap) so the gathers hit in L1; 512-channel layers run one 128 x 512 tile per pixel block),
 // all with a fused epilogue (folded BN scale/shift or bias, residual add, ReLU) that either
 //   * stages bf16 64-channel chunks in swizzled shared memory and writes them with TMA stores
 //     (pixel-shuffle for ConvTranspose2d 2x2 = four parity views of the output), the residual being
-//     prefetched by TMA loads two chunks ahead, or
-//   * stores directly from registers (fp32 outputs, DCN coordinate records, nearest-upsampled residual).
+//     prefetched by TMA loads into the very buffer the result overwrites, or
+//   * stores directly from registers (fp32 outputs, DCN coordinate records), or
+//   * folds the DB head's last transposed conv in (B200_EPI_HEAD_DOT) and writes fp32 logits.
 //
 // GEMM view:  D[M = output pixels of one 128-pixel tile][N = out channels] =
 //             A[M][K = taps * Cin] * B[N][K]^T,   K ordered (64-channel chunk, tap),  BLOCK_K = 64 (one SW128 atom).
-// (Measured and dropped: sharing one 130-pixel halo row between the three taps of a kernel row -- legal, because TMA
-//  and UMMA both swizzle on absolute shared-memory address bits -- cut L2->SM traffic by a third but did not speed up
-//  any layer: these GEMMs are bound by shared-memory bandwidth (every operand byte is written once and read once).)
+//
+// Things measured on B200 that shaped this file (tools/ring_probe.cu, mma_probe.cu, sts_probe.cu):
+// an mbarrier hand-shake costs ~380 cycles of the waiting thread; tcgen05.mma M=128 K=16 takes 57/63/75/128 cycles at
+// N = 32/64/128/256 (operand reads at ~100 B/clk, not math, below N = 256); uniform-datapath instructions inside an
+// `if (lane == 0)` region get an ELECT/BRA.U.ANY loop each (so warps 0-3 run converged and elect); a few dozen bytes of
+// spills or generic-pointer loads in the epilogue chunk loop cost the HBM-bound layers 10-15 % (so rare epilogues are
+// their own instantiations and shared-memory parameters are read with explicit ld.shared).
 //
 // Reference call sites replaced: see include/dbnet_b200.h.
 #include "common.cuh"
