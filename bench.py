@@ -383,6 +383,18 @@ def main():
                                   "frac": round(top_conv[3] / (top_conv[2] * 1e-3) / 1e12 / pk["tf_sustained"], 4),
                                   "algorithmic_bytes": 2 * b * (H // 4) * (W // 4) * 256 * 2 if top_conv[0] == "smooth0" else None,
                                   "traffic_is_for": "this launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)"}
+        # bandwidth side of the roofline: the conv launches whose arithmetic intensity is below the machine balance
+        # (peak TFLOP/s / peak GB/s) are HBM-bound; achieved = their algorithmic bytes / their time
+        lb = model._get_plan(x_dev).launch_bytes()
+        balance = pk["tf_sustained"] * 1e12 / (pk["hbm_gbs"] * 1e9)
+        hb = [(n, ms, lb[n]) for n, kind, ms, fl in launches if kind in ("conv", "stem") and n in lb and fl / lb[n] < balance]
+        hbm_line = None
+        if hb:
+            hb_ms, hb_bytes = sum(h[1] for h in hb), sum(h[2] for h in hb)
+            hbm_line = {"launches": len(hb), "bound": "hbm", "achieved": round(hb_bytes / (hb_ms * 1e-3) / 1e9, 1),
+                        "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": round(hb_bytes / (hb_ms * 1e-3) / 1e9 / pk["hbm_gbs"], 4),
+                        "share_of_step": round(hb_ms / tot_ms, 4), "algorithmic_bytes_per_step": int(hb_bytes),
+                        "what": "TMA-fed conv launches with FLOP/byte below the machine balance (1x1 convs, stem, ConvT)"}
         shares = {k: round(v["ms"] / tot_ms, 4) for k, v in by_kind.items()}
         if args.dump_launches:
             with open(args.dump_launches, "w") as f:
@@ -409,7 +421,7 @@ def main():
                            "api": "same, fed uint8 HWC images: the reference's host normalisation (pipeline2.py:312-314) runs on the GPU"},
                 "gpu_launches": n_launch * args.steps,
                 "gpu_launches_per_step": n_launch,
-                "roofline": roofline, "dcn": dcn_line, "kernel_time_shares": shares,
+                "roofline": roofline, "dcn": dcn_line, "hbm_bound_convs": hbm_line, "kernel_time_shares": shares,
                 "forward_ms_sum_of_launches": round(tot_ms, 3), "postproc_ms": round(postproc_ms, 3),
                 "postproc_gbs": round(b * H * W * 8 / (postproc_ms * 1e-3) / 1e9, 1), "prob_map_foreground_frac": round(fg_frac, 3),
                 "components_per_image": int(post.fetch(post.run_device(pm, want_labels=False))[1].mean()),

@@ -97,6 +97,7 @@ class Plan:
         self.n_igemm = 0
         self.step_flops: Dict[str, float] = {}
         self.step_kind: Dict[str, str] = {}
+        self.step_bytes: Dict[str, float] = {}  # algorithmic HBM bytes: every operand read once, every output written once
         b = batch
         bf = lambda *s: torch.empty(*s, device=dev, dtype=torch.bfloat16)
         P = W.P
@@ -111,6 +112,12 @@ class Plan:
             self.names.append(name)
             self.step_flops[name] = op.flops
             self.step_kind[name] = {ops.IGEMM_CONV: "conv", ops.IGEMM_STEM: "stem", ops.IGEMM_DCN: "dcn"}[mode]
+            oh, ow = in_h // stride, in_w // stride
+            out_px = b * oh * ow * (4 if flags & ops.EPI_SHUFFLE2 else 1)
+            out_bytes = out_px * 4 * 4 if flags & ops.EPI_HEAD_DOT else y.element_size() * b * oh * ow * out_c
+            in_px = b * in_h * in_w if ksize > 1 or stride == 1 else b * oh * ow  # a strided 1x1 reads only its pixels
+            res_bytes = (2 * b * oh * ow * out_c if flags & ops.EPI_RES else 0) + (2 * b * oh * ow * out_c // 4 if flags & ops.EPI_RES_UP2 else 0)
+            self.step_bytes[name] = float(in_px * in_c * 2 + out_bytes + res_bytes + w.numel() * 2)
             self.flops += op.flops
             self.n_igemm += 1
             return op
@@ -288,6 +295,10 @@ class Plan:
                 acc[i] += ev[i].elapsed_time(ev[i + 1])
         return [(nm, self.step_kind.get(nm, "elementwise"), acc[i] / iters, self.step_flops.get(nm, 0.0))
                 for i, nm in enumerate(self.names)]
+
+    def launch_bytes(self) -> Dict[str, float]:
+        """Algorithmic HBM bytes per igemm launch (for the bandwidth side of the roofline)."""
+        return dict(self.step_bytes)
 
     def tap(self, name: str) -> torch.Tensor:
         """NCHW fp32 copy of a recorded stage tensor (tests only)."""
