@@ -188,6 +188,44 @@ int b200_postproc(const float* prob, int32_t* labels, b200_box* boxes, int32_t* 
                   int batch, int h, int w, double thresh, double box_thresh, double unclip_ratio,
                   int min_area, int max_candidates, void* stream);
 
+/* ---- detection -> recognition hand-over -------------------------------
+ * Replaces, for a whole batch of pages in one launch and without the boxes leaving the device:
+ *   the box rescale loop            src/pipeline/pipeline2.py:323-328 (float64 quotient, truncated toward zero)
+ *   crop_image                      src/det/test.py:123-130           (cv2.boundingRect + clamps + slice)
+ *   preprocess_for_recognition      src/pipeline/pipeline2.py:92-128  (cv2.resize to height th, white pad to tw,
+ *                                                                      /255, mean, std, HWC -> CHW fp32)
+ *   the blank tensor of recognize_text_batch for an empty crop (pipeline2.py:153-157).
+ * Bit-exact against oracle/recprep_oracle.py, which is pinned to the reference's own functions. */
+#define B200_REC_MAX_IMAGES 32
+enum {
+    B200_REC_OK = 0,
+    B200_REC_EMPTY = 1,      /* crop.size == 0: the tensor is all zeros (pipeline2.py:155-157)                 */
+    B200_REC_DEGENERATE = 2  /* int(w * th / h) == 0: cv2.resize raises in the reference; zeros are written
+                                and the host side of this library raises unless told otherwise             */
+};
+typedef struct b200_image {  /* HOST-side descriptor of one original page resident on the device */
+    const void* pixels;      /* device, uint8 HWC RGB, `pitch` bytes per row                      */
+    int32_t h, w, pitch, reserved;
+    double scale_h, scale_w; /* (new_h / h, new_w / w) of resize_image_for_det (pipeline2.py:40): boxes are DIVIDED by them */
+} b200_image;
+typedef struct b200_rec_rect {
+    int32_t image;           /* index into `images`                                               */
+    int32_t x, y, w, h;      /* the slice crop_image takes: page[y:y+h, x:x+w]; w or h <= 0 = empty */
+    int32_t status;          /* B200_REC_*                                                        */
+} b200_rec_rect;
+/* boxes / counts: the device arrays b200_postproc wrote for `n_images` maps ([n_images][max_candidates], [n_images]).
+ * Crop slots are the kept boxes of image 0, then image 1, ... (label order inside an image).
+ * out: device fp32 [capacity][3][th][tw]; rects: device [capacity]; total: device int32[1] = number of boxes
+ * (slots past `capacity` are not written).  Nothing is read back: the caller may queue the recogniser behind it. */
+int b200_rec_prep_boxes(const b200_image* images, int n_images, const b200_box* boxes, const int32_t* counts,
+                        int max_candidates, float* out, b200_rec_rect* rects, int32_t* total, int capacity,
+                        int th, int tw, const float* mean3, const float* std3, void* stream);
+/* the same from explicit rectangles (device array, fields image / x / y / w / h; a rectangle that is not inside its
+ * page is treated as empty): preprocess_for_recognition for crops the caller chose. */
+int b200_rec_prep_rects(const b200_image* images, int n_images, const b200_rec_rect* rects_in, int n, float* out,
+                        b200_rec_rect* rects, int32_t* total, int capacity, int th, int tw,
+                        const float* mean3, const float* std3, void* stream);
+
 /* ---- plain CUDA-core cross-check kernels (slow; used by the GPU tests, never by the engine) -- */
 int b200_ref_conv2d(const void* x, const void* w, const float* scale, const float* shift,
                     const void* residual, void* y, int batch, int in_h, int in_w, int in_c,

@@ -39,6 +39,19 @@ class Box(C.Structure):
     ]
 
 
+class Image(C.Structure):
+    _fields_ = [("pixels", C.c_void_p), ("h", C.c_int32), ("w", C.c_int32), ("pitch", C.c_int32), ("reserved", C.c_int32),
+                ("scale_h", C.c_double), ("scale_w", C.c_double)]
+
+
+class RecRect(C.Structure):
+    _fields_ = [("image", C.c_int32), ("x", C.c_int32), ("y", C.c_int32), ("w", C.c_int32), ("h", C.c_int32),
+                ("status", C.c_int32)]
+
+
+REC_OK, REC_EMPTY, REC_DEGENERATE = 0, 1, 2
+REC_MAX_IMAGES = 32
+
 # every symbol include/dbnet_b200.h declares: name -> (restype, argtypes)
 _i, _p, _f, _d, _i64 = C.c_int, C.c_void_p, C.c_float, C.c_double, C.c_int64
 SYMBOLS = {
@@ -60,6 +73,10 @@ SYMBOLS = {
     "b200_dcn_coords": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "b200_postproc_workspace_bytes": (_i64, [_i, _i, _i, _i]),
     "b200_postproc": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _d, _d, _d, _i, _i, _p]),
+    "b200_rec_prep_boxes": (_i, [C.POINTER(Image), _i, _p, _p, _i, _p, _p, _p, _i, _i, _i, C.POINTER(C.c_float),
+                                 C.POINTER(C.c_float), _p]),
+    "b200_rec_prep_rects": (_i, [C.POINTER(Image), _i, _p, _i, _p, _p, _p, _i, _i, _i, C.POINTER(C.c_float),
+                                 C.POINTER(C.c_float), _p]),
     "b200_ref_conv2d": (_i, [_p] * 6 + [_i] * 12 + [_p]),
     "b200_ref_dcn2d": (_i, [_p] * 6 + [_i] * 8 + [_p]),
 }

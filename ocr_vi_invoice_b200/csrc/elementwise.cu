@@ -1,6 +1,7 @@
 // Bandwidth-bound kernels of the DBNet++ path: stem packing, max-pool, the fused adaptive-scale-fusion
 // (ScaleFeatureSelection) and the DB head tail.  All activations NHWC bf16, 16-byte vector accesses.
 #include "common.cuh"
+#include "imgproc.cuh"
 #include "internal.h"
 
 namespace b200 {
@@ -348,20 +349,6 @@ __global__ void __launch_bounds__(256, 3) asf_combine_kernel(const AsfParams P) 
 // x: fx = float((dx + 0.5) * scale_x - 0.5), sx = floor(fx), fx -= sx, clamped at both borders (fx = 0);
 // y: NOT clamped -- the two source rows are clipped into the image instead, so a border row is blended with itself by
 // two separately truncated products.
-__device__ __forceinline__ void resize_coef(int d, double scale, int src, bool clamp_frac, int& s0, int& s1, int& a0, int& a1) {
-    float f = static_cast<float>((d + 0.5) * scale - 0.5);
-    int s = static_cast<int>(floorf(f));
-    f -= static_cast<float>(s);
-    if (clamp_frac) {
-        if (s < 0) { f = 0.0f; s = 0; }
-        if (s >= src - 1) { f = 0.0f; s = src - 1; }
-    }
-    a0 = __float2int_rn((1.0f - f) * 2048.0f);  // saturate_cast<short>(float) = round half to even
-    a1 = __float2int_rn(f * 2048.0f);
-    s0 = min(max(s, 0), src - 1);
-    s1 = min(max(s + 1, 0), src - 1);
-}
-
 __global__ void resize_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int sh, int sw, int dh, int dw,
                                  int src_pitch, int dst_pitch, double scale_x, double scale_y) {
     const int64_t total = static_cast<int64_t>(dh) * dw;

@@ -16,7 +16,7 @@ from ._lib import (EPI_DCN_COORDS, EPI_HEAD_DOT, EPI_OUT_F32, EPI_RELU, EPI_RES,
 
 __all__ = [
     "Igemm", "pack_conv_weight", "pack_stem_weight", "pack_convT_weight", "fold_bn", "pad_vec",
-    "stem_pack", "stem_pack_u8", "resize_u8_linear", "maxpool3x3s2", "asf_fwd", "asf_combine", "db_head_fwd", "postproc", "ref_conv2d", "ref_dcn2d",
+    "stem_pack", "stem_pack_u8", "resize_u8_linear", "maxpool3x3s2", "asf_fwd", "asf_combine", "db_head_fwd", "postproc", "rec_prep_boxes", "rec_prep_rects", "ref_conv2d", "ref_dcn2d",
     "EPI_RELU", "EPI_RES", "EPI_RES_UP2", "EPI_OUT_F32", "EPI_SHUFFLE2", "EPI_DCN_COORDS", "EPI_HEAD_DOT", "db_maps", "dcn_coords", "IGEMM_CONV", "IGEMM_STEM", "IGEMM_DCN",
 ]
 
@@ -222,6 +222,46 @@ def postproc(prob, labels, boxes, counts, ncomp, workspace, batch, h, w, thresh,
                                          _lib.ptr(ncomp), _lib.ptr(workspace), workspace.numel() * workspace.element_size(),
                                          batch, h, w, float(thresh), float(box_thresh), float(unclip_ratio),
                                          int(min_area), int(max_candidates), _lib.current_stream()), "postproc")
+
+
+def _rec_images(pages, scales):
+    """ctypes array of b200_image for uint8 HWC CUDA pages (row pitch free, pixels packed RGB)."""
+    if not 1 <= len(pages) <= _lib.REC_MAX_IMAGES:
+        raise ValueError(f"1..{_lib.REC_MAX_IMAGES} pages per call")
+    arr = (_lib.Image * len(pages))()
+    for i, (pg, (sh, sw)) in enumerate(zip(pages, scales)):
+        if not (pg.is_cuda and pg.dtype == torch.uint8 and pg.dim() == 3 and pg.shape[2] == 3 and pg.stride(2) == 1
+                and pg.stride(1) == 3):
+            raise RuntimeError("recognition crops: pages must be uint8 HWC CUDA tensors with packed RGB pixels (no CPU fallback)")
+        arr[i].pixels, arr[i].h, arr[i].w, arr[i].pitch = pg.data_ptr(), pg.shape[0], pg.shape[1], pg.stride(0)
+        arr[i].scale_h, arr[i].scale_w = float(sh), float(sw)
+    return arr
+
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+def rec_prep_boxes(pages, scales, boxes, counts, max_candidates: int, out, rects, total, mean=IMAGENET_MEAN,
+                   std=IMAGENET_STD) -> None:
+    """Detector box records (device, as b200_postproc wrote them) -> (capacity, 3, th, tw) fp32 recognition inputs.
+    Replaces pipeline2.py:323-328 + crop_image (test.py:123-130) + preprocess_for_recognition (pipeline2.py:92-128)."""
+    capacity, _, th, tw = out.shape
+    assert out.dtype == torch.float32 and out.is_contiguous() and rects.numel() * rects.element_size() >= capacity * 24
+    _lib.check(_lib.load().b200_rec_prep_boxes(_rec_images(pages, scales), len(pages), _lib.ptr(boxes), _lib.ptr(counts),
+                                               int(max_candidates), _lib.ptr(out), _lib.ptr(rects), _lib.ptr(total),
+                                               capacity, th, tw, _f3(mean), _f3(std), _lib.current_stream()),
+               "rec_prep_boxes")
+
+
+def rec_prep_rects(pages, rects_in, n: int, out, rects, total, mean=IMAGENET_MEAN, std=IMAGENET_STD) -> None:
+    """The same from explicit (image, x, y, w, h, _) int32 rectangles on the device."""
+    capacity, _, th, tw = out.shape
+    assert out.dtype == torch.float32 and out.is_contiguous() and rects.numel() * rects.element_size() >= capacity * 24
+    _lib.check(_lib.load().b200_rec_prep_rects(_rec_images(pages, [(1.0, 1.0)] * len(pages)), len(pages), _lib.ptr(rects_in),
+                                               int(n), _lib.ptr(out), _lib.ptr(rects), _lib.ptr(total), capacity, th, tw,
+                                               _f3(mean), _f3(std), _lib.current_stream()),
+               "rec_prep_rects")
 
 
 def ref_conv2d(x, w, scale, shift, residual, y, batch, in_h, in_w, in_c, out_c, ksize, stride, flags, out_ld,

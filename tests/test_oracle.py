@@ -224,3 +224,51 @@ def test_det_size_matches_reference_formula():
         (nh, nw), (sh, sw) = pre.det_size(h, w, size)
         assert nh % 32 == 0 and nw % 32 == 0 and max(nh, nw) in (size - 16, size, size + 16) or max(nh, nw) % 32 == 0
         assert sh == nh / h and sw == nw / w
+
+
+# ------------------------------------------------------------------ detection -> recognition hand-over
+def _recprep_golden():
+    return np.load(GOLD / "recprep_reference.npz")
+
+
+def test_recprep_restatement_matches_reference_code():
+    """oracle/recprep_oracle.py vs the reference's own crop_image / preprocess_for_recognition / rescale loop
+    (tests/golden/make_recprep_golden.py): rectangles, statuses and every float of the tensors, bit for bit."""
+    from oracle import recprep_oracle as ro
+    g = _recprep_golden()
+    table = g["norm_table"]
+    seen = set()
+    for name in "abc":
+        page, boxes = g[f"{name}_page"], g[f"{name}_boxes"]
+        sh, sw = (float(v) for v in g[f"{name}_scales"])
+        out, rects = ro.crops_for_recognition(page, boxes, sh, sw)
+        assert np.array_equal(rects[:, :4], g[f"{name}_rects"])
+        assert np.array_equal(rects[:, 4], g[f"{name}_status"])
+        idx = g[f"{name}_tensor_index"]
+        want = np.stack([table[c][idx[:, c]] for c in range(3)], axis=1)
+        want[g[f"{name}_status"] != 0] = 0.0
+        assert out.dtype == np.float32 and np.array_equal(out, want)
+        seen |= set(rects[:, 4].tolist())
+    assert seen == {ro.STATUS_OK, ro.STATUS_EMPTY, ro.STATUS_DEGENERATE}
+
+
+def test_recprep_normalisation_table_is_the_reference_arithmetic():
+    from oracle import recprep_oracle as ro
+    g = _recprep_golden()
+    ramp = np.repeat(np.repeat(np.arange(256, dtype=np.uint8)[None, :, None], 3, axis=2), 32, axis=0)
+    t, st = ro.preprocess_for_recognition(ramp)
+    assert st == ro.STATUS_OK and np.array_equal(t[:, 0, :], g["norm_table"])
+
+
+def test_recprep_quirks():
+    from oracle import recprep_oracle as ro
+    # truncation toward zero, not floor, for negative coordinates (pipeline2.py:325-326)
+    rb = ro.rescale_box(np.array([[-9, -9], [10, -9], [10, 10], [-9, 10]]), 0.64, 0.64)
+    assert rb.min() == -14 and rb.dtype == np.int32
+    # a negative corner shifts the crop, it does not shrink it (test.py:126-129)
+    assert ro.crop_rect(100, 100, np.array([[-5, 3], [20, 3], [20, 9], [-5, 9]])) == (0, 3, 26, 7)
+    # right / bottom borders cut
+    assert ro.crop_rect(100, 100, np.array([[90, 95], [120, 95], [120, 130], [90, 130]])) == (90, 95, 10, 5)
+    img = np.zeros((100, 100, 3), np.uint8)
+    assert ro.crop_image(img, np.array([[120, 5], [130, 5], [130, 9], [120, 9]])).size == 0
+    assert ro.rec_width(400, 2) == 0 and ro.rec_width(32, 256) == 256 and ro.rec_width(33, 300) == 290
