@@ -226,6 +226,15 @@ int b200_rec_prep_rects(const b200_image* images, int n_images, const b200_rec_r
                         b200_rec_rect* rects, int32_t* total, int capacity, int th, int tw,
                         const float* mean3, const float* std3, void* stream);
 
+/* ---- greedy CTC decode (tail of the recognition path) --------------------
+ * Replaces SVTRv2.decode_probs, model/rec2/svtrv2.py:550-569: argmax over the class axis of (T, B, C) fp32
+ * log-probabilities (first index of the maximum, NaN = maximum, as torch.argmax), then per sequence the frames whose
+ * class is neither `blank_id` nor the previous frame's class.  Element (t, b, c) is at log_probs[t*stride_t + b*stride_b
+ * + c] (strides in elements).  tokens: device int32 [B][T], the kept classes then -1 padding; lengths: device int32 [B].
+ * The id -> character join of Tokenizer.decode (model/rec2/tokenizer.py:54-79) is host string work. */
+int b200_ctc_greedy(const float* log_probs, int T, int B, int C, int64_t stride_t, int64_t stride_b, int blank_id,
+                    int32_t* tokens, int32_t* lengths, void* stream);
+
 /* ---- plain CUDA-core cross-check kernels (slow; used by the GPU tests, never by the engine) -- */
 int b200_ref_conv2d(const void* x, const void* w, const float* scale, const float* shift,
                     const void* residual, void* y, int batch, int in_h, int in_w, int in_c,

@@ -77,6 +77,7 @@ SYMBOLS = {
                                  C.POINTER(C.c_float), _p]),
     "b200_rec_prep_rects": (_i, [C.POINTER(Image), _i, _p, _i, _p, _p, _p, _i, _i, _i, C.POINTER(C.c_float),
                                  C.POINTER(C.c_float), _p]),
+    "b200_ctc_greedy": (_i, [_p, _i, _i, _i, _i64, _i64, _i, _p, _p, _p]),
     "b200_ref_conv2d": (_i, [_p] * 6 + [_i] * 12 + [_p]),
     "b200_ref_dcn2d": (_i, [_p] * 6 + [_i] * 8 + [_p]),
 }

@@ -16,7 +16,7 @@ from ._lib import (EPI_DCN_COORDS, EPI_HEAD_DOT, EPI_OUT_F32, EPI_RELU, EPI_RES,
 
 __all__ = [
     "Igemm", "pack_conv_weight", "pack_stem_weight", "pack_convT_weight", "fold_bn", "pad_vec",
-    "stem_pack", "stem_pack_u8", "resize_u8_linear", "maxpool3x3s2", "asf_fwd", "asf_combine", "db_head_fwd", "postproc", "rec_prep_boxes", "rec_prep_rects", "ref_conv2d", "ref_dcn2d",
+    "stem_pack", "stem_pack_u8", "resize_u8_linear", "maxpool3x3s2", "asf_fwd", "asf_combine", "db_head_fwd", "postproc", "rec_prep_boxes", "rec_prep_rects", "ctc_greedy", "ref_conv2d", "ref_dcn2d",
     "EPI_RELU", "EPI_RES", "EPI_RES_UP2", "EPI_OUT_F32", "EPI_SHUFFLE2", "EPI_DCN_COORDS", "EPI_HEAD_DOT", "db_maps", "dcn_coords", "IGEMM_CONV", "IGEMM_STEM", "IGEMM_DCN",
 ]
 
@@ -262,6 +262,17 @@ def rec_prep_rects(pages, rects_in, n: int, out, rects, total, mean=IMAGENET_MEA
                                                int(n), _lib.ptr(out), _lib.ptr(rects), _lib.ptr(total), capacity, th, tw,
                                                _f3(mean), _f3(std), _lib.current_stream()),
                "rec_prep_rects")
+
+
+def ctc_greedy(log_probs: torch.Tensor, blank_id: int, tokens: torch.Tensor, lengths: torch.Tensor) -> None:
+    """(T, B, C) fp32 CUDA log-probabilities (class axis contiguous) -> int32 tokens [B][T] (-1 padded), lengths [B].
+    Replaces the argmax + collapse loop of SVTRv2.decode_probs (model/rec2/svtrv2.py:561-571)."""
+    assert log_probs.dtype == torch.float32 and log_probs.dim() == 3 and log_probs.stride(2) == 1
+    T, B, C = log_probs.shape
+    assert tokens.dtype == torch.int32 and tokens.is_contiguous() and tokens.numel() >= B * T and lengths.numel() >= B
+    _lib.check(_lib.load().b200_ctc_greedy(_lib.ptr(log_probs), T, B, C, log_probs.stride(0), log_probs.stride(1),
+                                           int(blank_id), _lib.ptr(tokens), _lib.ptr(lengths), _lib.current_stream()),
+               "ctc_greedy")
 
 
 def ref_conv2d(x, w, scale, shift, residual, y, batch, in_h, in_w, in_c, out_c, ksize, stride, flags, out_ld,

@@ -15,6 +15,8 @@ import torch
 
 from .model.det.dbnet import DBNetPP
 from .postprocess import DBPostProcessor
+from .preprocess import resize_image_for_det
+from .recprep import RecognitionCropper
 
 Result = Tuple[List[np.ndarray], List[float]]
 
@@ -75,6 +77,21 @@ class Detector:
             buf.copy_(host, non_blocking=True)
             ready.record(self._copy_stream)
         return buf, ready
+
+    def detect_and_crop(self, page: torch.Tensor, image_size: int = 640, cropper: RecognitionCropper = None):
+        """Steps 2 and 3a of the reference pipeline for one page (pipeline2.py:307-343), without leaving the device:
+        resize_image_for_det -> normalise + forward -> post-processing -> box rescale -> crop_image ->
+        preprocess_for_recognition.  `page`: the ORIGINAL uint8 HWC CUDA image.  Everything is queued on the current
+        stream and nothing synchronises; returns (crop buffers {"out", "rects", "total"}, detector buffers) -- the
+        recogniser input is crops["out"][:total] (RecognitionCropper.fetch gives it together with the rectangles)."""
+        if cropper is None:
+            cropper = self._cropper = getattr(self, "_cropper", None) or RecognitionCropper(device=self.device)
+        with torch.cuda.device(self.device):
+            resized, scales = resize_image_for_det(page, image_size)
+            out = self.model(resized[None])
+            det = self.post.run_device(out["binary"][:, 0], want_labels=False)
+            crops = cropper.from_detector(det, [page], [scales], int(self.post.max_candidates))
+        return crops, det
 
     def detect(self, host_batch: torch.Tensor) -> List[Result]:
         """One batch: H2D, forward, GPU post-processing, D2H of the box records."""

@@ -182,3 +182,39 @@ def test_detector_to_recogniser_without_host_round_trip():
         at += k
     assert at == len(rects)
     assert det_size(480, 640, 640)[0] == (480, 640)
+
+
+def test_page_to_crops_chain_matches_reference_chain():
+    """Detector.detect_and_crop (GPU resize -> forward -> post-processing -> crops, nothing returns to the host) vs the
+    oracle chain run on the SAME probability map: resize restatement, post-processing oracle, crop oracle."""
+    from oracle import postproc_oracle as ppo
+    from oracle import preprocess_oracle as pre
+    from oracle import recprep_oracle as ro
+    from oracle.weights import make_state_dict
+    from ocr_vi_invoice_b200.model.det.dbnet import DBNetPP
+    from ocr_vi_invoice_b200.pipeline import Detector
+    from ocr_vi_invoice_b200.postprocess import DBPostProcessor
+    from ocr_vi_invoice_b200.recprep import RecognitionCropper
+    from ocr_vi_invoice_b200.synth import synthetic_batch_u8
+    dev = _dev()
+    model = DBNetPP(pretrained=False)
+    model.load_state_dict(make_state_dict(seed=3, offset_px=0.5), strict=True)
+    model = model.to(dev).eval()
+    post = DBPostProcessor(thresh=0.3, box_thresh=0.5, unclip_ratio=1.6, device=dev)
+    det = Detector(model, post, dev, use_cuda_graph=False)
+    page_np = np.ascontiguousarray(synthetic_batch_u8(1, 300, 420, seed=4)[0])
+    page = torch.from_numpy(page_np).to(dev)
+    cr = RecognitionCropper((32, 256), capacity=1024)
+    crops, dbuf = det.detect_and_crop(page, image_size=256, cropper=cr)
+    out, rects = cr.fetch(crops, on_degenerate="zeros")
+    # the reference chain on the host, from the very same probability map
+    resized, (sh, sw) = pre.resize_image_for_det(page_np, 256)
+    prob = model(torch.from_numpy(resized).to(dev)[None])["binary"][0, 0].cpu().numpy()
+    _, _, recs = ppo.postprocess(prob, 0.3, 0.5, 1000, 1.6, 10)
+    boxes = [np.array([[r["x0"], r["y0"]], [r["x1"], r["y0"]], [r["x1"], r["y1"]], [r["x0"], r["y1"]]], dtype=np.int64)
+             for r in recs]
+    want, wr = ro.crops_for_recognition(page_np, boxes, sh, sw)
+    assert len(rects) == len(boxes)
+    assert np.array_equal(np.stack([rects["x"], rects["y"], rects["w"], rects["h"], rects["status"]], axis=1).reshape(-1, 5),
+                          wr.reshape(-1, 5))
+    assert np.array_equal(out.cpu().numpy(), want)

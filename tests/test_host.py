@@ -99,3 +99,29 @@ def test_postprocessor_attributes():
     assert (pp.thresh, pp.box_thresh, pp.max_candidates, pp.unclip_ratio, pp.min_size) == (0.3, 0.5, 1000, 1.6, 3)
     with pytest.raises(RuntimeError):
         pp.run_device(torch.zeros(1, 8, 8))
+
+
+def test_rec2_vocab_and_tokenizer_match_reference():
+    """VOCAB (built from its description) == the charset of the reference's tokenizer; Tokenizer.decode of the golden id
+    lists == the strings the reference's decode_probs returned (tests/golden/ctc_reference.npz)."""
+    from pathlib import Path
+    import numpy as np
+    from ocr_vi_invoice_b200.model.rec2 import VOCAB, Tokenizer
+    g = np.load(Path(__file__).parent / "golden" / "ctc_reference.npz")
+    assert VOCAB == "".join(g["charset"].tolist())
+    tok = Tokenizer(VOCAB)
+    assert tok.num_classes == int(g["num_classes"]) and tok.blank_id == 0 and tok.pad_id == 1
+    for name in "abc":
+        ids = [row[:n].tolist() for row, n in zip(g[f"{name}_ids"], g[f"{name}_lengths"])]
+        assert tok.decode(ids) == g[f"{name}_texts"].tolist()
+    enc = tok.encode(["ab", "đồng ₫", ""])
+    assert enc.shape == (3, 6) and enc[2].tolist() == [1] * 6 and tok.decode(enc) == ["ab", "đồng ₫", ""]
+    assert tok.encode([]).shape == (0,) or tok.encode([]).numel() == 0
+
+
+def test_rec2_decode_refuses_cpu_tensors():
+    import pytest
+    import torch
+    from ocr_vi_invoice_b200.model.rec2 import VOCAB, Tokenizer, decode_probs
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        decode_probs(torch.zeros(4, 2, 232), Tokenizer(VOCAB))

@@ -37,12 +37,14 @@ def test_model_oracle_matches_reference_golden():
     for k, v in out.items():
         ref = torch.from_numpy(g["out." + k])
         assert v.shape == ref.shape
-        torch.testing.assert_close(v, ref, rtol=1e-5, atol=1e-5)
+        # fp32 CPU convolutions are not run-to-run identical (thread partitioning changes the summation order) and
+        # thresh_binary amplifies logit differences by k = 50: 1e-4, observed 1e-6 .. 1e-5
+        torch.testing.assert_close(v, ref, rtol=1e-4, atol=1e-4)
     tap_keys = [k[4:] for k in g.files if k.startswith("tap.")]
     assert len(tap_keys) == 24
     for k in tap_keys:
         ref = torch.from_numpy(g["tap." + k])
-        torch.testing.assert_close(taps[k], ref, rtol=1e-5, atol=1e-5 * float(ref.abs().max()))
+        torch.testing.assert_close(taps[k], ref, rtol=1e-4, atol=1e-4 * float(ref.abs().max()))
 
 
 def test_model_oracle_with_torchvision_op():
@@ -51,7 +53,7 @@ def test_model_oracle_with_torchvision_op():
     g = np.load(GOLD / "dbnet_small.npz")
     sd = make_state_dict(int(g["seed"]))
     out = dbo.dbnet_forward(sd, torch.from_numpy(g["x"]), deform=dbo.torchvision_deform)
-    torch.testing.assert_close(out["bin_logits"], torch.from_numpy(g["out.bin_logits"]), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(out["bin_logits"], torch.from_numpy(g["out.bin_logits"]), rtol=1e-4, atol=1e-4)
 
 
 def test_deform_conv_restatement_matches_torchvision_golden():
@@ -272,3 +274,21 @@ def test_recprep_quirks():
     img = np.zeros((100, 100, 3), np.uint8)
     assert ro.crop_image(img, np.array([[120, 5], [130, 5], [130, 9], [120, 9]])).size == 0
     assert ro.rec_width(400, 2) == 0 and ro.rec_width(32, 256) == 256 and ro.rec_width(33, 300) == 290
+
+
+# ------------------------------------------------------------------ greedy CTC decode (tail)
+def test_ctc_restatement_matches_reference_code():
+    """oracle/ctc_oracle.py vs SVTRv2.decode_probs of the reference (tests/golden/make_ctc_golden.py): ids and strings."""
+    from oracle import ctc_oracle as co
+    g = np.load(GOLD / "ctc_reference.npz")
+    charset = "".join(g["charset"].tolist())
+    table = co.make_id_to_token(charset)
+    assert len(table) == int(g["num_classes"])
+    for name in "abc":
+        lp = g[f"{name}_log_probs"]
+        ids = co.greedy_ids(lp)
+        assert [len(i) for i in ids] == g[f"{name}_lengths"].tolist()
+        for b, i in enumerate(ids):
+            assert i == g[f"{name}_ids"][b, :len(i)].tolist()
+        assert co.decode_ids(ids, table) == g[f"{name}_texts"].tolist()
+    assert g["a_lengths"][0] == 0  # the all-blank sequence
