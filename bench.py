@@ -133,6 +133,68 @@ def cpu_reference_run(state_dict, steps, warmup, sample_hw=(1024, 1024), k=50.0)
     return ips, cores, sum(times) / len(times)
 
 
+def next_row_kernels(dev, peak_gbs):
+    """SURVEY 8(f) rows built after the detector: the detection -> recognition hand-over kernel and the greedy CTC decode,
+    timed alone with CUDA events (L2 flushed between launches), algorithmic bytes over time against the HBM copy peak."""
+    import numpy as np
+    import torch
+    from ocr_vi_invoice_b200.model.rec2 import VOCAB, GreedyCTCDecoder, Tokenizer
+    from ocr_vi_invoice_b200.postprocess import _BOX_DTYPE
+    from ocr_vi_invoice_b200.preprocess import det_size
+    from ocr_vi_invoice_b200.recprep import RecognitionCropper
+
+    rng = np.random.default_rng(0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timed(fn, iters=20):
+        for _ in range(3):
+            fn()
+        ms = []
+        for _ in range(iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        return float(np.median(ms))
+
+    # 16 pages of the generator's largest native size, 60 text-line boxes each, in detector (1024-px) coordinates
+    n_pages, n_boxes, h, w, mc = 16, 60, 1400, 1000, 1000
+    (nh, nw), (sh, sw) = det_size(h, w, 1024)
+    pages = [torch.randint(0, 256, (h, w, 3), dtype=torch.uint8, device=dev) for _ in range(n_pages)]
+    recs = np.zeros((n_pages, mc), dtype=_BOX_DTYPE)
+    src_bytes = 0
+    for i in range(n_pages):
+        for j in range(n_boxes):
+            bw, bh = int(rng.integers(60, 500)), int(rng.integers(18, 48))
+            x0, y0 = int(rng.integers(0, nw - bw)), int(rng.integers(0, nh - bh))
+            recs[i, j]["x0"], recs[i, j]["y0"], recs[i, j]["x1"], recs[i, j]["y1"] = x0, y0, x0 + bw, y0 + bh
+            src_bytes += int(bw / sw + 1) * int(bh / sh + 1) * 3
+    det = {"boxes": torch.from_numpy(recs.view(np.uint8).reshape(-1)).to(dev),
+           "counts": torch.full((n_pages,), n_boxes, dtype=torch.int32, device=dev)}
+    n = n_pages * n_boxes
+    cr = RecognitionCropper((32, 256), capacity=1024)
+    ms = timed(lambda: cr.from_detector(det, pages, [(sh, sw)] * n_pages, mc))
+    by = src_bytes + n * 3 * 32 * 256 * 4
+    out = {"rec_prep": {"kernel": "rec_prep_kernel<true> (box rescale + crop_image + preprocess_for_recognition)",
+                        "crops": n, "ms": round(ms, 4), "crops_per_s": round(n / ms * 1e3), "bound": "hbm",
+                        "algorithmic_bytes": by, "achieved": round(by / ms / 1e6, 1), "peak": peak_gbs, "unit": "GB/s",
+                        "frac": round(by / ms / 1e6 / peak_gbs, 3)}}
+    # the recogniser's output for those crops: T = 64 frames, 232 classes (SVTRv2 on 32 x 256 crops)
+    T, C = 64, Tokenizer(VOCAB).num_classes
+    lp = torch.randn(T, n, C, device=dev).log_softmax(-1)
+    dec = GreedyCTCDecoder(Tokenizer(VOCAB))
+    ms = timed(lambda: dec.run_device(lp))
+    by = T * n * C * 4 + n * (T + 1) * 4
+    out["ctc_greedy"] = {"kernel": "ctc_greedy_kernel (argmax + collapse of SVTRv2.decode_probs)", "sequences": n, "frames": T,
+                         "classes": C, "ms": round(ms, 4), "bound": "hbm", "algorithmic_bytes": by,
+                         "achieved": round(by / ms / 1e6, 1), "peak": peak_gbs, "unit": "GB/s",
+                         "frac": round(by / ms / 1e6 / peak_gbs, 3)}
+    return out
+
+
 def run_sharded(args, rank, world, dev, dist, model, post, config):
     """BASELINE configs[3]: N synthetic invoice images sharded over the ranks (contiguous shards, no collective on the
     data path), each rank streaming its shard through pipeline.Detector (uint8 HWC host images -> H2D -> GPU
@@ -427,6 +489,7 @@ def main():
                 "components_per_image": int(post.fetch(post.run_device(pm, want_labels=False))[1].mean()),
                 "top_launches_ms": [[n, round(ms, 3)] for n, _, ms, _ in top],
                 "clocks": clocks}
+        line["next_rows"] = next_row_kernels(dev, pk["hbm_gbs"])
         if not args.no_cpu_baseline and world == 1:
             ips, cores, sec = cpu_reference_run(sd_cpu, steps=2, warmup=1)
             line["cpu_baseline"] = {"value": round(ips, 4), "unit": "images/s", "cores": cores, "kind": "port",

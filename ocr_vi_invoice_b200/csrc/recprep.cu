@@ -21,7 +21,7 @@ namespace b200 {
 
 constexpr int kRecMaxImages = B200_REC_MAX_IMAGES;
 constexpr int kRecMaxTh = 64;
-constexpr int kRecThreads = 256;
+constexpr int kRecThreads = 128;  // 48 registers: 10 blocks per SM, a 16-page batch (~1000 slots) is resident in one wave
 
 struct RecImages {
     const uint8_t* pixels[kRecMaxImages];
@@ -73,11 +73,14 @@ __global__ void __launch_bounds__(kRecThreads) rec_prep_kernel(const __grid_cons
     }
     int n_slots;
     if (kFromBoxes) {
+        if (tid < imgs.n) s_prefix[tid + 1] = min(max(__ldg(p.counts + tid), 0), p.max_candidates);  // loads in parallel
+        __syncthreads();
         if (tid == 0) {
             int acc = 0;
             for (int i = 0; i < imgs.n; ++i) {
+                const int c = s_prefix[i + 1];
                 s_prefix[i] = acc;
-                acc += min(max(p.counts[i], 0), p.max_candidates);
+                acc += c;
             }
             s_prefix[imgs.n] = acc;
             if (blockIdx.x == 0) *p.total = acc;
