@@ -292,3 +292,29 @@ def test_ctc_restatement_matches_reference_code():
             assert i == g[f"{name}_ids"][b, :len(i)].tolist()
         assert co.decode_ids(ids, table) == g[f"{name}_texts"].tolist()
     assert g["a_lengths"][0] == 0  # the all-blank sequence
+
+
+# ------------------------------------------------------------------ SVTRv2 recogniser
+def test_svtrv2_restatement_matches_reference_module():
+    """oracle/svtrv2_oracle.py vs the reference's own SVTRv2('base') (tests/golden/make_svtrv2_golden.py): key set,
+    log-probabilities, stage taps, decoded strings."""
+    from oracle import ctc_oracle as co
+    from oracle import svtrv2_oracle as so
+    g = np.load(GOLD / "svtrv2_small.npz")
+    shapes = so.param_shapes("base")
+    assert len(shapes) == 318
+    assert sum(int(np.prod(s)) for k, s in shapes.items()
+               if not k.endswith(("running_mean", "running_var", "num_batches_tracked"))) == 22630864
+    sd = so.make_state_dict("base", int(g["seed"]))
+    taps = {}
+    lp = so.svtrv2_forward(sd, torch.from_numpy(g["x"]), "base", taps)
+    torch.testing.assert_close(lp, torch.from_numpy(g["log_probs"]), rtol=1e-4, atol=1e-4)
+    st = int(g["tap_stride"])
+    for k in ("stem", "stage0", "stage1", "stage2"):
+        ref = torch.from_numpy(g["tap." + k])
+        torch.testing.assert_close(taps[k][:, ::st], ref, rtol=1e-4, atol=1e-4 * float(ref.abs().max()))
+    for k in ("frm", "logits"):
+        ref = torch.from_numpy(g["tap." + k])
+        torch.testing.assert_close(taps[k], ref, rtol=1e-4, atol=1e-4 * float(ref.abs().max()))
+    from ocr_vi_invoice_b200.model.rec2 import VOCAB
+    assert co.decode_probs(lp.numpy(), VOCAB) == g["texts"].tolist()
