@@ -235,6 +235,29 @@ int b200_rec_prep_rects(const b200_image* images, int n_images, const b200_rec_r
 int b200_ctc_greedy(const float* log_probs, int T, int B, int C, int64_t stride_t, int64_t stride_b, int blank_id,
                     int32_t* tokens, int32_t* lengths, void* stream);
 
+/* ---- SVTRv2 recogniser: the kernels around the tcgen05 GEMMs ------------
+ * Every nn.Linear / nn.Conv2d of model/rec2/svtrv2.py runs through b200_igemm_* (tokens are the pixels of an NHWC image);
+ * these cover the rest.  All activations bf16, channels contiguous; statistics and accumulation in fp32. */
+/* ConvStem.conv1 + bn1 + GELU (svtrv2.py:112-114,120): x fp32 NCHW (batch, 3, h, w), w fp32 [mid][27] in (ci, ky, kx) order,
+ * scale/shift = folded BatchNorm + conv bias, y bf16 NHWC (batch, h/2, w/2, mid). */
+int b200_svtr_stem1(const float* x, const float* w, const float* scale, const float* shift, void* y,
+                    int batch, int h, int wd, int mid, void* stream);
+/* nn.LayerNorm over the last axis (svtrv2.py:93,95,173-187,446): rows of d channels, leading dimensions in elements. */
+int b200_layernorm(const void* x, void* y, const float* gamma, const float* beta, int64_t rows, int d,
+                   int x_ld, int y_ld, float eps, void* stream);
+/* y = GELU(x) (erf form) [+ residual when given] on n bf16 elements; y may equal x. */
+int b200_gelu(const void* x, const void* residual, void* y, int64_t n, void* stream);
+/* softmax(q k^T * scale) v per (sequence, head), head_dim 32 (GlobalMixing svtrv2.py:79-86, FRM rows :208-215).
+ * qkv: [n_seq][n][3*d], channel = which*d + head*32 + e; out: [n_seq][n][d], channel = head*32 + e. */
+int b200_mhsa(const void* qkv, void* out, int n_seq, int n, int d, float scale, void* stream);
+/* FRM vertical cross-attention of the selecting token (svtrv2.py:236-243): q fp32 [d] (parameters only),
+ * kv: [batch][h][w][2*d] (k | v), out: [batch][w][d]. */
+int b200_frm_select(const float* q, const void* kv, void* out, int batch, int h, int w, int d, float scale, void* stream);
+/* rows 0, 2, 4, .. of an NHWC tensor: the stride (2, 1) of PatchMerging (svtrv2.py:128) applied to a stride-1 conv output. */
+int b200_decimate_rows(const void* x, void* y, int batch, int in_h, int w, int c, void* stream);
+/* F.log_softmax over the classes + permute to (T, B, C) (svtrv2.py:536-537): logits fp32 [batch*t_len][ld]. */
+int b200_log_softmax_tbc(const float* logits, float* out, int batch, int t_len, int c, int ld, void* stream);
+
 /* ---- plain CUDA-core cross-check kernels (slow; used by the GPU tests, never by the engine) -- */
 int b200_ref_conv2d(const void* x, const void* w, const float* scale, const float* shift,
                     const void* residual, void* y, int batch, int in_h, int in_w, int in_c,

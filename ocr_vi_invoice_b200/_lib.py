@@ -78,6 +78,13 @@ SYMBOLS = {
     "b200_rec_prep_rects": (_i, [C.POINTER(Image), _i, _p, _i, _p, _p, _p, _i, _i, _i, C.POINTER(C.c_float),
                                  C.POINTER(C.c_float), _p]),
     "b200_ctc_greedy": (_i, [_p, _i, _i, _i, _i64, _i64, _i, _p, _p, _p]),
+    "b200_svtr_stem1": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "b200_layernorm": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _f, _p]),
+    "b200_gelu": (_i, [_p, _p, _p, _i64, _p]),
+    "b200_mhsa": (_i, [_p, _p, _i, _i, _i, _f, _p]),
+    "b200_frm_select": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _p]),
+    "b200_decimate_rows": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "b200_log_softmax_tbc": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "b200_ref_conv2d": (_i, [_p] * 6 + [_i] * 12 + [_p]),
     "b200_ref_dcn2d": (_i, [_p] * 6 + [_i] * 8 + [_p]),
 }

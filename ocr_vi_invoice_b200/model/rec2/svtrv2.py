@@ -1,0 +1,400 @@
+"""Drop-in SVTRv2 recogniser, inference only (reference: model/rec2/svtrv2.py:409-569).
+
+Same constructor (`variant`, `in_channels`, `charset`, `dropout`, `context_window`), the same 318 `state_dict` keys
+(strictly loadable from a reference checkpoint, src/pipeline/pipeline2.py:72-79 -- the training-only SGM parameters are
+held but never run), `forward(x) -> log_probs (T, B, num_classes)`, `decode_probs`, `decode_greedy`, `.tokenizer`,
+`.blank_id`.  The forward is a static launch list on one B200 (activations = NHWC bf16 token maps):
+
+  * every nn.Linear / nn.Conv2d except the 3-channel stem conv is one tcgen05 implicit-GEMM launch of igemm.cu (Linear =
+    1x1 conv over the token image; LocalMixing's grouped 3x3 convs = a 3x3 conv with block-diagonal weights, BatchNorm and
+    bias folded into the epilogue; residual adds in the epilogue);
+  * LayerNorm, GELU(+residual), multi-head attention (head_dim 32), the FRM selecting-token attention, PatchMerging's
+    row stride and log_softmax are the kernels of svtr.cu; the greedy decode is ctc.cu.
+
+No CPU fallback, no eager torch path: CPU tensors, training mode or `targets` raise.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from ... import ops
+from .decode import GreedyCTCDecoder
+from .tokenizer import Tokenizer
+from .vocab import VOCAB
+
+VARIANTS = {  # reference svtrv2.py:388-404
+    "tiny": {"dims": [64, 128, 256], "num_blocks": [3, 6, 3], "num_local": [3, 3, 0]},
+    "small": {"dims": [96, 192, 256], "num_blocks": [3, 6, 6], "num_local": [3, 3, 0]},
+    "base": {"dims": [128, 256, 384], "num_blocks": [3, 6, 6], "num_local": [3, 2, 0]},
+}
+
+
+# ---------------------------------------------------------------------------------------- parameter holders (no forward)
+class _MLP(nn.Module):
+    def __init__(self, dim, expansion=4):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, int(dim * expansion))
+        self.fc2 = nn.Linear(int(dim * expansion), dim)
+
+
+class _Local(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        g = max(dim // 32, 1)
+        self.conv1 = nn.Conv2d(dim, dim, 3, 1, 1, groups=g)
+        self.bn1 = nn.BatchNorm2d(dim)
+        self.conv2 = nn.Conv2d(dim, dim, 3, 1, 1, groups=g)
+        self.bn2 = nn.BatchNorm2d(dim)
+
+
+class _Global(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.qkv = nn.Linear(dim, dim * 3)
+        self.proj = nn.Linear(dim, dim)
+
+
+class _Block(nn.Module):
+    def __init__(self, dim, is_local):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim)
+        self.mixer = _Local(dim) if is_local else _Global(dim)
+        self.norm2 = nn.LayerNorm(dim)
+        self.mlp = _MLP(dim)
+
+
+class _Stage(nn.Module):
+    def __init__(self, dim, num_blocks, num_local):
+        super().__init__()
+        self.blocks = nn.ModuleList(_Block(dim, i < num_local) for i in range(num_blocks))
+
+
+class _Stem(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cout // 2, 3, stride=2, padding=1)
+        self.bn1 = nn.BatchNorm2d(cout // 2)
+        self.conv2 = nn.Conv2d(cout // 2, cout, 3, stride=2, padding=1)
+        self.bn2 = nn.BatchNorm2d(cout)
+
+
+class _Merge(nn.Module):
+    def __init__(self, din, dout):
+        super().__init__()
+        self.conv = nn.Conv2d(din, dout, 3, stride=(2, 1), padding=1)
+        self.norm = nn.BatchNorm2d(dout)
+
+
+class _FRM(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.h_qkv = nn.Linear(dim, dim * 3)
+        self.h_proj = nn.Linear(dim, dim)
+        self.h_norm = nn.LayerNorm(dim)
+        self.h_mlp = _MLP(dim)
+        self.h_norm2 = nn.LayerNorm(dim)
+        self.select_token = nn.Parameter(torch.randn(1, 1, dim) * 0.02)
+        self.v_q = nn.Linear(dim, dim)
+        self.v_kv = nn.Linear(dim, dim * 2)
+        self.v_proj = nn.Linear(dim, dim)
+        self.v_norm_q = nn.LayerNorm(dim)
+        self.v_norm_kv = nn.LayerNorm(dim)
+        self.v_mlp = _MLP(dim)
+        self.v_norm2 = nn.LayerNorm(dim)
+
+
+class _SGM(nn.Module):
+    """Training-only branch (reference svtrv2.py:253-383): parameters kept for strict state_dict loading, never run."""
+
+    def __init__(self, dim, num_classes):
+        super().__init__()
+        heads = max(dim // 32, 1)
+        self.char_embed = nn.Embedding(num_classes, dim)
+        self.context_norm = nn.LayerNorm(dim)
+        self.context_attn = nn.MultiheadAttention(dim, heads, batch_first=True)
+        self.context_mlp = _MLP(dim, expansion=2)
+        self.context_norm2 = nn.LayerNorm(dim)
+        self.left_token = nn.Parameter(torch.randn(1, 1, dim) * 0.02)
+        self.right_token = nn.Parameter(torch.randn(1, 1, dim) * 0.02)
+        self.cross_q = nn.Linear(dim, dim)
+        self.cross_kv = nn.Linear(dim, dim * 2)
+        self.cross_proj = nn.Linear(dim, dim)
+        self.cross_norm_q = nn.LayerNorm(dim)
+        self.cross_norm_kv = nn.LayerNorm(dim)
+        self.sgm_head = nn.Linear(dim, num_classes)
+
+
+# ---------------------------------------------------------------------------------------- weight preparation
+class _Prepared:
+    """bf16 K-major matrices + fp32 (scale, shift) per GEMM, fp32 LayerNorm affines, the constant FRM query."""
+
+    def __init__(self, model: "SVTRv2", device):
+        f32 = lambda t: t.detach().to(device=device, dtype=torch.float32)
+        self.device = device
+        self.G: Dict[str, tuple] = {}
+        self.LN: Dict[str, tuple] = {}
+
+        def linear(name, lin, extra_shift=None):
+            w = ops.pack_conv_weight(f32(lin.weight).reshape(lin.out_features, lin.in_features, 1, 1))
+            shift = f32(lin.bias) if extra_shift is None else f32(lin.bias) + extra_shift
+            self.G[name] = (w, torch.ones(w.shape[0], device=device), ops.pad_vec(shift, w.shape[0]))
+
+        def conv_bn(name, conv, bn):
+            w = f32(conv.weight)
+            if conv.groups > 1:  # grouped -> block-diagonal dense (o, i, 3, 3)
+                o, ig = w.shape[0], w.shape[1]
+                dense = torch.zeros(o, ig * conv.groups, 3, 3, device=device)
+                og = o // conv.groups
+                for g in range(conv.groups):
+                    dense[g * og:(g + 1) * og, g * ig:(g + 1) * ig] = w[g * og:(g + 1) * og]
+                w = dense
+            wp = ops.pack_conv_weight(w)
+            s, t = ops.fold_bn(f32(bn.weight), f32(bn.bias), f32(bn.running_mean), f32(bn.running_var), bn.eps, f32(conv.bias))
+            self.G[name] = (wp, ops.pad_vec(s, wp.shape[0], 1.0), ops.pad_vec(t, wp.shape[0]))
+
+        def ln(name, m):
+            self.LN[name] = (f32(m.weight).contiguous(), f32(m.bias).contiguous(), float(m.eps))
+
+        st = model.stem
+        s, t = ops.fold_bn(f32(st.bn1.weight), f32(st.bn1.bias), f32(st.bn1.running_mean), f32(st.bn1.running_var), st.bn1.eps,
+                           f32(st.conv1.bias))
+        self.stem1 = (f32(st.conv1.weight).reshape(st.conv1.out_channels, 27).contiguous(), s.contiguous(), t.contiguous())
+        conv_bn("stem.conv2", st.conv2, st.bn2)
+        for si, stage in enumerate(model.stages):
+            for bi, blk in enumerate(stage.blocks):
+                p = f"stages.{si}.blocks.{bi}"
+                ln(p + ".norm1", blk.norm1)
+                ln(p + ".norm2", blk.norm2)
+                if isinstance(blk.mixer, _Local):
+                    conv_bn(p + ".conv1", blk.mixer.conv1, blk.mixer.bn1)
+                    conv_bn(p + ".conv2", blk.mixer.conv2, blk.mixer.bn2)
+                else:
+                    linear(p + ".qkv", blk.mixer.qkv)
+                    linear(p + ".proj", blk.mixer.proj)
+                linear(p + ".fc1", blk.mlp.fc1)
+                linear(p + ".fc2", blk.mlp.fc2)
+        for mi, mg in enumerate(model.merges):
+            conv_bn(f"merges.{mi}", mg.conv, mg.norm)
+        ln("backbone_norm", model.backbone_norm)
+        fr = model.frm
+        for n in ("h_norm", "h_norm2", "v_norm_kv", "v_norm2"):
+            ln("frm." + n, getattr(fr, n))
+        linear("frm.h_qkv", fr.h_qkv)
+        linear("frm.h_proj", fr.h_proj)
+        linear("frm.h_fc1", fr.h_mlp.fc1)
+        linear("frm.h_fc2", fr.h_mlp.fc2)
+        linear("frm.v_kv", fr.v_kv)
+        tok = f32(fr.select_token).reshape(-1)
+        linear("frm.v_proj", fr.v_proj, extra_shift=tok)  # t_q = select_token + v_proj(out)  (svtrv2.py:244)
+        linear("frm.v_fc1", fr.v_mlp.fc1)
+        linear("frm.v_fc2", fr.v_mlp.fc2)
+        # the query of the vertical attention depends on parameters only (svtrv2.py:226-233): v_q(v_norm_q(select_token))
+        qn = torch.nn.functional.layer_norm(tok, (tok.numel(),), f32(fr.v_norm_q.weight), f32(fr.v_norm_q.bias), fr.v_norm_q.eps)
+        self.frm_q = (f32(fr.v_q.weight) @ qn + f32(fr.v_q.bias)).contiguous()
+        linear("head", model.head)
+        self.num_classes = model.head.out_features
+
+
+class _Plan:
+    """Static launch list + activation buffers for one batch size (crops are (3, H, W) with H % 8 == 0, W % 4 == 0)."""
+
+    def __init__(self, W: _Prepared, cfg, batch: int, H: int, Wd: int):
+        dev = W.device
+        self.batch = batch
+        b = batch + (batch & 1)  # whole 2-row tiles for the token-matrix GEMMs; the padding crop is zeros
+        self.bp = b
+        dims = cfg["dims"]
+        bf = lambda *s: torch.empty(*s, device=dev, dtype=torch.bfloat16)
+        self.x_in = torch.zeros(b, 3, H, Wd, device=dev, dtype=torch.float32)
+        self.steps: List = []
+        self.names: List[str] = []
+        self.flops = 0.0
+        self.keep: List = []
+
+        def add(name, fn):
+            self.steps.append(fn)
+            self.names.append(name)
+
+        def gemm(name, key, x, y, *, rows=None, geom=None, in_c, out_c, ksize=1, stride=1, flags=0, residual=None):
+            """rows: token-matrix Linear (image = 1 x rows/64 x 64); geom = (batch, h, w): a real convolution."""
+            w, s, t = W.G[key]
+            if geom is None:
+                assert rows % 128 == 0
+                geom = (1, rows // 64, 64)
+            op = ops.Igemm(ops.IGEMM_CONV, x, w, s, t, y, batch=geom[0], in_h=geom[1], in_w=geom[2], in_c=in_c, out_c=out_c,
+                           ksize=ksize, stride=stride, flags=flags, residual=residual, res_ld=out_c if residual is not None else 0,
+                           name=name)
+            self.flops += op.flops
+            add(name, op)
+
+        def lnorm(name, key, x, y, rows, d):
+            g, be, eps = W.LN[key]
+            add(name, lambda: ops.layernorm(x, y, g, be, rows, d, eps))
+
+        h, w = H // 4, Wd // 4
+        mid = dims[0] // 2
+        s1 = bf(b, H // 2, Wd // 2, mid)
+        add("stem.conv1", lambda: ops.svtr_stem1(self.x_in, *W.stem1, s1))
+        x = bf(b, h, w, dims[0])
+        gemm("stem.conv2", "stem.conv2", s1, x, geom=(b, H // 2, Wd // 2), in_c=mid, out_c=dims[0], ksize=3, stride=2)
+        add("stem.gelu2", lambda x=x: ops.gelu(x))
+        self.taps = {"stem": (x, len(self.steps))}  # (buffer, number of steps after which it holds the tap)
+        for si in range(3):
+            d = dims[si]
+            rows = b * h * w
+            other = bf(b, h, w, d)
+            nbuf, cbuf, cbuf2 = bf(b, h, w, d), bf(b, h, w, d), bf(b, h, w, d)
+            hid = bf(b, h, w, 4 * d)
+            qkv = bf(b, h, w, 3 * d) if cfg["num_local"][si] < cfg["num_blocks"][si] else None
+            for bi in range(cfg["num_blocks"][si]):
+                p = f"stages.{si}.blocks.{bi}"
+                lnorm(p + ".norm1", p + ".norm1", x, nbuf, rows, d)
+                if bi < cfg["num_local"][si]:
+                    gemm(p + ".conv1", p + ".conv1", nbuf, cbuf, geom=(b, h, w), in_c=d, out_c=d, ksize=3)
+                    add(p + ".gelu1", lambda c=cbuf: ops.gelu(c))
+                    gemm(p + ".conv2", p + ".conv2", cbuf, cbuf2, geom=(b, h, w), in_c=d, out_c=d, ksize=3)
+                    add(p + ".gelu2+res", lambda c=cbuf2, r=x, y=other: ops.gelu(c, y, r))
+                else:
+                    gemm(p + ".qkv", p + ".qkv", nbuf, qkv, rows=rows, in_c=d, out_c=3 * d)
+                    add(p + ".attn", lambda q=qkv, o=cbuf, n=h * w, d=d: ops.mhsa(q, o, b, n, d))
+                    gemm(p + ".proj", p + ".proj", cbuf, other, rows=rows, in_c=d, out_c=d, flags=ops.EPI_RES, residual=x)
+                x, other = other, x
+                lnorm(p + ".norm2", p + ".norm2", x, nbuf, rows, d)
+                gemm(p + ".fc1", p + ".fc1", nbuf, hid, rows=rows, in_c=d, out_c=4 * d)
+                add(p + ".gelu", lambda t=hid: ops.gelu(t))
+                gemm(p + ".fc2", p + ".fc2", hid, other, rows=rows, in_c=4 * d, out_c=d, flags=ops.EPI_RES, residual=x)
+                x, other = other, x
+            self.taps[f"stage{si}"] = (x, len(self.steps))
+            if si < 2:  # PatchMerging: stride-1 3x3 conv + BN, then every second row
+                dn = dims[si + 1]
+                full = bf(b, h, w, dn)
+                gemm(f"merges.{si}", f"merges.{si}", x, full, geom=(b, h, w), in_c=d, out_c=dn, ksize=3)
+                nx = bf(b, h // 2, w, dn)
+                add(f"merges.{si}.rows", lambda f=full, y=nx, hh=h, ww=w, c=dn: ops.decimate_rows(f, y, b, hh, ww, c))
+                x, h = nx, h // 2
+        d = dims[2]
+        rows = b * h * w
+        xn = bf(b, h, w, d)
+        lnorm("backbone_norm", "backbone_norm", x, xn, rows, d)
+        # ---- FRM, horizontal: self-attention inside each row of w tokens
+        n1, qkv, att, r2, r3 = bf(rows, d), bf(rows, 3 * d), bf(rows, d), bf(rows, d), bf(rows, d)
+        hid = bf(rows, 4 * d)
+        lnorm("frm.h_norm", "frm.h_norm", xn, n1, rows, d)
+        gemm("frm.h_qkv", "frm.h_qkv", n1, qkv, rows=rows, in_c=d, out_c=3 * d)
+        add("frm.h_attn", lambda: ops.mhsa(qkv, att, b * h, w, d))
+        gemm("frm.h_proj", "frm.h_proj", att, r2, rows=rows, in_c=d, out_c=d, flags=ops.EPI_RES, residual=xn)
+        lnorm("frm.h_norm2", "frm.h_norm2", r2, n1, rows, d)
+        gemm("frm.h_fc1", "frm.h_fc1", n1, hid, rows=rows, in_c=d, out_c=4 * d)
+        add("frm.h_gelu", lambda: ops.gelu(hid))
+        gemm("frm.h_fc2", "frm.h_fc2", hid, r3, rows=rows, in_c=4 * d, out_c=d, flags=ops.EPI_RES, residual=r2)
+        self.taps["frm_h"] = (r3, len(self.steps))
+        # ---- FRM, vertical: the selecting token attends over the h rows of each column
+        kv = bf(rows, 2 * d)
+        lnorm("frm.v_norm_kv", "frm.v_norm_kv", r3, n1, rows, d)
+        gemm("frm.v_kv", "frm.v_kv", n1, kv, rows=rows, in_c=d, out_c=2 * d)
+        trows = b * w
+        sel, t1, t1n, t2 = bf(trows, d), bf(trows, d), bf(trows, d), bf(trows, d)
+        thid = bf(trows, 4 * d)
+        add("frm.v_attn", lambda: ops.frm_select(W.frm_q, kv, sel, b, h, w, d))
+        gemm("frm.v_proj", "frm.v_proj", sel, t1, rows=trows, in_c=d, out_c=d)
+        lnorm("frm.v_norm2", "frm.v_norm2", t1, t1n, trows, d)
+        gemm("frm.v_fc1", "frm.v_fc1", t1n, thid, rows=trows, in_c=d, out_c=4 * d)
+        add("frm.v_gelu", lambda: ops.gelu(thid))
+        gemm("frm.v_fc2", "frm.v_fc2", thid, t2, rows=trows, in_c=4 * d, out_c=d, flags=ops.EPI_RES, residual=t1)
+        self.taps["frm"] = (t2, len(self.steps))
+        nc = W.num_classes
+        self.ld = (nc + 7) // 8 * 8
+        self.logits = torch.empty(trows, self.ld, device=dev, dtype=torch.float32)
+        w_head = W.G["head"][0]
+        op = ops.Igemm(ops.IGEMM_CONV, t2, *W.G["head"], self.logits, batch=1, in_h=trows // 64, in_w=64, in_c=d, out_c=self.ld,
+                       ksize=1, stride=1, flags=ops.EPI_OUT_F32, name="head")
+        self.flops += op.flops
+        add("head", op)
+        self.T, self.nc = w, nc
+        self.log_probs = torch.empty(w, b, nc, device=dev, dtype=torch.float32)
+        add("log_softmax", lambda: ops.log_softmax_tbc(self.logits, self.log_probs, b, w, nc, self.ld))
+        self.n_launches = len(self.steps)
+
+    def run(self, x: torch.Tensor, taps: Optional[dict] = None) -> torch.Tensor:
+        self.x_in[:self.batch].copy_(x)
+        for i, s in enumerate(self.steps):
+            s()
+            if taps is not None:  # buffers are recycled by later blocks: copy a tap right after the step that completes it
+                for k, (buf, after) in self.taps.items():
+                    if after == i + 1:
+                        taps[k] = buf.float().reshape(self.bp, -1, buf.shape[-1])[:self.batch].clone()
+        return self.log_probs[:, :self.batch]
+
+
+# ---------------------------------------------------------------------------------------- the module
+class SVTRv2(nn.Module):
+    def __init__(self, variant="small", in_channels=3, charset=VOCAB, dropout=0.0, context_window=3):
+        super().__init__()
+        assert variant in VARIANTS, f"Unknown variant: {variant}. Choose from {list(VARIANTS.keys())}"
+        cfg = VARIANTS[variant]
+        dims = cfg["dims"]
+        if in_channels != 3 or any(d % 64 for d in dims):
+            raise NotImplementedError("B200 SVTRv2 path: 3 input channels and stage widths that are multiples of 64 "
+                                      "('base'; 'tiny' and 'small' have 96 / 192-wide or 64-wide stages the tcgen05 "
+                                      "GEMM's 64-channel K blocks do not cover yet) -- no unaccelerated fallback")
+        self.variant, self.cfg = variant, cfg
+        self.tokenizer = Tokenizer(charset)
+        self.dims = dims
+        self.stem = _Stem(in_channels, dims[0])
+        self.stages = nn.ModuleList(_Stage(dims[i], cfg["num_blocks"][i], cfg["num_local"][i]) for i in range(3))
+        self.merges = nn.ModuleList(_Merge(dims[i], dims[i + 1]) for i in range(2))
+        self.backbone_norm = nn.LayerNorm(dims[2])
+        self.frm = _FRM(dims[2])
+        self.sgm = _SGM(dims[2], self.tokenizer.num_classes)
+        self.head = nn.Linear(dims[2], self.tokenizer.num_classes)
+        self.blank_id = self.tokenizer.blank_id
+        self._prepared: Optional[_Prepared] = None
+        self._sig = None
+        self._plans: Dict[tuple, _Plan] = {}
+        self._decoder = GreedyCTCDecoder(self.tokenizer)
+
+    def _signature(self):
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
+    def _plan(self, x) -> _Plan:
+        sig = (x.device, self._signature())
+        if self._prepared is None or self._sig != sig:
+            self._prepared, self._sig = _Prepared(self, x.device), sig
+            self._plans.clear()
+        key = tuple(x.shape)
+        if key not in self._plans:
+            self._plans[key] = _Plan(self._prepared, self.cfg, x.shape[0], x.shape[2], x.shape[3])
+        return self._plans[key]
+
+    @torch.no_grad()
+    def forward(self, x, targets=None):
+        if targets is not None or self.training:
+            raise RuntimeError("B200 SVTRv2 path is inference-only: call model.eval() and pass no targets "
+                               "(the SGM branch and training, src/rec2/train.py, are out of scope)")
+        if not (isinstance(x, torch.Tensor) and x.dim() == 4 and x.shape[1] == 3 and x.is_floating_point()):
+            raise ValueError("SVTRv2.forward expects a float (B, 3, H, W) tensor")
+        if not x.is_cuda:
+            raise RuntimeError("B200 SVTRv2 path runs on CUDA only (there is no CPU fallback)")
+        if x.shape[2] % 8 or x.shape[3] % 4 or (x.shape[3] // 4) != 64:
+            raise ValueError("B200 SVTRv2 path: crops must be (3, H, 256) with H a multiple of 8 (the pipeline's 32 x 256)")
+        with torch.cuda.device(x.device):
+            return self._plan(x).run(x.float().contiguous())
+
+    @torch.no_grad()
+    def forward_with_taps(self, x):
+        """forward + (B, N, D) fp32 copies of the stage outputs, for the parity tests."""
+        with torch.cuda.device(x.device):
+            taps = {}
+            lp = self._plan(x).run(x.float().contiguous(), taps).clone()
+            return lp, taps
+
+    def decode_probs(self, log_probs):
+        return self._decoder(log_probs)
+
+    @torch.inference_mode()
+    def decode_greedy(self, images):
+        self.eval()
+        return self.decode_probs(self.forward(images))

@@ -16,7 +16,7 @@ from ._lib import (EPI_DCN_COORDS, EPI_HEAD_DOT, EPI_OUT_F32, EPI_RELU, EPI_RES,
 
 __all__ = [
     "Igemm", "pack_conv_weight", "pack_stem_weight", "pack_convT_weight", "fold_bn", "pad_vec",
-    "stem_pack", "stem_pack_u8", "resize_u8_linear", "maxpool3x3s2", "asf_fwd", "asf_combine", "db_head_fwd", "postproc", "rec_prep_boxes", "rec_prep_rects", "ctc_greedy", "ref_conv2d", "ref_dcn2d",
+    "stem_pack", "stem_pack_u8", "resize_u8_linear", "maxpool3x3s2", "asf_fwd", "asf_combine", "db_head_fwd", "postproc", "rec_prep_boxes", "rec_prep_rects", "ctc_greedy", "svtr_stem1", "layernorm", "gelu", "mhsa", "frm_select", "decimate_rows", "log_softmax_tbc", "ref_conv2d", "ref_dcn2d",
     "EPI_RELU", "EPI_RES", "EPI_RES_UP2", "EPI_OUT_F32", "EPI_SHUFFLE2", "EPI_DCN_COORDS", "EPI_HEAD_DOT", "db_maps", "dcn_coords", "IGEMM_CONV", "IGEMM_STEM", "IGEMM_DCN",
 ]
 
@@ -273,6 +273,42 @@ def ctc_greedy(log_probs: torch.Tensor, blank_id: int, tokens: torch.Tensor, len
     _lib.check(_lib.load().b200_ctc_greedy(_lib.ptr(log_probs), T, B, C, log_probs.stride(0), log_probs.stride(1),
                                            int(blank_id), _lib.ptr(tokens), _lib.ptr(lengths), _lib.current_stream()),
                "ctc_greedy")
+
+
+# ----------------------------------------------------------------------------- SVTRv2 (model/rec2/svtrv2.py)
+def svtr_stem1(x, w, scale, shift, y) -> None:
+    b, c, h, wd = x.shape
+    assert c == 3 and x.dtype == torch.float32 and x.is_contiguous() and y.dtype == torch.bfloat16
+    _lib.check(_lib.load().b200_svtr_stem1(_lib.ptr(x), _lib.ptr(w), _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(y), b, h, wd,
+                                           w.shape[0], _lib.current_stream()), "svtr_stem1")
+
+
+def layernorm(x, y, gamma, beta, rows: int, d: int, eps: float = 1e-5, x_ld: int = 0, y_ld: int = 0) -> None:
+    _lib.check(_lib.load().b200_layernorm(_lib.ptr(x), _lib.ptr(y), _lib.ptr(gamma), _lib.ptr(beta), rows, d, x_ld or d,
+                                          y_ld or d, float(eps), _lib.current_stream()), "layernorm")
+
+
+def gelu(x, y=None, residual=None) -> None:
+    y = x if y is None else y
+    _lib.check(_lib.load().b200_gelu(_lib.ptr(x), _lib.ptr(residual), _lib.ptr(y), x.numel(), _lib.current_stream()), "gelu")
+
+
+def mhsa(qkv, out, n_seq: int, n: int, d: int) -> None:
+    _lib.check(_lib.load().b200_mhsa(_lib.ptr(qkv), _lib.ptr(out), n_seq, n, d, 32.0 ** -0.5, _lib.current_stream()), "mhsa")
+
+
+def frm_select(q, kv, out, batch: int, h: int, w: int, d: int) -> None:
+    _lib.check(_lib.load().b200_frm_select(_lib.ptr(q), _lib.ptr(kv), _lib.ptr(out), batch, h, w, d, 32.0 ** -0.5,
+                                           _lib.current_stream()), "frm_select")
+
+
+def decimate_rows(x, y, batch: int, in_h: int, w: int, c: int) -> None:
+    _lib.check(_lib.load().b200_decimate_rows(_lib.ptr(x), _lib.ptr(y), batch, in_h, w, c, _lib.current_stream()), "decimate_rows")
+
+
+def log_softmax_tbc(logits, out, batch: int, t_len: int, c: int, ld: int) -> None:
+    _lib.check(_lib.load().b200_log_softmax_tbc(_lib.ptr(logits), _lib.ptr(out), batch, t_len, c, ld, _lib.current_stream()),
+               "log_softmax_tbc")
 
 
 def ref_conv2d(x, w, scale, shift, residual, y, batch, in_h, in_w, in_c, out_c, ksize, stride, flags, out_ld,

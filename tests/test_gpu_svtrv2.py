@@ -1,0 +1,170 @@
+"""GPU: SVTRv2 recogniser -- the svtr.cu kernels one by one against torch fp32, then the whole
+drop-in model against the oracle (pinned to the reference's own module) on the golden crops.
+
+Tolerances (bf16 storage, fp32 accumulation, stated per check): single kernels 1 bf16 ulp-ish (2^-7 relative to the row
+scale); whole model: rms(error) / rms(stage) per stage tap, and agreement of the per-frame arg-max where the oracle's
+margin between the two best classes exceeds the observed logit error."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden"
+DEV = "cuda"
+
+
+def _bf(t):
+    return t.to(torch.bfloat16)
+
+
+def _rel(a, b):
+    return float((a.float() - b.float()).pow(2).mean().sqrt() / b.float().pow(2).mean().sqrt().clamp_min(1e-12))
+
+
+def test_layernorm_gelu_decimate_logsoftmax():
+    from ocr_vi_invoice_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(0)
+    for d in (128, 256, 384, 1024):
+        rows = 777
+        x = _bf(torch.randn(rows, d, generator=g) * 3 + 1).to(DEV)
+        gamma, beta = (torch.rand(d, generator=g) + 0.5).to(DEV), torch.randn(d, generator=g).to(DEV)
+        y = torch.empty_like(x)
+        ops.layernorm(x, y, gamma, beta, rows, d, 1e-5)
+        ref = F.layer_norm(x.float(), (d,), gamma, beta, 1e-5)
+        assert torch.equal(y, _bf(ref)) or (y.float() - ref).abs().max() <= 2 ** -7 * ref.abs().max()
+        assert _rel(y, ref) < 3e-3
+    x = _bf(torch.randn(4096 * 8, generator=g) * 3).to(DEV)
+    r = _bf(torch.randn(4096 * 8, generator=g)).to(DEV)
+    y = torch.empty_like(x)
+    ops.gelu(x, y)
+    assert _rel(y, F.gelu(x.float())) < 3e-3
+    ops.gelu(x, y, r)
+    assert _rel(y, F.gelu(x.float()) + r.float()) < 3e-3
+    ops.gelu(x)  # in place
+    assert _rel(x, y.float() - r.float()) < 1e-2
+    t = _bf(torch.randn(3, 8, 64, 128, generator=g)).to(DEV)
+    o = torch.empty(3, 4, 64, 128, dtype=torch.bfloat16, device=DEV)
+    ops.decimate_rows(t, o, 3, 8, 64, 128)
+    assert torch.equal(o, t[:, ::2])
+    logits = torch.randn(5 * 64, 232, generator=g).to(DEV) * 4
+    out = torch.empty(64, 5, 232, device=DEV)
+    ops.log_softmax_tbc(logits, out, 5, 64, 232, 232)
+    ref = F.log_softmax(logits.reshape(5, 64, 232).permute(1, 0, 2), dim=-1)
+    torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-5)
+
+
+def test_stem_conv1():
+    from ocr_vi_invoice_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(3, 3, 32, 256, generator=g)
+    w = torch.randn(64, 3, 3, 3, generator=g) * 0.3
+    scale, shift = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.2
+    y = torch.empty(3, 16, 128, 64, dtype=torch.bfloat16, device=DEV)
+    ops.svtr_stem1(x.to(DEV), w.reshape(64, 27).contiguous().to(DEV), scale.to(DEV), shift.to(DEV), y)
+    ref = F.gelu(F.conv2d(x, w, None, 2, 1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)).permute(0, 2, 3, 1)
+    assert _rel(y.cpu(), ref) < 3e-3
+
+
+@pytest.mark.parametrize("n_seq,n,d", [(6, 64, 384), (3, 256, 256), (2, 128, 384), (1, 512, 128), (5, 40, 64)])
+def test_mhsa(n_seq, n, d):
+    from ocr_vi_invoice_b200 import ops
+    g = torch.Generator().manual_seed(n)
+    qkv = _bf(torch.randn(n_seq, n, 3 * d, generator=g) * 1.5).to(DEV)
+    out = torch.empty(n_seq, n, d, dtype=torch.bfloat16, device=DEV)
+    ops.mhsa(qkv, out, n_seq, n, d)
+    heads = d // 32
+    t = qkv.float().reshape(n_seq, n, 3, heads, 32).permute(2, 0, 3, 1, 4)
+    ref = ((t[0] @ t[1].transpose(-2, -1)) * 32 ** -0.5).softmax(-1) @ t[2]
+    ref = ref.transpose(1, 2).reshape(n_seq, n, d)
+    assert _rel(out, ref) < 4e-3
+
+
+def test_frm_select():
+    from ocr_vi_invoice_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    b, h, w, d = 3, 2, 64, 384
+    q = torch.randn(d, generator=g).to(DEV)
+    kv = _bf(torch.randn(b, h, w, 2 * d, generator=g)).to(DEV)
+    out = torch.empty(b, w, d, dtype=torch.bfloat16, device=DEV)
+    ops.frm_select(q, kv, out, b, h, w, d)
+    heads = d // 32
+    k = kv.float()[..., :d].reshape(b, h, w, heads, 32)
+    v = kv.float()[..., d:].reshape(b, h, w, heads, 32)
+    s = (k * q.reshape(heads, 32)).sum(-1) * 32 ** -0.5          # (b, h, w, heads)
+    p = s.softmax(dim=1)
+    ref = (p.unsqueeze(-1) * v).sum(1).reshape(b, w, d)
+    assert _rel(out, ref) < 4e-3
+
+
+def test_linear_as_token_image_gemm():
+    """nn.Linear through the tcgen05 kernel with N not a multiple of the block (232 fp32 logits, 1152 / 384 bf16 columns)."""
+    from ocr_vi_invoice_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    rows = 6 * 64
+    for din, dout, f32out in ((384, 232, True), (384, 1152, False), (1536, 384, False), (128, 512, False)):
+        x = _bf(torch.randn(rows, din, generator=g)).to(DEV)
+        wt = torch.randn(dout, din, generator=g) * din ** -0.5
+        bias = torch.randn(dout, generator=g)
+        w = ops.pack_conv_weight(wt.reshape(dout, din, 1, 1).to(DEV))
+        s, t = torch.ones(w.shape[0], device=DEV), ops.pad_vec(bias.to(DEV), w.shape[0])
+        res = _bf(torch.randn(rows, dout, generator=g)).to(DEV)
+        y = torch.full((rows, dout), 7.0, dtype=torch.float32 if f32out else torch.bfloat16, device=DEV)
+        flags = ops.EPI_OUT_F32 if f32out else ops.EPI_RES
+        op = ops.Igemm(ops.IGEMM_CONV, x, w, s, t, y, batch=1, in_h=rows // 64, in_w=64, in_c=din, out_c=dout, ksize=1, stride=1,
+                       flags=flags, residual=None if f32out else res, res_ld=0 if f32out else dout)
+        op()
+        ref = x.float() @ _bf(wt).float().t().to(DEV) + bias.to(DEV) + (0 if f32out else res.float())
+        assert _rel(y, ref) < (1e-4 if f32out else 4e-3), (din, dout)
+
+
+def _golden_model():
+    from oracle import svtrv2_oracle as so
+    from ocr_vi_invoice_b200.model.rec2.svtrv2 import SVTRv2
+    g = np.load(GOLD / "svtrv2_small.npz")
+    sd = so.make_state_dict("base", int(g["seed"]))
+    model = SVTRv2(variant="base")
+    model.load_state_dict(sd, strict=True)
+    return g, sd, model.to(DEV).eval()
+
+
+def test_model_against_oracle_and_reference_golden():
+    from oracle import svtrv2_oracle as so
+    g, sd, model = _golden_model()
+    x = torch.from_numpy(g["x"])
+    lp, taps = model.forward_with_taps(x.to(DEV))
+    ref_taps = {}
+    ref = so.svtrv2_forward(sd, x, "base", ref_taps)
+    torch.testing.assert_close(ref, torch.from_numpy(g["log_probs"]), rtol=1e-4, atol=1e-4)  # the oracle is the reference
+    errs = {k: _rel(taps[k].cpu(), ref_taps[k]) for k in ("stem", "stage0", "stage1", "stage2", "frm_h", "frm")}
+    print("rel rms error per stage:", {k: round(v, 4) for k, v in errs.items()})
+    assert errs["stem"] < 0.01 and errs["stage0"] < 0.02 and errs["stage1"] < 0.03 and errs["stage2"] < 0.04
+    assert errs["frm_h"] < 0.05 and errs["frm"] < 0.05
+    lp = lp.cpu()
+    assert lp.shape == ref.shape and torch.isfinite(lp).all()
+    torch.testing.assert_close(lp.exp().sum(-1), torch.ones(lp.shape[:2]), rtol=1e-4, atol=1e-4)
+    err = (lp - ref).abs().max().item()
+    print("max |log_prob error|:", err)
+    assert err < 0.15
+    top2 = ref.topk(2, dim=-1).values
+    clear = (top2[..., 0] - top2[..., 1]) > 2 * err
+    assert clear.float().mean() > 0.5
+    assert torch.equal(lp.argmax(-1)[clear], ref.argmax(-1)[clear])
+
+
+def test_model_batches_and_decode():
+    """Odd batch (padding crop), batch invariance bit for bit, decode_greedy == decode_probs(forward), CPU refusal."""
+    g, sd, model = _golden_model()
+    x = torch.from_numpy(g["x"]).to(DEV)
+    lp3 = model(x).clone()
+    big = torch.cat([x, x.flip(0), x[:1]])  # 7 crops
+    lp7 = model(big).clone()
+    assert torch.equal(lp7[:, :3], lp3) and torch.equal(lp7[:, 6], lp3[:, 0]) and torch.equal(lp7[:, 3], lp3[:, 2])
+    texts = model.decode_greedy(x)
+    assert texts == model.decode_probs(lp3) and len(texts) == 3 and all(isinstance(t, str) for t in texts)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model(x.cpu())
+    with pytest.raises(RuntimeError, match="inference-only"):
+        model(x, targets=torch.zeros(3, 4, dtype=torch.long))

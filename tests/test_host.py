@@ -125,3 +125,24 @@ def test_rec2_decode_refuses_cpu_tensors():
     from ocr_vi_invoice_b200.model.rec2 import VOCAB, Tokenizer, decode_probs
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         decode_probs(torch.zeros(4, 2, 232), Tokenizer(VOCAB))
+
+
+def test_svtrv2_dropin_state_dict_matches_reference_key_set():
+    """The drop-in SVTRv2 holds exactly the reference's 318 state_dict entries (names, order, shapes: the oracle's table is
+    checked against the real module by tests/golden/make_svtrv2_golden.py) and loads them strictly; unsupported variants
+    are refused instead of running unaccelerated."""
+    import pytest
+    from oracle import svtrv2_oracle as so
+    from ocr_vi_invoice_b200.model.rec2.svtrv2 import SVTRv2
+    model = SVTRv2(variant="base")
+    sd = model.state_dict()
+    shapes = so.param_shapes("base", model.tokenizer.num_classes)
+    assert list(sd.keys()) == list(shapes.keys())
+    assert all(tuple(sd[k].shape) == tuple(shapes[k]) for k in shapes)
+    model.load_state_dict(so.make_state_dict("base", 1), strict=True)
+    assert model.blank_id == 0 and model.tokenizer.num_classes == 232
+    with pytest.raises(NotImplementedError):
+        SVTRv2(variant="small")
+    import torch
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model.eval()(torch.zeros(1, 3, 32, 256))
