@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace b200 {
 
@@ -37,7 +38,19 @@ __device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
 __device__ __forceinline__ uint4 pack8_bf16(const float* f) {
     return make_uint4(pack2_bf16(f[0], f[1]), pack2_bf16(f[2], f[3]), pack2_bf16(f[4], f[5]), pack2_bf16(f[6], f[7]));
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, i.e. 2^-15 of a bf16 ulp at |erf| ~ 1): one MUFU.RCP, one MUFU.EX2
+// and seven FMAs instead of erff's ~30 instructions -- the GELU kernels are issue-bound, not HBM-bound, with erff.
+__device__ __forceinline__ float erf_as(float x) {
+    const float a = fabsf(x);
+    const float t = __frcp_rn(fmaf(0.3275911f, a, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float e = 1.0f - p * t * __expf(-a * a);
+    return copysignf(e, x);
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752440f)); }
 
 // ------------------------------------------------------------------------------------------ stem conv1
 // one thread = one output pixel, all `mid` (<= 64) output channels; weights [mid][27] (ci, ky, kx) + folded scale/shift in smem
@@ -84,20 +97,25 @@ __global__ void __launch_bounds__(128) svtr_stem1_kernel(const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------ LayerNorm
-// one warp per row of D channels (D multiple of 8, <= 1024); fp32 two-pass statistics like torch's layer_norm
+// 16 lanes per row of D channels (two rows per warp), kLnChunks 16-byte chunks per lane (D <= 128 * kLnChunks); fp32
+// two-pass statistics like torch's layer_norm.  D = 128 / 256 / 384 keep every lane busy (one warp per row left half of
+// them idle at D = 128: 1.4 TB/s).
+template <int kLnChunks>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         int64_t rows, int d, int x_ld, int y_ld, float eps) {
-    const int lane = threadIdx.x & 31;
+    const int sub = threadIdx.x & 15;
     const int chunks = d >> 3;
-    for (int64_t r = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5; r < rows;
-         r += (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5) {
-        const __nv_bfloat16* xr = x + r * x_ld;
-        float v[4][8];  // up to 4 chunks per lane: D <= 1024
+    const int64_t stride = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 4;
+    const int64_t rows_pad = (rows + 1) & ~static_cast<int64_t>(1);  // both halves of a warp iterate together (shuffles)
+    for (int64_t r = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 4; r < rows_pad; r += stride) {
+        const bool live = r < rows;
+        const __nv_bfloat16* xr = x + (live ? r : 0) * x_ld;
+        float v[kLnChunks][8];
         float sum = 0.0f;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int c = lane + 32 * k;
+        for (int k = 0; k < kLnChunks; ++k) {
+            const int c = sub + 16 * k;
             if (c < chunks) {
                 unpack8_bf16(__ldg(reinterpret_cast<const uint4*>(xr) + c), v[k]);
 #pragma unroll
@@ -105,24 +123,25 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
             }
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         const float mean = sum / static_cast<float>(d);
         float sq = 0.0f;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (lane + 32 * k < chunks)
+        for (int k = 0; k < kLnChunks; ++k)
+            if (sub + 16 * k < chunks)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float t = v[k][j] - mean;
                     sq = fmaf(t, t, sq);
                 }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        for (int o = 8; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
         const float rstd = rsqrtf(sq / static_cast<float>(d) + eps);
+        if (!live) continue;
         __nv_bfloat16* yr = y + r * y_ld;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int c = lane + 32 * k;
+        for (int k = 0; k < kLnChunks; ++k) {
+            const int c = sub + 16 * k;
             if (c < chunks) {
                 float o8[8];
                 const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c + 1);
@@ -223,6 +242,125 @@ __global__ void __launch_bounds__(128) mhsa_kernel(const __nv_bfloat16* __restri
     for (int c8 = 0; c8 < 4; ++c8) *reinterpret_cast<uint4*>(o + c8 * 8) = pack8_bf16(acc + c8 * 8);
 }
 
+// ------------------------------------------------------------------------------------------ attention on the tensor cores
+// Same contract as mhsa_kernel, for n a multiple of 16.  One block per (sequence, head): K ([n][32], rows padded to 80 bytes)
+// and V^T ([32][n], rows padded by 16 bytes) of the head are staged once in shared memory as bf16 (both paddings make the
+// fragment loads bank-conflict free); each warp owns 16 queries and walks the keys in chunks of 64 with an online softmax
+// (fp32 statistics and accumulators): S = Q K^T by mma.sync.m16n8k16 (bf16, fp32 accumulate), P re-used in registers as
+// the A operand of O += P V.  This is the warp-level tensor-core path; a tcgen05 / TMEM version (128 queries x 256 keys
+// per instruction) is the next step -- head_dim 32 gives the P V product only N = 32 columns to work with.
+__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int kKStride = 40;  // bf16 elements per K row in shared memory (32 + 8 padding)
+
+__global__ void __launch_bounds__(512) mhsa_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int n,
+                                                       int d, float scale_log2e) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __nv_bfloat16* s_k = reinterpret_cast<__nv_bfloat16*>(s_raw);  // [n][kKStride]
+    const int vt_stride = n + 8;                                    // bf16 elements per V^T row
+    __nv_bfloat16* s_vt = s_k + static_cast<size_t>(n) * kKStride;  // [32][vt_stride]
+    const int head = blockIdx.x;
+    const int64_t seq = blockIdx.y;
+    const __nv_bfloat16* base = qkv + seq * n * 3 * d + head * 32;
+    for (int i = threadIdx.x; i < n * 4; i += blockDim.x) {
+        const int key = i >> 2, c8 = i & 3;
+        const __nv_bfloat16* src = base + static_cast<int64_t>(key) * 3 * d + c8 * 8;
+        *reinterpret_cast<uint4*>(s_k + key * kKStride + c8 * 8) = __ldg(reinterpret_cast<const uint4*>(src + d));
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + 2 * d));
+        const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s_vt[(c8 * 8 + j) * vt_stride + key] = ve[j];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int g = lane >> 2, tq = lane & 3;
+    for (int q0 = warp * 16; q0 < n; q0 += nwarps * 16) {
+        // Q fragments: two k-steps of 16 channels
+        uint32_t qa[2][4];
+        const __nv_bfloat16* qr0 = base + static_cast<int64_t>(q0 + g) * 3 * d + tq * 2;
+        const __nv_bfloat16* qr1 = qr0 + static_cast<int64_t>(8) * 3 * d;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            qa[ks][0] = __ldg(reinterpret_cast<const uint32_t*>(qr0 + ks * 16));
+            qa[ks][1] = __ldg(reinterpret_cast<const uint32_t*>(qr1 + ks * 16));
+            qa[ks][2] = __ldg(reinterpret_cast<const uint32_t*>(qr0 + ks * 16 + 8));
+            qa[ks][3] = __ldg(reinterpret_cast<const uint32_t*>(qr1 + ks * 16 + 8));
+        }
+        float o[4][4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) o[t][0] = o[t][1] = o[t][2] = o[t][3] = 0.0f;
+        float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;  // rows g and g + 8
+        for (int k0 = 0; k0 < n; k0 += 64) {
+            const int tiles = min(8, (n - k0) >> 3);  // n % 16 == 0: an even number of 8-key tiles
+            float sc[8][4];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                sc[t][0] = sc[t][1] = sc[t][2] = sc[t][3] = 0.0f;
+                if (t < tiles) {
+                    const __nv_bfloat16* kr = s_k + (k0 + t * 8 + g) * kKStride + tq * 2;
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks)
+                        mma_bf16_16816(sc[t], qa[ks], *reinterpret_cast<const uint32_t*>(kr + ks * 16),
+                                       *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 8));
+                }
+            }
+            float mx0 = m0, mx1 = m1;
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+                if (t < tiles) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) sc[t][e] *= scale_log2e;
+                    mx0 = fmaxf(mx0, fmaxf(sc[t][0], sc[t][1]));
+                    mx1 = fmaxf(mx1, fmaxf(sc[t][2], sc[t][3]));
+                }
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+            const float r0 = exp2f(m0 - mx0), r1 = exp2f(m1 - mx1);
+            m0 = mx0; m1 = mx1;
+            l0 *= r0; l1 *= r1;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { o[t][0] *= r0; o[t][1] *= r0; o[t][2] *= r1; o[t][3] *= r1; }
+            uint32_t pa[4][4];  // P as A fragments: one per 16-key k-step
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
+                if (t < tiles) {
+                    p0 = exp2f(sc[t][0] - m0); p1 = exp2f(sc[t][1] - m0); p2 = exp2f(sc[t][2] - m1); p3 = exp2f(sc[t][3] - m1);
+                }
+                // the probabilities are rounded to bf16 for the tensor core; the row sums use the same rounded values
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(p0, p1), hi = __floats2bfloat162_rn(p2, p3);
+                l0 += __low2float(lo) + __high2float(lo);
+                l1 += __low2float(hi) + __high2float(hi);
+                pa[t >> 1][(t & 1) * 2] = *reinterpret_cast<const uint32_t*>(&lo);
+                pa[t >> 1][(t & 1) * 2 + 1] = *reinterpret_cast<const uint32_t*>(&hi);
+            }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+                if (kk * 2 < tiles) {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {  // 8 output channels per tile
+                        const __nv_bfloat16* vr = s_vt + (t * 8 + g) * vt_stride + k0 + kk * 16 + tq * 2;
+                        mma_bf16_16816(o[t], pa[kk], *reinterpret_cast<const uint32_t*>(vr), *reinterpret_cast<const uint32_t*>(vr + 8));
+                    }
+                }
+        }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+        __nv_bfloat16* or0 = out + (seq * n + q0 + g) * d + head * 32 + tq * 2;
+        __nv_bfloat16* or1 = or0 + static_cast<int64_t>(8) * d;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            *reinterpret_cast<uint32_t*>(or0 + t * 8) = pack2_bf16(o[t][0] * i0, o[t][1] * i0);
+            *reinterpret_cast<uint32_t*>(or1 + t * 8) = pack2_bf16(o[t][2] * i1, o[t][3] * i1);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ FRM selecting-token attention
 // q: fp32 [d] (v_q(v_norm_q(select_token)): parameters only, computed at weight-preparation time); kv: [b][h][w][2 * d] bf16
 // (channel = which * d + head * 32 + e); out: [b][w][d] bf16.  One warp per (b, w, head), lane = e.
@@ -316,8 +454,13 @@ extern "C" int b200_layernorm(const void* x, void* y, const float* gamma, const 
     if (!x || !y || !gamma || !beta) return set_error("b200_layernorm: null pointer");
     if (rows <= 0 || d <= 0 || (d % 8) || d > 1024 || (x_ld % 8) || (y_ld % 8) || x_ld < d || y_ld < d)
         return set_error("b200_layernorm: need D a multiple of 8 (<= 1024) and leading dimensions multiples of 8");
-    layernorm_kernel<<<grid_of(rows, 8), 256, 0, ST(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x),
-                                                              reinterpret_cast<__nv_bfloat16*>(y), gamma, beta, rows, d, x_ld, y_ld, eps);
+    const __nv_bfloat16* xi = reinterpret_cast<const __nv_bfloat16*>(x);
+    __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(y);
+    const int grid = grid_of(rows, 16);
+    if (d <= 128) layernorm_kernel<1><<<grid, 256, 0, ST(stream)>>>(xi, yo, gamma, beta, rows, d, x_ld, y_ld, eps);
+    else if (d <= 256) layernorm_kernel<2><<<grid, 256, 0, ST(stream)>>>(xi, yo, gamma, beta, rows, d, x_ld, y_ld, eps);
+    else if (d <= 384) layernorm_kernel<3><<<grid, 256, 0, ST(stream)>>>(xi, yo, gamma, beta, rows, d, x_ld, y_ld, eps);
+    else layernorm_kernel<8><<<grid, 256, 0, ST(stream)>>>(xi, yo, gamma, beta, rows, d, x_ld, y_ld, eps);
     return check_cuda(cudaGetLastError(), "b200_layernorm launch");
 }
 
@@ -333,6 +476,19 @@ extern "C" int b200_mhsa(const void* qkv, void* out, int n_seq, int n, int d, fl
     if (!qkv || !out) return set_error("b200_mhsa: null pointer");
     if (n_seq <= 0 || n <= 0 || n > 768 || d <= 0 || (d % 32)) return set_error("b200_mhsa: need 1 <= N <= 768 and D a multiple of 32 (head_dim 32)");
     if (n_seq > 65535) return set_error("b200_mhsa: at most 65535 sequences per launch");
+    if ((n % 16) == 0 && !getenv("B200_MHSA_SIMT")) {  // tensor-core path
+        const int smem_mma = (n * kKStride + 32 * (n + 8)) * 2;
+        static int configured_mma = 0;
+        if (smem_mma > 48 * 1024 && smem_mma > configured_mma) {
+            if (check_cuda(cudaFuncSetAttribute(mhsa_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (768 * kKStride + 32 * 776) * 2),
+                           "b200_mhsa smem opt-in")) return 1;
+            configured_mma = (768 * kKStride + 32 * 776) * 2;
+        }
+        const int warps = n / 16 < 16 ? n / 16 : 16;
+        mhsa_mma_kernel<<<dim3(d / 32, n_seq), warps * 32, smem_mma, ST(stream)>>>(
+            reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), n, d, scale * 1.4426950408889634f);
+        return check_cuda(cudaGetLastError(), "b200_mhsa launch");
+    }
     const int smem = n * 64 * static_cast<int>(sizeof(float));
     static int configured = 0;
     if (smem > configured) {
