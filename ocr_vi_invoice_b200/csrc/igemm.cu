@@ -350,12 +350,30 @@ __device__ __forceinline__ void epilogue_head_dot(const IgemmParams& p, uint32_t
     }
 }
 
+// ------------------------------------------------------------------------------------------ GELU epilogue (kEpi == 3)
+// nn.GELU (exact erf form) of the SVTRv2 recogniser (model/rec2/svtrv2.py:33,51,54,114,117) applied to scale * acc + shift,
+// BEFORE the optional residual add (LocalMixing: x + act(bn(conv(.)))).  erf by Abramowitz & Stegun 7.1.26
+// (|error| <= 1.5e-7, far below a bf16 ulp): one MUFU.RCP + one MUFU.EX2 + seven FMAs per element.
+__device__ __forceinline__ float gelu_as(float x) {
+    const float z = x * 0.70710678118654752440f;
+    const float a = fabsf(z);
+    float t;  // MUFU.RCP (1 ulp): __frcp_rn would be a ~25-instruction IEEE sequence
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, a, 1.0f)));
+    float q = fmaf(1.061405429f, t, -1.453152027f);
+    q = fmaf(q, t, 1.421413741f);
+    q = fmaf(q, t, -0.284496736f);
+    q = fmaf(q, t, 0.254829592f);
+    const float e = copysignf(1.0f - q * t * __expf(-a * a), z);
+    return 0.5f * x * (1.0f + e);
+}
+
 // ------------------------------------------------------------------------------------------ kernel
 // kVariant: 0 = TMA-fed conv (one A tile + one weight k-block per stage), 1 = gather producers (DCN / stem fallback),
 // 2 = TMA-fed 3x3 stride-1 conv in share mode.  Separate instantiations: the loops of one variant must not cost the
 // others registers or instructions (the MMA warp and the epilogue warps are latency-critical).
 // kEpi: 0 = common epilogue; 1 = adds a nearest-upsampled half-resolution residual (FPN top-down path, keeps eight more
-// vector registers alive); 2 = DB-head tail folded in (B200_EPI_HEAD_DOT).  Own instantiations: the common epilogue must
+// vector registers alive); 2 = DB-head tail folded in (B200_EPI_HEAD_DOT); 3 = GELU before the residual add
+// (B200_EPI_GELU, the recogniser's Linear / conv + GELU layers).  Own instantiations: the common epilogue must
 // not pay registers (spills) for the rare ones.
 template <int kVariant, int kEpi = 0>
 __global__ void __launch_bounds__((base_warps(kVariant == 1) + (kVariant == 1 ? kGatherWarps : 0)) * 32, 1)
@@ -785,6 +803,10 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                             f[5] = fmaf(__uint_as_float(v[j * 8 + 5]), sc1.y, sh1.y);
                             f[6] = fmaf(__uint_as_float(v[j * 8 + 6]), sc1.z, sh1.z);
                             f[7] = fmaf(__uint_as_float(v[j * 8 + 7]), sc1.w, sh1.w);
+                            if constexpr (kEpi == 3) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) f[i] = gelu_as(f[i]);
+                            }
                             if (p.res_tma) {
                                 uint4 u;
                                 if constexpr (up2) u = rup[piece];
@@ -1057,6 +1079,10 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
         (!(d->flags & B200_EPI_SHUFFLE2) || d->shuf_c != 64 || d->out_c != 256 || d->mode != B200_IGEMM_CONV || !d->offsets ||
          (d->flags & (B200_EPI_RES | B200_EPI_RES_UP2 | B200_EPI_OUT_F32))))
         return set_error("igemm: HEAD_DOT is for the 64 -> 4x64 transposed conv with the 257-float tail weights in `offsets`");
+    if ((d->flags & B200_EPI_GELU) &&
+        (d->mode != B200_IGEMM_CONV || (d->out_c % 64) != 0 ||
+         (d->flags & (B200_EPI_RELU | B200_EPI_RES_UP2 | B200_EPI_OUT_F32 | B200_EPI_SHUFFLE2 | B200_EPI_DCN_COORDS | B200_EPI_HEAD_DOT))))
+        return set_error("igemm: GELU is for plain bf16 conv outputs with out_c a multiple of 64 (optionally + RES)");
     if ((d->flags & B200_EPI_DCN_COORDS) && (d->out_c != 32 || d->ksize != 3 || d->mode != B200_IGEMM_CONV))
         return set_error("igemm: DCN_COORDS is for the 3x3 offset conv with out_c == 32");
     int block_n = d->block_n;
@@ -1223,7 +1249,7 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
         // chunk and group.  Enough groups to keep up with the mainloop, one buffer per group plus one draining (plus
         // two more of residual prefetch), the rest to the pipeline stages.
         const int chunks = (block_n < d->out_c ? block_n : d->out_c) / 64;
-        const int main_clk = p.k_blocks * 2 * block_n, epi_clk = chunks * 1600;
+        const int main_clk = p.k_blocks * 2 * block_n, epi_clk = chunks * ((d->flags & B200_EPI_GELU) ? 2600 : 1600);
         ga = (epi_clk + main_clk - 1) / main_clk;
         if (ga > G) ga = G;
         if (ga < 1) ga = 1;
@@ -1334,6 +1360,10 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
         e = cudaFuncSetAttribute(igemm_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(igemm_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(igemm_kernel<0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(igemm_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) {
         delete op;
         return set_error("igemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -1347,6 +1377,10 @@ extern "C" int b200_igemm_launch(const b200_igemm* op, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (op->gather)
         igemm_kernel<1><<<op->grid, op->threads, op->smem_bytes, st>>>(op->tm, op->p);
+    else if ((op->p.flags & B200_EPI_GELU) && op->p.a_kb > 1)
+        igemm_kernel<2, 3><<<op->grid, op->threads, op->smem_bytes, st>>>(op->tm, op->p);
+    else if (op->p.flags & B200_EPI_GELU)
+        igemm_kernel<0, 3><<<op->grid, op->threads, op->smem_bytes, st>>>(op->tm, op->p);
     else if (op->p.a_kb > 1)
         igemm_kernel<2><<<op->grid, op->threads, op->smem_bytes, st>>>(op->tm, op->p);
     else if (op->p.flags & B200_EPI_HEAD_DOT)

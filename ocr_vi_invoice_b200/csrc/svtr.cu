@@ -42,7 +42,8 @@ __device__ __forceinline__ uint4 pack8_bf16(const float* f) {
 // and seven FMAs instead of erff's ~30 instructions -- the GELU kernels are issue-bound, not HBM-bound, with erff.
 __device__ __forceinline__ float erf_as(float x) {
     const float a = fabsf(x);
-    const float t = __frcp_rn(fmaf(0.3275911f, a, 1.0f));
+    float t;  // MUFU.RCP (1 ulp): __frcp_rn would be a ~25-instruction IEEE sequence
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, a, 1.0f)));
     float p = fmaf(1.061405429f, t, -1.453152027f);
     p = fmaf(p, t, 1.421413741f);
     p = fmaf(p, t, -0.284496736f);
@@ -257,7 +258,7 @@ __device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint
 
 constexpr int kKStride = 40;  // bf16 elements per K row in shared memory (32 + 8 padding)
 
-__global__ void __launch_bounds__(512) mhsa_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int n,
+__global__ void __launch_bounds__(256, 3) mhsa_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int n,
                                                        int d, float scale_log2e) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     __nv_bfloat16* s_k = reinterpret_cast<__nv_bfloat16*>(s_raw);  // [n][kKStride]
@@ -363,32 +364,54 @@ __global__ void __launch_bounds__(512) mhsa_mma_kernel(const __nv_bfloat16* __re
 
 // ------------------------------------------------------------------------------------------ FRM selecting-token attention
 // q: fp32 [d] (v_q(v_norm_q(select_token)): parameters only, computed at weight-preparation time); kv: [b][h][w][2 * d] bf16
-// (channel = which * d + head * 32 + e); out: [b][w][d] bf16.  One warp per (b, w, head), lane = e.
-__global__ void __launch_bounds__(256) frm_select_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ kv,
+// (channel = which * d + head * 32 + e); out: [b][w][d] bf16.
+__global__ void __launch_bounds__(128) frm_select_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ kv,
                                                          __nv_bfloat16* __restrict__ out, int batch, int h, int w, int d, float scale) {
-    const int lane = threadIdx.x & 31;
+    // one thread per (b, x, head): adjacent threads take adjacent heads, so a warp reads contiguous 64-byte K (and V) rows
     const int heads = d >> 5;
     const int64_t total = static_cast<int64_t>(batch) * w * heads;
-    for (int64_t i = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5; i < total;
-         i += (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5) {
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int head = static_cast<int>(i % heads);
         const int x = static_cast<int>((i / heads) % w);
         const int n = static_cast<int>(i / (static_cast<int64_t>(heads) * w));
-        const float qe = __ldg(q + head * 32 + lane) * scale;
-        float m = -INFINITY, l = 0.0f, acc = 0.0f;
-        for (int y = 0; y < h; ++y) {
-            const __nv_bfloat16* t = kv + ((static_cast<int64_t>(n) * h + y) * w + x) * 2 * d + head * 32 + lane;
-            float s = qe * __bfloat162float(t[0]);
+        float qe[32];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            const float v = __bfloat162float(t[d]);
+        for (int c = 0; c < 8; ++c) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(q + head * 32) + c);
+            qe[4 * c] = t.x * scale; qe[4 * c + 1] = t.y * scale; qe[4 * c + 2] = t.z * scale; qe[4 * c + 3] = t.w * scale;
+        }
+        float m = -INFINITY, l = 0.0f, acc[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) acc[e] = 0.0f;
+        for (int y = 0; y < h; ++y) {
+            const __nv_bfloat16* t = kv + ((static_cast<int64_t>(n) * h + y) * w + x) * 2 * d + head * 32;
+            float s = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float f[8];
+                unpack8_bf16(__ldg(reinterpret_cast<const uint4*>(t) + c), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s = fmaf(qe[c * 8 + j], f[j], s);
+            }
             const float mn = fmaxf(m, s);
-            const float r = __expf(m - mn), p = __expf(s - mn);
-            l = l * r + p;
-            acc = acc * r + p * v;
+            const float r = __expf(m - mn), pr = __expf(s - mn);
+            l = l * r + pr;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float f[8];
+                unpack8_bf16(__ldg(reinterpret_cast<const uint4*>(t + d) + c), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[c * 8 + j] = fmaf(pr, f[j], acc[c * 8 + j] * r);
+            }
             m = mn;
         }
-        out[(static_cast<int64_t>(n) * w + x) * d + head * 32 + lane] = __float2bfloat16(acc / l);
+        const float inv = 1.0f / l;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) acc[e] *= inv;
+        __nv_bfloat16* o = out + (static_cast<int64_t>(n) * w + x) * d + head * 32;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) *(reinterpret_cast<uint4*>(o) + c) = pack8_bf16(acc + c * 8);
     }
 }
 
@@ -484,7 +507,7 @@ extern "C" int b200_mhsa(const void* qkv, void* out, int n_seq, int n, int d, fl
                            "b200_mhsa smem opt-in")) return 1;
             configured_mma = (768 * kKStride + 32 * 776) * 2;
         }
-        const int warps = n / 16 < 16 ? n / 16 : 16;
+        const int warps = n / 16 < 8 ? n / 16 : 8;  // 8 warps x 84 registers: three blocks per SM hide the mma / exp latencies
         mhsa_mma_kernel<<<dim3(d / 32, n_seq), warps * 32, smem_mma, ST(stream)>>>(
             reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), n, d, scale * 1.4426950408889634f);
         return check_cuda(cudaGetLastError(), "b200_mhsa launch");
@@ -504,7 +527,7 @@ extern "C" int b200_mhsa(const void* qkv, void* out, int n_seq, int n, int d, fl
 extern "C" int b200_frm_select(const float* q, const void* kv, void* out, int batch, int h, int w, int d, float scale, void* stream) {
     if (!q || !kv || !out) return set_error("b200_frm_select: null pointer");
     if (batch <= 0 || h <= 0 || w <= 0 || d <= 0 || (d % 32)) return set_error("b200_frm_select: bad shape");
-    frm_select_kernel<<<grid_of(static_cast<int64_t>(batch) * w * (d / 32), 8), 256, 0, ST(stream)>>>(
+    frm_select_kernel<<<grid_of(static_cast<int64_t>(batch) * w * (d / 32), 128), 128, 0, ST(stream)>>>(
         q, reinterpret_cast<const __nv_bfloat16*>(kv), reinterpret_cast<__nv_bfloat16*>(out), batch, h, w, d, scale);
     return check_cuda(cudaGetLastError(), "b200_frm_select launch");
 }

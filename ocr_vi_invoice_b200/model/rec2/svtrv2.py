@@ -8,7 +8,7 @@ held but never run), `forward(x) -> log_probs (T, B, num_classes)`, `decode_prob
   * every nn.Linear / nn.Conv2d except the 3-channel stem conv is one tcgen05 implicit-GEMM launch of igemm.cu (Linear =
     1x1 conv over the token image; LocalMixing's grouped 3x3 convs = a 3x3 conv with block-diagonal weights, BatchNorm and
     bias folded into the epilogue; residual adds in the epilogue);
-  * LayerNorm, GELU(+residual), multi-head attention (head_dim 32), the FRM selecting-token attention, PatchMerging's
+  * GELU runs in the GEMM epilogue (B200_EPI_GELU, before the residual add); LayerNorm, multi-head attention (head_dim 32), the FRM selecting-token attention, PatchMerging's
     row stride and log_softmax are the kernels of svtr.cu; the greedy decode is ctc.cu.
 
 No CPU fallback, no eager torch path: CPU tensors, training mode or `targets` raise.
@@ -239,32 +239,30 @@ class _Plan:
         s1 = bf(b, H // 2, Wd // 2, mid)
         add("stem.conv1", lambda: ops.svtr_stem1(self.x_in, *W.stem1, s1))
         x = bf(b, h, w, dims[0])
-        gemm("stem.conv2", "stem.conv2", s1, x, geom=(b, H // 2, Wd // 2), in_c=mid, out_c=dims[0], ksize=3, stride=2)
-        add("stem.gelu2", lambda x=x: ops.gelu(x))
+        gemm("stem.conv2", "stem.conv2", s1, x, geom=(b, H // 2, Wd // 2), in_c=mid, out_c=dims[0], ksize=3, stride=2,
+             flags=ops.EPI_GELU)
         self.taps = {"stem": (x, len(self.steps))}  # (buffer, number of steps after which it holds the tap)
         for si in range(3):
             d = dims[si]
             rows = b * h * w
             other = bf(b, h, w, d)
-            nbuf, cbuf, cbuf2 = bf(b, h, w, d), bf(b, h, w, d), bf(b, h, w, d)
+            nbuf, cbuf = bf(b, h, w, d), bf(b, h, w, d)
             hid = bf(b, h, w, 4 * d)
             qkv = bf(b, h, w, 3 * d) if cfg["num_local"][si] < cfg["num_blocks"][si] else None
             for bi in range(cfg["num_blocks"][si]):
                 p = f"stages.{si}.blocks.{bi}"
                 lnorm(p + ".norm1", p + ".norm1", x, nbuf, rows, d)
                 if bi < cfg["num_local"][si]:
-                    gemm(p + ".conv1", p + ".conv1", nbuf, cbuf, geom=(b, h, w), in_c=d, out_c=d, ksize=3)
-                    add(p + ".gelu1", lambda c=cbuf: ops.gelu(c))
-                    gemm(p + ".conv2", p + ".conv2", cbuf, cbuf2, geom=(b, h, w), in_c=d, out_c=d, ksize=3)
-                    add(p + ".gelu2+res", lambda c=cbuf2, r=x, y=other: ops.gelu(c, y, r))
+                    gemm(p + ".conv1", p + ".conv1", nbuf, cbuf, geom=(b, h, w), in_c=d, out_c=d, ksize=3, flags=ops.EPI_GELU)
+                    gemm(p + ".conv2", p + ".conv2", cbuf, other, geom=(b, h, w), in_c=d, out_c=d, ksize=3,
+                         flags=ops.EPI_GELU | ops.EPI_RES, residual=x)  # x + gelu(bn2(conv2(.))): GELU before the add
                 else:
                     gemm(p + ".qkv", p + ".qkv", nbuf, qkv, rows=rows, in_c=d, out_c=3 * d)
                     add(p + ".attn", lambda q=qkv, o=cbuf, n=h * w, d=d: ops.mhsa(q, o, b, n, d))
                     gemm(p + ".proj", p + ".proj", cbuf, other, rows=rows, in_c=d, out_c=d, flags=ops.EPI_RES, residual=x)
                 x, other = other, x
                 lnorm(p + ".norm2", p + ".norm2", x, nbuf, rows, d)
-                gemm(p + ".fc1", p + ".fc1", nbuf, hid, rows=rows, in_c=d, out_c=4 * d)
-                add(p + ".gelu", lambda t=hid: ops.gelu(t))
+                gemm(p + ".fc1", p + ".fc1", nbuf, hid, rows=rows, in_c=d, out_c=4 * d, flags=ops.EPI_GELU)
                 gemm(p + ".fc2", p + ".fc2", hid, other, rows=rows, in_c=4 * d, out_c=d, flags=ops.EPI_RES, residual=x)
                 x, other = other, x
             self.taps[f"stage{si}"] = (x, len(self.steps))
@@ -287,8 +285,7 @@ class _Plan:
         add("frm.h_attn", lambda: ops.mhsa(qkv, att, b * h, w, d))
         gemm("frm.h_proj", "frm.h_proj", att, r2, rows=rows, in_c=d, out_c=d, flags=ops.EPI_RES, residual=xn)
         lnorm("frm.h_norm2", "frm.h_norm2", r2, n1, rows, d)
-        gemm("frm.h_fc1", "frm.h_fc1", n1, hid, rows=rows, in_c=d, out_c=4 * d)
-        add("frm.h_gelu", lambda: ops.gelu(hid))
+        gemm("frm.h_fc1", "frm.h_fc1", n1, hid, rows=rows, in_c=d, out_c=4 * d, flags=ops.EPI_GELU)
         gemm("frm.h_fc2", "frm.h_fc2", hid, r3, rows=rows, in_c=4 * d, out_c=d, flags=ops.EPI_RES, residual=r2)
         self.taps["frm_h"] = (r3, len(self.steps))
         # ---- FRM, vertical: the selecting token attends over the h rows of each column
@@ -301,8 +298,7 @@ class _Plan:
         add("frm.v_attn", lambda: ops.frm_select(W.frm_q, kv, sel, b, h, w, d))
         gemm("frm.v_proj", "frm.v_proj", sel, t1, rows=trows, in_c=d, out_c=d)
         lnorm("frm.v_norm2", "frm.v_norm2", t1, t1n, trows, d)
-        gemm("frm.v_fc1", "frm.v_fc1", t1n, thid, rows=trows, in_c=d, out_c=4 * d)
-        add("frm.v_gelu", lambda: ops.gelu(thid))
+        gemm("frm.v_fc1", "frm.v_fc1", t1n, thid, rows=trows, in_c=d, out_c=4 * d, flags=ops.EPI_GELU)
         gemm("frm.v_fc2", "frm.v_fc2", thid, t2, rows=trows, in_c=4 * d, out_c=d, flags=ops.EPI_RES, residual=t1)
         self.taps["frm"] = (t2, len(self.steps))
         nc = W.num_classes

@@ -11,13 +11,13 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (EPI_DCN_COORDS, EPI_HEAD_DOT, EPI_OUT_F32, EPI_RELU, EPI_RES, EPI_RES_UP2, EPI_SHUFFLE2, IGEMM_CONV,
+from ._lib import (EPI_DCN_COORDS, EPI_GELU, EPI_HEAD_DOT, EPI_OUT_F32, EPI_RELU, EPI_RES, EPI_RES_UP2, EPI_SHUFFLE2, IGEMM_CONV,
                    IGEMM_DCN, IGEMM_STEM)
 
 __all__ = [
     "Igemm", "pack_conv_weight", "pack_stem_weight", "pack_convT_weight", "fold_bn", "pad_vec",
     "stem_pack", "stem_pack_u8", "resize_u8_linear", "maxpool3x3s2", "asf_fwd", "asf_combine", "db_head_fwd", "postproc", "rec_prep_boxes", "rec_prep_rects", "ctc_greedy", "svtr_stem1", "layernorm", "gelu", "mhsa", "frm_select", "decimate_rows", "log_softmax_tbc", "ref_conv2d", "ref_dcn2d",
-    "EPI_RELU", "EPI_RES", "EPI_RES_UP2", "EPI_OUT_F32", "EPI_SHUFFLE2", "EPI_DCN_COORDS", "EPI_HEAD_DOT", "db_maps", "dcn_coords", "IGEMM_CONV", "IGEMM_STEM", "IGEMM_DCN",
+    "EPI_RELU", "EPI_RES", "EPI_RES_UP2", "EPI_OUT_F32", "EPI_SHUFFLE2", "EPI_DCN_COORDS", "EPI_HEAD_DOT", "EPI_GELU", "db_maps", "dcn_coords", "IGEMM_CONV", "IGEMM_STEM", "IGEMM_DCN",
 ]
 
 

@@ -120,6 +120,41 @@ def test_linear_as_token_image_gemm():
         assert _rel(y, ref) < (1e-4 if f32out else 4e-3), (din, dout)
 
 
+def test_gelu_epilogue_conv_and_linear():
+    """B200_EPI_GELU: GELU(scale * acc + shift) [+ residual, added AFTER the GELU] in the tcgen05 kernel's epilogue, for a
+    Linear (TMA-fed variant), a 3x3 stride-1 conv with N = 128 (share variant) and a stride-2 conv."""
+    from ocr_vi_invoice_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    # Linear 128 -> 512 + GELU
+    rows, din, dout = 4 * 64, 128, 512
+    x = _bf(torch.randn(rows, din, generator=g)).to(DEV)
+    wt, bias = torch.randn(dout, din, generator=g) * din ** -0.5, torch.randn(dout, generator=g)
+    w = ops.pack_conv_weight(wt.reshape(dout, din, 1, 1).to(DEV))
+    y = torch.empty(rows, dout, dtype=torch.bfloat16, device=DEV)
+    ops.Igemm(ops.IGEMM_CONV, x, w, torch.ones(w.shape[0], device=DEV), ops.pad_vec(bias.to(DEV), w.shape[0]), y, batch=1,
+              in_h=rows // 64, in_w=64, in_c=din, out_c=dout, ksize=1, stride=1, flags=ops.EPI_GELU)()
+    ref = F.gelu(x.float().cpu() @ _bf(wt).float().t() + bias)
+    assert _rel(y.cpu(), ref) < 4e-3
+    # 3x3 convs (+ residual after the GELU)
+    for cin, cout, stride, hh, ww, res in ((128, 128, 1, 8, 64, True), (64, 128, 2, 16, 128, False), (256, 256, 1, 4, 64, True)):
+        b = 2
+        xi = _bf(torch.randn(b, hh, ww, cin, generator=g)).to(DEV)
+        wt = torch.randn(cout, cin, 3, 3, generator=g) * (cin * 9) ** -0.5
+        sc, sh = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.3
+        w = ops.pack_conv_weight(wt.to(DEV))
+        oh, ow = hh // stride, ww // stride
+        r = _bf(torch.randn(b, oh, ow, cout, generator=g)).to(DEV)
+        y = torch.empty(b, oh, ow, cout, dtype=torch.bfloat16, device=DEV)
+        ops.Igemm(ops.IGEMM_CONV, xi, w, ops.pad_vec(sc.to(DEV), w.shape[0], 1.0), ops.pad_vec(sh.to(DEV), w.shape[0]), y, batch=b,
+                  in_h=hh, in_w=ww, in_c=cin, out_c=cout, ksize=3, stride=stride, flags=ops.EPI_GELU | (ops.EPI_RES if res else 0),
+                  residual=r if res else None, res_ld=cout if res else 0)()
+        ref = F.conv2d(xi.float().cpu().permute(0, 3, 1, 2), _bf(wt).float(), None, stride, 1)
+        ref = F.gelu(ref * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)).permute(0, 2, 3, 1)
+        if res:
+            ref = ref + r.float().cpu()
+        assert _rel(y.cpu(), ref) < 4e-3, (cin, cout, stride)
+
+
 def _golden_model():
     from oracle import svtrv2_oracle as so
     from ocr_vi_invoice_b200.model.rec2.svtrv2 import SVTRv2
