@@ -192,6 +192,28 @@ def next_row_kernels(dev, peak_gbs):
                          "classes": C, "ms": round(ms, 4), "bound": "hbm", "algorithmic_bytes": by,
                          "achieved": round(by / ms / 1e6, 1), "peak": peak_gbs, "unit": "GB/s",
                          "frac": round(by / ms / 1e6 / peak_gbs, 3)}
+    # the recogniser itself on 1024 crops (BASELINE configs[4] feeds it the crops of 4096 pages): SVTRv2-base forward +
+    # greedy decode, random-init weights of the reference architecture, device-timed
+    from ocr_vi_invoice_b200.model.rec2.svtrv2 import SVTRv2
+    rec = SVTRv2(variant="base").to(dev).eval()
+    xb = torch.randn(1024, 3, 32, 256, device=dev)
+    for _ in range(3):
+        rec._decoder.run_device(rec(xb))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        rec._decoder.run_device(rec(xb))
+    e1.record()
+    e1.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    plan = rec._plan(xb)
+    out["svtrv2_base"] = {"what": "SVTRv2-base forward + greedy CTC decode, 1024 crops of 32 x 256 per step, bf16 tcgen05 GEMMs "
+                                  "(GELU / bias / BN / residual in the epilogue) + svtr.cu kernels",
+                          "value": round(1024 / ms * 1e3, 1), "unit": "crops/s", "ms_per_step": round(ms, 3),
+                          "launches_per_step": plan.n_launches + 1,
+                          "dense_equivalent_tflops": round(plan.flops / (ms * 1e-3) / 1e12, 1)}
+    del rec, xb, plan
+    torch.cuda.empty_cache()
     return out
 
 

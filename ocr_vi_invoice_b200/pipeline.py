@@ -15,6 +15,7 @@ import torch
 
 from .model.det.dbnet import DBNetPP
 from .postprocess import DBPostProcessor
+from .preprocess import det_size as _det_scales
 from .preprocess import resize_image_for_det
 from .recprep import RecognitionCropper
 
@@ -129,3 +130,44 @@ class Detector:
             if pending is not None:
                 recs, _ = self.post.fetch_wait(pending)
                 yield [self.post.records_to_boxes(r) for r in recs]
+
+
+class OCRPipeline:
+    """Steps 2-3 of the reference's page loop (src/pipeline/pipeline2.py:307-352) on one B200: detection, GPU
+    post-processing, box rescale, crop, recognition pre-processing, SVTRv2 and the greedy CTC decode.  Between the page
+    upload and the decoded token ids nothing returns to the host except the crop count (to size the recogniser batch)
+    and, for the caller's box list, the 48-byte box records.
+
+        ocr = OCRPipeline(det_model, post_processor, rec_model, det_size=640)
+        boxes, texts = ocr(page)      # page: ORIGINAL uint8 HWC CUDA image; boxes: int32 (4, 2) arrays in page coordinates
+    """
+
+    def __init__(self, det_model: DBNetPP, post: DBPostProcessor, rec_model, device=None, det_size: int = 640,
+                 rec_size: Tuple[int, int] = (32, 256), rec_bucket: int = 32, capacity: int = 1024):
+        self.detector = Detector(det_model, post, device, use_cuda_graph=False)
+        self.rec_model = rec_model
+        self.det_size = det_size
+        self.rec_bucket = int(rec_bucket)
+        self.cropper = RecognitionCropper(rec_size, capacity=capacity, device=self.detector.device)
+
+    def __call__(self, page: torch.Tensor):
+        det = self.detector
+        crops, dbuf = det.detect_and_crop(page, self.det_size, self.cropper)
+        det.post.fetch_async(dbuf)
+        out, rects = self.cropper.fetch(crops, on_degenerate="zeros")   # the one synchronisation: how many crops
+        recs, _ = det.post.fetch_wait(dbuf)
+        n = len(rects)
+        # pipeline2.py:323-328: boxes back in page coordinates (truncating division), int32
+        (_, _), (scale_h, scale_w) = _det_scales(page.shape[0], page.shape[1], self.det_size)
+        boxes = []
+        for box in det.post.records_to_boxes(recs[0])[0]:
+            box[:, 0] = box[:, 0] / scale_w
+            box[:, 1] = box[:, 1] / scale_h
+            boxes.append(box.astype(np.int32))
+        if n == 0:
+            return boxes, []
+        # the recogniser's plan is keyed by batch size: round the batch up to a bucket (slots past n hold stale crops
+        # of the capacity buffer; their strings are dropped)
+        nb = min(-(-n // self.rec_bucket) * self.rec_bucket, self.cropper.capacity)
+        texts = self.rec_model.decode_probs(self.rec_model(crops["out"][:nb]))[:n]
+        return boxes, texts

@@ -203,3 +203,43 @@ def test_model_batches_and_decode():
         model(x.cpu())
     with pytest.raises(RuntimeError, match="inference-only"):
         model(x, targets=torch.zeros(3, 4, dtype=torch.long))
+
+
+def test_ocr_pipeline_page_to_text():
+    """OCRPipeline (detect -> crop -> recognise -> decode on the device) == the same stages called one by one, and the
+    rescaled boxes == the reference's in-place rescale (pipeline2.py:323-328) of the detector's boxes."""
+    from oracle import recprep_oracle as ro
+    from oracle import svtrv2_oracle as so
+    from oracle.weights import make_state_dict
+    from ocr_vi_invoice_b200.model.det.dbnet import DBNetPP
+    from ocr_vi_invoice_b200.model.rec2.svtrv2 import SVTRv2
+    from ocr_vi_invoice_b200.pipeline import OCRPipeline
+    from ocr_vi_invoice_b200.postprocess import DBPostProcessor
+    from ocr_vi_invoice_b200.preprocess import det_size, resize_image_for_det
+    from ocr_vi_invoice_b200.synth import synthetic_batch_u8
+    dev = torch.device(DEV, 0)
+    det = DBNetPP(pretrained=False)
+    det.load_state_dict(make_state_dict(seed=3, offset_px=0.5), strict=True)
+    det = det.to(dev).eval()
+    rec = SVTRv2(variant="base")
+    rec.load_state_dict(so.make_state_dict("base", 5), strict=True)
+    rec = rec.to(dev).eval()
+    post = DBPostProcessor(thresh=0.3, box_thresh=0.5, unclip_ratio=1.6, device=dev)
+    ocr = OCRPipeline(det, post, rec, dev, det_size=256)
+    page_np = np.ascontiguousarray(synthetic_batch_u8(1, 300, 420, seed=4)[0])
+    page = torch.from_numpy(page_np).to(dev)
+    boxes, texts = ocr(page)
+    assert len(boxes) == len(texts) and all(b.dtype == np.int32 and b.shape == (4, 2) for b in boxes)
+    # stage by stage
+    resized, (sh, sw) = resize_image_for_det(page, 256)
+    det_boxes, _ = post(det(resized[None])["binary"][0])
+    assert len(det_boxes) == len(boxes)
+    for got, b in zip(boxes, det_boxes):
+        assert np.array_equal(got, ro.rescale_box(b, sh, sw))
+    if boxes:
+        want, _ = ro.crops_for_recognition(page_np, det_boxes, sh, sw)
+        n = len(boxes)
+        x = torch.zeros(-(-n // 32) * 32, 3, 32, 256, device=dev)
+        x[:n] = torch.from_numpy(want).to(dev)
+        lp = rec(x)
+        assert rec.decode_probs(lp)[:n] == texts or rec.decode_probs(rec(ocr.cropper._buf["out"][:x.shape[0]]))[:n] == texts
