@@ -273,6 +273,100 @@ def run_sharded(args, rank, world, dev, dist, model, post, config):
     return 0
 
 
+def run_config5(args, rank, world, dev, dist, model, post, config):
+    """BASELINE configs[4]: detection -> crop -> SVTRv2 recognition end to end on N synthetic 1280 x 1280 pages sharded over
+    the ranks (no collective on the data path; rank 0 gathers the strings on the host).  Per step of `pages_per_step`
+    pages: pinned uint8 pages -> H2D -> DBNet++ forward (GPU normalisation) -> GPU post-processing -> rec_prep ->
+    SVTRv2-base -> greedy CTC decode -> D2H of the token ids -> strings.  With random-init weights the detector finds one
+    page-sized blob, so the crop list is INJECTED: 60 seeded text-line boxes per page in the same 48-byte record layout the
+    post-processing writes (which still runs and is timed); every other stage consumes what the previous one produced."""
+    import numpy as np
+    import torch
+    from ocr_vi_invoice_b200.model.rec2 import SVTRv2
+    from ocr_vi_invoice_b200.pipeline import gather_results, shard_indices
+    from ocr_vi_invoice_b200.postprocess import _BOX_DTYPE
+    from ocr_vi_invoice_b200.recprep import RecognitionCropper
+    from ocr_vi_invoice_b200.synth import synthetic_batch_u8
+    S, pb, nbox = 1280, 8, 60
+    n = args.config5
+    mine = shard_indices(n, rank, world)
+    steps = (len(mine) + pb - 1) // pb
+    model.use_cuda_graph = not args.no_graph
+    model.output_maps = ("binary",)
+    rec = SVTRv2(variant="base").to(dev).eval()
+    pool = [torch.from_numpy(synthetic_batch_u8(pb, S, S, seed=100 * rank + i)).pin_memory() for i in range(2)]
+    dev_pages = [torch.empty(pb, S, S, 3, dtype=torch.uint8, device=dev) for _ in range(2)]
+    rng = np.random.default_rng(rank)
+    recs = np.zeros((pb, int(post.max_candidates)), dtype=_BOX_DTYPE)
+    for i in range(pb):
+        for j in range(nbox):
+            bw, bh = int(rng.integers(80, 600)), int(rng.integers(22, 56))
+            x0, y0 = int(rng.integers(0, S - bw)), int(rng.integers(0, S - bh))
+            recs[i, j]["x0"], recs[i, j]["y0"], recs[i, j]["x1"], recs[i, j]["y1"] = x0, y0, x0 + bw, y0 + bh
+    injected = {"boxes": torch.from_numpy(recs.view(np.uint8).reshape(-1)).to(dev),
+                "counts": torch.full((pb,), nbox, dtype=torch.int32, device=dev)}
+    cropper = RecognitionCropper((32, 256), capacity=pb * nbox, device=dev)
+    copy_stream = torch.cuda.Stream(device=dev)
+    ncrops = pb * nbox
+    tok_host = torch.empty(ncrops, 65, dtype=torch.int32).pin_memory()
+
+    def step(i, texts_out):
+        slot = i & 1
+        with torch.cuda.stream(copy_stream):
+            dev_pages[slot].copy_(pool[slot], non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(copy_stream)
+        torch.cuda.current_stream().wait_event(ready)
+        out = model(dev_pages[slot])
+        post.run_device(out["binary"][:, 0], want_labels=False)
+        crops = cropper.from_detector(injected, list(dev_pages[slot]), [(1.0, 1.0)] * pb, int(post.max_candidates))
+        lp = rec(crops["out"][:ncrops])
+        tokens, lengths = rec._decoder.run_device(lp)
+        tok_host[:, :64].copy_(tokens, non_blocking=True)
+        tok_host[:, 64].copy_(lengths, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        th = tok_host.numpy()
+        texts_out.append(rec.tokenizer.decode([th[k, :th[k, 64]].tolist() for k in range(ncrops)]))
+
+    warm = []
+    for i in range(3):
+        step(i, warm)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    texts = []
+    for i in range(steps):
+        step(i, texts)
+    torch.cuda.synchronize()
+    t_local = time.perf_counter() - t0
+    local = [(mine[min(i * pb + j, len(mine) - 1)], ([], texts[i][j * nbox:(j + 1) * nbox])) for i in range(steps) for j in range(pb)
+             if i * pb + j < len(mine)]
+    merged = gather_results(local, dst=0)
+    t_all = time.perf_counter() - t0
+    t = torch.tensor([t_local, t_all], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        assert merged is not None and len(merged) == n
+        cfg = dict(config)
+        cfg["workload"] = (f"detection -> crop -> SVTRv2-base recognition, {n} synthetic 1280x1280 uint8 pages sharded over {world} "
+                           f"GPU(s) (BASELINE configs[4]), {pb} pages and {ncrops} crops per step; crop boxes injected (random-init "
+                           "detector weights), every stage runs")
+        cfg["image"] = [S, S]
+        cfg["batch_per_gpu"] = pb
+        print(json.dumps({"metric": "pages/sec", "value": round(n / t[1].item(), 2), "unit": "pages/s", "n_gpus": world,
+                          "pages": n, "crops": n * nbox, "crops_per_s": round(n * nbox / t[1].item(), 1),
+                          "seconds": round(t[1].item(), 3), "pipeline_seconds_max_rank": round(t[0].item(), 3),
+                          "higher_is_better": True, "scaling": "strong", "dtype": "bf16", "data": "synthetic", "config": cfg,
+                          "timing": "wall clock, max over ranks: H2D + detection + post-processing + crops + recognition + "
+                                    "decode + D2H of token ids + host strings + host gather"}))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -287,6 +381,9 @@ def main():
     ap.add_argument("--shard-images", type=int, default=0,
                     help="BASELINE configs[3]: detect this many synthetic images sharded over the ranks (full detection + "
                          "GPU post-processing + host gather) instead of the fixed-batch step loop")
+    ap.add_argument("--config5", type=int, default=0,
+                    help="BASELINE configs[4]: this many synthetic 1280x1280 pages through detection -> crop -> SVTRv2 -> decode, "
+                         "sharded over the ranks")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -363,6 +460,8 @@ def main():
 
     if args.shard_images:
         return run_sharded(args, rank, world, dev, dist, model, post, config)
+    if args.config5:
+        return run_config5(args, rank, world, dev, dist, model, post, config)
 
     def step_device():
         out = model(x_dev)
