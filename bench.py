@@ -196,6 +196,7 @@ def next_row_kernels(dev, peak_gbs):
     # greedy decode, random-init weights of the reference architecture, device-timed
     from ocr_vi_invoice_b200.model.rec2.svtrv2 import SVTRv2
     rec = SVTRv2(variant="base").to(dev).eval()
+    rec.use_cuda_graph = True
     xb = torch.randn(1024, 3, 32, 256, device=dev)
     for _ in range(3):
         rec._decoder.run_device(rec(xb))
@@ -294,6 +295,7 @@ def run_config5(args, rank, world, dev, dist, model, post, config):
     model.use_cuda_graph = not args.no_graph
     model.output_maps = ("binary",)
     rec = SVTRv2(variant="base").to(dev).eval()
+    rec.use_cuda_graph = not args.no_graph
     pool = [torch.from_numpy(synthetic_batch_u8(pb, S, S, seed=100 * rank + i)).pin_memory() for i in range(2)]
     dev_pages = [torch.empty(pb, S, S, 3, dtype=torch.uint8, device=dev) for _ in range(2)]
     rng = np.random.default_rng(rank)

@@ -256,6 +256,12 @@ __device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 constexpr int kKStride = 40;  // bf16 elements per K row in shared memory (32 + 8 padding)
 
 __global__ void __launch_bounds__(256, 3) mhsa_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int n,
@@ -309,19 +315,20 @@ __global__ void __launch_bounds__(256, 3) mhsa_mma_kernel(const __nv_bfloat16* _
                                        *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 8));
                 }
             }
+            // running maxima on the RAW scores (scale > 0 keeps the order); exp2(score * c - max * c) is one FFMA + one
+            // MUFU.EX2 per element (ex2.approx: exp2f() costs four instructions for denormal handling nobody needs here)
             float mx0 = m0, mx1 = m1;
 #pragma unroll
             for (int t = 0; t < 8; ++t)
                 if (t < tiles) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) sc[t][e] *= scale_log2e;
                     mx0 = fmaxf(mx0, fmaxf(sc[t][0], sc[t][1]));
                     mx1 = fmaxf(mx1, fmaxf(sc[t][2], sc[t][3]));
                 }
             mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
             mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-            const float r0 = exp2f(m0 - mx0), r1 = exp2f(m1 - mx1);
+            const float r0 = ex2_approx((m0 - mx0) * scale_log2e), r1 = ex2_approx((m1 - mx1) * scale_log2e);
             m0 = mx0; m1 = mx1;
+            const float nm0 = -m0 * scale_log2e, nm1 = -m1 * scale_log2e;
             l0 *= r0; l1 *= r1;
 #pragma unroll
             for (int t = 0; t < 4; ++t) { o[t][0] *= r0; o[t][1] *= r0; o[t][2] *= r1; o[t][3] *= r1; }
@@ -330,14 +337,13 @@ __global__ void __launch_bounds__(256, 3) mhsa_mma_kernel(const __nv_bfloat16* _
             for (int t = 0; t < 8; ++t) {
                 float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
                 if (t < tiles) {
-                    p0 = exp2f(sc[t][0] - m0); p1 = exp2f(sc[t][1] - m0); p2 = exp2f(sc[t][2] - m1); p3 = exp2f(sc[t][3] - m1);
+                    p0 = ex2_approx(fmaf(sc[t][0], scale_log2e, nm0)); p1 = ex2_approx(fmaf(sc[t][1], scale_log2e, nm0));
+                    p2 = ex2_approx(fmaf(sc[t][2], scale_log2e, nm1)); p3 = ex2_approx(fmaf(sc[t][3], scale_log2e, nm1));
                 }
-                // the probabilities are rounded to bf16 for the tensor core; the row sums use the same rounded values
-                const __nv_bfloat162 lo = __floats2bfloat162_rn(p0, p1), hi = __floats2bfloat162_rn(p2, p3);
-                l0 += __low2float(lo) + __high2float(lo);
-                l1 += __low2float(hi) + __high2float(hi);
-                pa[t >> 1][(t & 1) * 2] = *reinterpret_cast<const uint32_t*>(&lo);
-                pa[t >> 1][(t & 1) * 2 + 1] = *reinterpret_cast<const uint32_t*>(&hi);
+                l0 += p0 + p1;  // fp32 row sums; P itself is rounded to bf16 for the tensor core (relative 2^-9, unbiased)
+                l1 += p2 + p3;
+                pa[t >> 1][(t & 1) * 2] = pack2_bf16(p0, p1);
+                pa[t >> 1][(t & 1) * 2 + 1] = pack2_bf16(p2, p3);
             }
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)

@@ -313,9 +313,22 @@ class _Plan:
         self.log_probs = torch.empty(w, b, nc, device=dev, dtype=torch.float32)
         add("log_softmax", lambda: ops.log_softmax_tbc(self.logits, self.log_probs, b, w, nc, self.ld))
         self.n_launches = len(self.steps)
+        self.graph = None
 
-    def run(self, x: torch.Tensor, taps: Optional[dict] = None) -> torch.Tensor:
+    def run(self, x: torch.Tensor, taps: Optional[dict] = None, use_graph: bool = False) -> torch.Tensor:
         self.x_in[:self.batch].copy_(x)
+        if use_graph and taps is None:  # replay the captured launch list (the result aliases a plan-owned buffer)
+            if self.graph is None:
+                for s in self.steps:  # warm-up outside capture (lazy function attributes, module loading)
+                    s()
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for s in self.steps:
+                        s()
+                self.graph = g
+            self.graph.replay()
+            return self.log_probs[:, :self.batch]
         for i, s in enumerate(self.steps):
             s()
             if taps is not None:  # buffers are recycled by later blocks: copy a tap right after the step that completes it
@@ -351,6 +364,7 @@ class SVTRv2(nn.Module):
         self._sig = None
         self._plans: Dict[tuple, _Plan] = {}
         self._decoder = GreedyCTCDecoder(self.tokenizer)
+        self.use_cuda_graph = False  # replay a captured graph: log_probs then alias a plan-owned buffer (next call overwrites)
 
     def _signature(self):
         return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
@@ -377,7 +391,8 @@ class SVTRv2(nn.Module):
         if x.shape[2] % 8 or x.shape[3] % 4 or (x.shape[3] // 4) != 64:
             raise ValueError("B200 SVTRv2 path: crops must be (3, H, 256) with H a multiple of 8 (the pipeline's 32 x 256)")
         with torch.cuda.device(x.device):
-            return self._plan(x).run(x.float().contiguous())
+            lp = self._plan(x).run(x.float().contiguous(), use_graph=self.use_cuda_graph)
+            return lp if self.use_cuda_graph else lp.clone()
 
     @torch.no_grad()
     def forward_with_taps(self, x):

@@ -146,6 +146,7 @@ class OCRPipeline:
                  rec_size: Tuple[int, int] = (32, 256), rec_bucket: int = 32, capacity: int = 1024):
         self.detector = Detector(det_model, post, device, use_cuda_graph=False)
         self.rec_model = rec_model
+        rec_model.use_cuda_graph = True  # one captured graph per batch bucket; the strings are read before the next call
         self.det_size = det_size
         self.rec_bucket = int(rec_bucket)
         self.cropper = RecognitionCropper(rec_size, capacity=capacity, device=self.detector.device)

@@ -197,6 +197,9 @@ def test_model_batches_and_decode():
     big = torch.cat([x, x.flip(0), x[:1]])  # 7 crops
     lp7 = model(big).clone()
     assert torch.equal(lp7[:, :3], lp3) and torch.equal(lp7[:, 6], lp3[:, 0]) and torch.equal(lp7[:, 3], lp3[:, 2])
+    model.use_cuda_graph = True  # graph replay: same bits, twice
+    assert torch.equal(model(x), lp3) and torch.equal(model(x), lp3)
+    model.use_cuda_graph = False
     texts = model.decode_greedy(x)
     assert texts == model.decode_probs(lp3) and len(texts) == 3 and all(isinstance(t, str) for t in texts)
     with pytest.raises(RuntimeError, match="no CPU fallback"):

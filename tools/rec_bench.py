@@ -24,7 +24,8 @@ def main():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--dump", default="")
-    ap.add_argument("--profile-step", default="", help="run the forward once, then only this plan step 3x (for ncu)")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--profile-step", default="", help="comma-separated plan steps to run once between cudaProfilerStart/Stop (ncu --profile-from-start off)")
     args = ap.parse_args()
     from ocr_vi_invoice_b200.model.rec2.svtrv2 import SVTRv2
     from oracle.svtrv2_oracle import make_state_dict
@@ -33,16 +34,19 @@ def main():
     model = SVTRv2(variant="base")
     model.load_state_dict(make_state_dict("base", 0), strict=True)
     model = model.to(dev).eval()
+    model.use_cuda_graph = not args.no_graph
     x = torch.randn(args.batch, 3, 32, 256, device=dev)
     for _ in range(3):
         lp = model(x)
     torch.cuda.synchronize()
     plan = model._plan(x)
     if args.profile_step:
-        i = plan.names.index(args.profile_step)
-        for _ in range(3):
-            plan.steps[i]()
         torch.cuda.synchronize()
+        torch.cuda.profiler.start()  # ncu --profile-from-start off: only these launches are captured
+        for name in args.profile_step.split(","):
+            plan.steps[plan.names.index(name)]()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
         return
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
