@@ -310,11 +310,15 @@ def run_config5(args, rank, world, dev, dist, model, post, config):
     cropper = RecognitionCropper((32, 256), capacity=pb * nbox, device=dev)
     copy_stream = torch.cuda.Stream(device=dev)
     ncrops = pb * nbox
-    tok_host = torch.empty(ncrops, 65, dtype=torch.int32).pin_memory()
+    tok_host = [torch.empty(ncrops, 65, dtype=torch.int32).pin_memory() for _ in range(2)]
+    tok_done = [None, None]
 
-    def step(i, texts_out):
+    def launch(i):
+        """Queue everything of step i; nothing here waits for the GPU."""
         slot = i & 1
         with torch.cuda.stream(copy_stream):
+            if tok_done[slot] is not None:
+                copy_stream.wait_event(tok_done[slot])  # the pages of step i-2 in this slot have been consumed
             dev_pages[slot].copy_(pool[slot], non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(copy_stream)
@@ -324,22 +328,34 @@ def run_config5(args, rank, world, dev, dist, model, post, config):
         crops = cropper.from_detector(injected, list(dev_pages[slot]), [(1.0, 1.0)] * pb, int(post.max_candidates))
         lp = rec(crops["out"][:ncrops])
         tokens, lengths = rec._decoder.run_device(lp)
-        tok_host[:, :64].copy_(tokens, non_blocking=True)
-        tok_host[:, 64].copy_(lengths, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        th = tok_host.numpy()
+        tok_host[slot][:, :64].copy_(tokens, non_blocking=True)
+        tok_host[slot][:, 64].copy_(lengths, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        tok_done[slot] = ev
+
+    def collect(i, texts_out):
+        """Host side of step i: wait for its token ids only, then build the strings (overlaps the GPU work of step i+1)."""
+        slot = i & 1
+        tok_done[slot].synchronize()
+        th = tok_host[slot].numpy()
         texts_out.append(rec.tokenizer.decode([th[k, :th[k, 64]].tolist() for k in range(ncrops)]))
 
-    warm = []
-    for i in range(3):
-        step(i, warm)
+    def run(nsteps, texts_out):
+        for i in range(nsteps):
+            launch(i)
+            if i > 0:
+                collect(i - 1, texts_out)
+        if nsteps:
+            collect(nsteps - 1, texts_out)
+
+    run(3, [])
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     t0 = time.perf_counter()
     texts = []
-    for i in range(steps):
-        step(i, texts)
+    run(steps, texts)
     torch.cuda.synchronize()
     t_local = time.perf_counter() - t0
     local = [(mine[min(i * pb + j, len(mine) - 1)], ([], texts[i][j * nbox:(j + 1) * nbox])) for i in range(steps) for j in range(pb)
