@@ -354,17 +354,52 @@ __device__ __forceinline__ void epilogue_head_dot(const IgemmParams& p, uint32_t
 // nn.GELU (exact erf form) of the SVTRv2 recogniser (model/rec2/svtrv2.py:33,51,54,114,117) applied to scale * acc + shift,
 // BEFORE the optional residual add (LocalMixing: x + act(bn(conv(.)))).  erf by Abramowitz & Stegun 7.1.26
 // (|error| <= 1.5e-7, far below a bf16 ulp): one MUFU.RCP + one MUFU.EX2 + seven FMAs per element.
-__device__ __forceinline__ float gelu_as(float x) {
-    const float z = x * 0.70710678118654752440f;
-    const float a = fabsf(z);
-    float t;  // MUFU.RCP (1 ulp): __frcp_rn would be a ~25-instruction IEEE sequence
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, a, 1.0f)));
-    float q = fmaf(1.061405429f, t, -1.453152027f);
-    q = fmaf(q, t, 1.421413741f);
-    q = fmaf(q, t, -0.284496736f);
-    q = fmaf(q, t, 0.254829592f);
-    const float e = copysignf(1.0f - q * t * __expf(-a * a), z);
-    return 0.5f * x * (1.0f + e);
+// Two elements at a time on the packed-fp32 pipe (FFMA2 / FMUL2, sm_100): GELU(x) = x * (x >= 0 ? 1 - h : h) with
+// h = 0.5 * (a1 t + .. + a5 t^5) * exp(-x^2 / 2), t = 1 / (1 + p |x| / sqrt 2) -- the 0.5 and the 1/sqrt 2 are folded into the
+// constants, so a pair costs ~20 issue slots instead of ~36 (the GELU epilogues are issue-bound: ncu 73 % issue active).
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float ex2_approx_f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void gelu_as2(float& x0, float& x1) {
+    const float u0 = fabsf(x0), u1 = fabsf(x1);
+    const uint64_t u = pk2(u0, u1);
+    float d0, d1;
+    upk2(fma2(u, pk2(0.23164189f, 0.23164189f), pk2(1.0f, 1.0f)), d0, d1);  // 0.3275911 / sqrt 2
+    const uint64_t t = pk2(rcp_approx(d0), rcp_approx(d1));
+    uint64_t q = fma2(pk2(0.5307027145f, 0.5307027145f), t, pk2(-0.7265760135f, -0.7265760135f));  // 0.5 * a5, 0.5 * a4
+    q = fma2(q, t, pk2(0.7107068705f, 0.7107068705f));
+    q = fma2(q, t, pk2(-0.142248368f, -0.142248368f));
+    q = fma2(q, t, pk2(0.127414796f, 0.127414796f));
+    q = mul2(q, t);
+    float s0, s1;
+    upk2(mul2(mul2(u, u), pk2(-0.72134752f, -0.72134752f)), s0, s1);  // -x^2 / 2 * log2 e
+    float h0, h1;
+    upk2(mul2(q, pk2(ex2_approx_f(s0), ex2_approx_f(s1))), h0, h1);
+    x0 *= (x0 >= 0.0f) ? 1.0f - h0 : h0;
+    x1 *= (x1 >= 0.0f) ? 1.0f - h1 : h1;
 }
 
 // ------------------------------------------------------------------------------------------ kernel
@@ -805,7 +840,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                             f[7] = fmaf(__uint_as_float(v[j * 8 + 7]), sc1.w, sh1.w);
                             if constexpr (kEpi == 3) {
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) f[i] = gelu_as(f[i]);
+                                for (int i = 0; i < 8; i += 2) gelu_as2(f[i], f[i + 1]);
                             }
                             if (p.res_tma) {
                                 uint4 u;
