@@ -204,7 +204,9 @@ class _Plan:
     def __init__(self, W: _Prepared, cfg, batch: int, H: int, Wd: int):
         dev = W.device
         self.batch = batch
-        b = batch + (batch & 1)  # whole 2-row tiles for the token-matrix GEMMs; the padding crop is zeros
+        import math
+        m = 128 // math.gcd(Wd // 4, 128)  # whole 128-token tiles for every token-matrix GEMM, down to the (b * W/4)-row
+        b = -(-batch // m) * m             # head: pad the batch (2 for the pipeline's W = 256); padding crops are zeros
         self.bp = b
         dims = cfg["dims"]
         bf = lambda *s: torch.empty(*s, device=dev, dtype=torch.bfloat16)
@@ -223,7 +225,7 @@ class _Plan:
             w, s, t = W.G[key]
             if geom is None:
                 assert rows % 128 == 0
-                geom = (1, rows // 64, 64)
+                geom = (1, rows // 64, 64)  # any factorisation works for a 1x1 conv; 2 rows x 64 tokens = one 128-row tile
             op = ops.Igemm(ops.IGEMM_CONV, x, w, s, t, y, batch=geom[0], in_h=geom[1], in_w=geom[2], in_c=in_c, out_c=out_c,
                            ksize=ksize, stride=stride, flags=flags, residual=residual, res_ld=out_c if residual is not None else 0,
                            name=name)
@@ -388,8 +390,9 @@ class SVTRv2(nn.Module):
             raise ValueError("SVTRv2.forward expects a float (B, 3, H, W) tensor")
         if not x.is_cuda:
             raise RuntimeError("B200 SVTRv2 path runs on CUDA only (there is no CPU fallback)")
-        if x.shape[2] % 8 or x.shape[3] % 4 or (x.shape[3] // 4) != 64:
-            raise ValueError("B200 SVTRv2 path: crops must be (3, H, 256) with H a multiple of 8 (the pipeline's 32 x 256)")
+        if x.shape[2] % 32 or x.shape[3] % 128 or x.shape[2] > 256 or x.shape[3] > 2048:
+            raise ValueError("B200 SVTRv2 path: crops must be (3, H, W) with H a multiple of 32 and W a multiple of 128 "
+                             "(the pipeline's 32 x 256): whole 128-token tiles at every stage")
         with torch.cuda.device(x.device):
             lp = self._plan(x).run(x.float().contiguous(), use_graph=self.use_cuda_graph)
             return lp if self.use_cuda_graph else lp.clone()

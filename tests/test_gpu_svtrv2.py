@@ -189,6 +189,21 @@ def test_model_against_oracle_and_reference_golden():
     assert torch.equal(lp.argmax(-1)[clear], ref.argmax(-1)[clear])
 
 
+def test_model_other_crop_sizes():
+    """(64, 128) and (32, 384) crops: other token grids (16 x 32 -> 4 x 32, 8 x 96 -> 2 x 96) against the oracle."""
+    from oracle import svtrv2_oracle as so
+    g, sd, model = _golden_model()
+    gen = torch.Generator().manual_seed(7)
+    for hh, ww in ((64, 128), (32, 384)):
+        x = torch.randn(2, 3, hh, ww, generator=gen)
+        lp = model(x.to(DEV)).cpu()
+        ref = so.svtrv2_forward(sd, x, "base")
+        assert lp.shape == ref.shape == (ww // 4, 2, 232)
+        assert (lp - ref).abs().max().item() < 0.15, (hh, ww)
+    with pytest.raises(ValueError, match="multiple of 32"):
+        model(torch.zeros(1, 3, 40, 256, device=DEV))
+
+
 def test_model_batches_and_decode():
     """Odd batch (padding crop), batch invariance bit for bit, decode_greedy == decode_probs(forward), CPU refusal."""
     g, sd, model = _golden_model()
