@@ -127,6 +127,21 @@ class _SGM(nn.Module):
         self.sgm_head = nn.Linear(dim, num_classes)
 
 
+def _p64(c: int) -> int:
+    """Channel counts are padded to whole 64-channel K blocks / 64-column store chunks ('small': 96 -> 128, stem 48 -> 64;
+    'tiny': stem 32 -> 64).  Padding weights, biases and activations are zero, LayerNorm runs over the real width."""
+    return (c + 63) // 64 * 64
+
+
+def _pad_w(w: torch.Tensor) -> torch.Tensor:
+    o, i = w.shape[0], w.shape[1]
+    if o == _p64(o) and i == _p64(i):
+        return w
+    out = torch.zeros(_p64(o), _p64(i), *w.shape[2:], device=w.device, dtype=w.dtype)
+    out[:o, :i] = w
+    return out
+
+
 # ---------------------------------------------------------------------------------------- weight preparation
 class _Prepared:
     """bf16 K-major matrices + fp32 (scale, shift) per GEMM, fp32 LayerNorm affines, the constant FRM query."""
@@ -138,7 +153,7 @@ class _Prepared:
         self.LN: Dict[str, tuple] = {}
 
         def linear(name, lin, extra_shift=None):
-            w = ops.pack_conv_weight(f32(lin.weight).reshape(lin.out_features, lin.in_features, 1, 1))
+            w = ops.pack_conv_weight(_pad_w(f32(lin.weight).reshape(lin.out_features, lin.in_features, 1, 1)))
             shift = f32(lin.bias) if extra_shift is None else f32(lin.bias) + extra_shift
             self.G[name] = (w, torch.ones(w.shape[0], device=device), ops.pad_vec(shift, w.shape[0]))
 
@@ -151,7 +166,7 @@ class _Prepared:
                 for g in range(conv.groups):
                     dense[g * og:(g + 1) * og, g * ig:(g + 1) * ig] = w[g * og:(g + 1) * og]
                 w = dense
-            wp = ops.pack_conv_weight(w)
+            wp = ops.pack_conv_weight(_pad_w(w))
             s, t = ops.fold_bn(f32(bn.weight), f32(bn.bias), f32(bn.running_mean), f32(bn.running_var), bn.eps, f32(conv.bias))
             self.G[name] = (wp, ops.pad_vec(s, wp.shape[0], 1.0), ops.pad_vec(t, wp.shape[0]))
 
@@ -161,7 +176,10 @@ class _Prepared:
         st = model.stem
         s, t = ops.fold_bn(f32(st.bn1.weight), f32(st.bn1.bias), f32(st.bn1.running_mean), f32(st.bn1.running_var), st.bn1.eps,
                            f32(st.conv1.bias))
-        self.stem1 = (f32(st.conv1.weight).reshape(st.conv1.out_channels, 27).contiguous(), s.contiguous(), t.contiguous())
+        mid = st.conv1.out_channels
+        w1 = torch.zeros(_p64(mid), 27, device=device)
+        w1[:mid] = f32(st.conv1.weight).reshape(mid, 27)
+        self.stem1 = (w1, ops.pad_vec(s, _p64(mid), 1.0), ops.pad_vec(t, _p64(mid)))
         conv_bn("stem.conv2", st.conv2, st.bn2)
         for si, stage in enumerate(model.stages):
             for bi, blk in enumerate(stage.blocks):
@@ -208,8 +226,9 @@ class _Plan:
         m = 128 // math.gcd(Wd // 4, 128)  # whole 128-token tiles for every token-matrix GEMM, down to the (b * W/4)-row
         b = -(-batch // m) * m             # head: pad the batch (2 for the pipeline's W = 256); padding crops are zeros
         self.bp = b
-        dims = cfg["dims"]
-        bf = lambda *s: torch.empty(*s, device=dev, dtype=torch.bfloat16)
+        real = cfg["dims"]
+        dims = [_p64(d) for d in real]  # buffer / GEMM widths; LayerNorm statistics run over real[si] channels
+        bf = lambda *s: torch.zeros(*s, device=dev, dtype=torch.bfloat16)  # zero: padding channels are never written
         self.x_in = torch.zeros(b, 3, H, Wd, device=dev, dtype=torch.float32)
         self.steps: List = []
         self.names: List[str] = []
@@ -234,23 +253,24 @@ class _Plan:
 
         def lnorm(name, key, x, y, rows, d):
             g, be, eps = W.LN[key]
-            add(name, lambda: ops.layernorm(x, y, g, be, rows, d, eps))
+            add(name, lambda: ops.layernorm(x, y, g, be, rows, g.numel(), eps, x_ld=d, y_ld=d))
 
         h, w = H // 4, Wd // 4
-        mid = dims[0] // 2
+        mid = _p64(real[0] // 2)
         s1 = bf(b, H // 2, Wd // 2, mid)
         add("stem.conv1", lambda: ops.svtr_stem1(self.x_in, *W.stem1, s1))
         x = bf(b, h, w, dims[0])
         gemm("stem.conv2", "stem.conv2", s1, x, geom=(b, H // 2, Wd // 2), in_c=mid, out_c=dims[0], ksize=3, stride=2,
              flags=ops.EPI_GELU)
-        self.taps = {"stem": (x, len(self.steps))}  # (buffer, number of steps after which it holds the tap)
+        self.taps = {"stem": (x, len(self.steps), real[0])}  # (buffer, steps after which it holds the tap, real width)
         for si in range(3):
             d = dims[si]
+            hidw, qkvw = _p64(4 * real[si]), _p64(3 * real[si])  # == 4 * d, 3 * d unless the stage width itself is padded
             rows = b * h * w
             other = bf(b, h, w, d)
             nbuf, cbuf = bf(b, h, w, d), bf(b, h, w, d)
-            hid = bf(b, h, w, 4 * d)
-            qkv = bf(b, h, w, 3 * d) if cfg["num_local"][si] < cfg["num_blocks"][si] else None
+            hid = bf(b, h, w, hidw)
+            qkv = bf(b, h, w, qkvw) if cfg["num_local"][si] < cfg["num_blocks"][si] else None
             for bi in range(cfg["num_blocks"][si]):
                 p = f"stages.{si}.blocks.{bi}"
                 lnorm(p + ".norm1", p + ".norm1", x, nbuf, rows, d)
@@ -259,15 +279,16 @@ class _Plan:
                     gemm(p + ".conv2", p + ".conv2", cbuf, other, geom=(b, h, w), in_c=d, out_c=d, ksize=3,
                          flags=ops.EPI_GELU | ops.EPI_RES, residual=x)  # x + gelu(bn2(conv2(.))): GELU before the add
                 else:
+                    assert qkvw == 3 * d, "attention needs an unpadded stage width"
                     gemm(p + ".qkv", p + ".qkv", nbuf, qkv, rows=rows, in_c=d, out_c=3 * d)
                     add(p + ".attn", lambda q=qkv, o=cbuf, n=h * w, d=d: ops.mhsa(q, o, b, n, d))
                     gemm(p + ".proj", p + ".proj", cbuf, other, rows=rows, in_c=d, out_c=d, flags=ops.EPI_RES, residual=x)
                 x, other = other, x
                 lnorm(p + ".norm2", p + ".norm2", x, nbuf, rows, d)
-                gemm(p + ".fc1", p + ".fc1", nbuf, hid, rows=rows, in_c=d, out_c=4 * d, flags=ops.EPI_GELU)
-                gemm(p + ".fc2", p + ".fc2", hid, other, rows=rows, in_c=4 * d, out_c=d, flags=ops.EPI_RES, residual=x)
+                gemm(p + ".fc1", p + ".fc1", nbuf, hid, rows=rows, in_c=d, out_c=hidw, flags=ops.EPI_GELU)
+                gemm(p + ".fc2", p + ".fc2", hid, other, rows=rows, in_c=hidw, out_c=d, flags=ops.EPI_RES, residual=x)
                 x, other = other, x
-            self.taps[f"stage{si}"] = (x, len(self.steps))
+            self.taps[f"stage{si}"] = (x, len(self.steps), real[si])
             if si < 2:  # PatchMerging: stride-1 3x3 conv + BN, then every second row
                 dn = dims[si + 1]
                 full = bf(b, h, w, dn)
@@ -289,7 +310,7 @@ class _Plan:
         lnorm("frm.h_norm2", "frm.h_norm2", r2, n1, rows, d)
         gemm("frm.h_fc1", "frm.h_fc1", n1, hid, rows=rows, in_c=d, out_c=4 * d, flags=ops.EPI_GELU)
         gemm("frm.h_fc2", "frm.h_fc2", hid, r3, rows=rows, in_c=4 * d, out_c=d, flags=ops.EPI_RES, residual=r2)
-        self.taps["frm_h"] = (r3, len(self.steps))
+        self.taps["frm_h"] = (r3, len(self.steps), real[2])
         # ---- FRM, vertical: the selecting token attends over the h rows of each column
         kv = bf(rows, 2 * d)
         lnorm("frm.v_norm_kv", "frm.v_norm_kv", r3, n1, rows, d)
@@ -302,7 +323,7 @@ class _Plan:
         lnorm("frm.v_norm2", "frm.v_norm2", t1, t1n, trows, d)
         gemm("frm.v_fc1", "frm.v_fc1", t1n, thid, rows=trows, in_c=d, out_c=4 * d, flags=ops.EPI_GELU)
         gemm("frm.v_fc2", "frm.v_fc2", thid, t2, rows=trows, in_c=4 * d, out_c=d, flags=ops.EPI_RES, residual=t1)
-        self.taps["frm"] = (t2, len(self.steps))
+        self.taps["frm"] = (t2, len(self.steps), real[2])
         nc = W.num_classes
         self.ld = (nc + 7) // 8 * 8
         self.logits = torch.empty(trows, self.ld, device=dev, dtype=torch.float32)
@@ -334,9 +355,9 @@ class _Plan:
         for i, s in enumerate(self.steps):
             s()
             if taps is not None:  # buffers are recycled by later blocks: copy a tap right after the step that completes it
-                for k, (buf, after) in self.taps.items():
+                for k, (buf, after, width) in self.taps.items():
                     if after == i + 1:
-                        taps[k] = buf.float().reshape(self.bp, -1, buf.shape[-1])[:self.batch].clone()
+                        taps[k] = buf.float().reshape(self.bp, -1, buf.shape[-1])[:self.batch, :, :width].clone()
         return self.log_probs[:, :self.batch]
 
 
@@ -347,10 +368,9 @@ class SVTRv2(nn.Module):
         assert variant in VARIANTS, f"Unknown variant: {variant}. Choose from {list(VARIANTS.keys())}"
         cfg = VARIANTS[variant]
         dims = cfg["dims"]
-        if in_channels != 3 or any(d % 64 for d in dims):
-            raise NotImplementedError("B200 SVTRv2 path: 3 input channels and stage widths that are multiples of 64 "
-                                      "('base'; 'tiny' and 'small' have 96 / 192-wide or 64-wide stages the tcgen05 "
-                                      "GEMM's 64-channel K blocks do not cover yet) -- no unaccelerated fallback")
+        if in_channels != 3:
+            raise NotImplementedError("B200 SVTRv2 path: RGB crops only (in_channels == 3, pipeline2.py:72) -- no "
+                                      "unaccelerated fallback")
         self.variant, self.cfg = variant, cfg
         self.tokenizer = Tokenizer(charset)
         self.dims = dims

@@ -65,6 +65,14 @@ def main():
     for k, v in taps.items():
         out["tap." + k] = v.numpy()[:, ::TAP_STRIDE] if k.startswith("sta") or k == "stem" else v.numpy()
         print(k, tuple(v.shape), float(v.abs().mean()))
+    # the other two variants (the class default is 'small'): log-probabilities on the same inputs
+    for variant in ("tiny", "small"):
+        mv = SVTRv2(variant=variant).eval()
+        sdv = so.make_state_dict(variant, SEED, mv.tokenizer.num_classes)
+        assert list(sdv.keys()) == list(mv.state_dict().keys())
+        mv.load_state_dict(sdv, strict=True)
+        with torch.no_grad():
+            out[f"log_probs_{variant}"] = mv(x).numpy()
     print("log_probs", lp.shape, "max prob per frame (mean)", float(lp.exp().max(-1).values.mean()), texts)
     np.savez_compressed(HERE / "svtrv2_small.npz", **out)
     print("wrote", HERE / "svtrv2_small.npz")

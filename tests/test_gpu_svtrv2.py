@@ -204,6 +204,28 @@ def test_model_other_crop_sizes():
         model(torch.zeros(1, 3, 40, 256, device=DEV))
 
 
+@pytest.mark.parametrize("variant", ["tiny", "small"])
+def test_other_variants_against_reference_golden(variant):
+    """'tiny' (stem 32 -> 64 padded) and 'small' (stage width 96 -> 128, stem 48 -> 64 padded; the class default): zero-padded
+    channels, LayerNorm over the real width; log-probabilities vs the reference module's (golden) and taps vs the oracle."""
+    from oracle import svtrv2_oracle as so
+    from ocr_vi_invoice_b200.model.rec2.svtrv2 import SVTRv2
+    g = np.load(GOLD / "svtrv2_small.npz")
+    sd = so.make_state_dict(variant, int(g["seed"]))
+    model = SVTRv2(variant=variant)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV).eval()
+    x = torch.from_numpy(g["x"])
+    lp, taps = model.forward_with_taps(x.to(DEV))
+    ref_taps = {}
+    ref = so.svtrv2_forward(sd, x, variant, ref_taps)
+    torch.testing.assert_close(ref, torch.from_numpy(g[f"log_probs_{variant}"]), rtol=1e-4, atol=1e-4)
+    errs = {k: _rel(taps[k].cpu(), ref_taps[k]) for k in ("stem", "stage0", "stage1", "stage2", "frm")}
+    print(variant, "rel rms error per stage:", {k: round(v, 4) for k, v in errs.items()})
+    assert max(errs.values()) < 0.04
+    assert (lp.cpu() - ref).abs().max().item() < 0.15
+
+
 def test_model_batches_and_decode():
     """Odd batch (padding crop), batch invariance bit for bit, decode_greedy == decode_probs(forward), CPU refusal."""
     g, sd, model = _golden_model()

@@ -141,8 +141,11 @@ def test_svtrv2_dropin_state_dict_matches_reference_key_set():
     assert all(tuple(sd[k].shape) == tuple(shapes[k]) for k in shapes)
     model.load_state_dict(so.make_state_dict("base", 1), strict=True)
     assert model.blank_id == 0 and model.tokenizer.num_classes == 232
+    for variant in ("tiny", "small"):  # the class default is 'small' (reference svtrv2.py:421)
+        mv = SVTRv2(variant=variant) if variant == "tiny" else SVTRv2()
+        assert list(mv.state_dict().keys()) == list(so.param_shapes(variant).keys())
     with pytest.raises(NotImplementedError):
-        SVTRv2(variant="small")
+        SVTRv2(in_channels=1)
     import torch
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         model.eval()(torch.zeros(1, 3, 32, 256))

@@ -318,3 +318,6 @@ def test_svtrv2_restatement_matches_reference_module():
         torch.testing.assert_close(taps[k], ref, rtol=1e-4, atol=1e-4 * float(ref.abs().max()))
     from ocr_vi_invoice_b200.model.rec2 import VOCAB
     assert co.decode_probs(lp.numpy(), VOCAB) == g["texts"].tolist()
+    for variant in ("tiny", "small"):
+        lpv = so.svtrv2_forward(so.make_state_dict(variant, int(g["seed"])), torch.from_numpy(g["x"]), variant)
+        torch.testing.assert_close(lpv, torch.from_numpy(g[f"log_probs_{variant}"]), rtol=1e-4, atol=1e-4)
