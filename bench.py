@@ -133,7 +133,7 @@ def cpu_reference_run(state_dict, steps, warmup, sample_hw=(1024, 1024), k=50.0)
     return ips, cores, sum(times) / len(times)
 
 
-def next_row_kernels(dev, peak_gbs):
+def next_row_kernels(dev, peak_gbs, cpu_leg=False):
     """SURVEY 8(f) rows built after the detector: the detection -> recognition hand-over kernel and the greedy CTC decode,
     timed alone with CUDA events (L2 flushed between launches), algorithmic bytes over time against the HBM copy peak."""
     import numpy as np
@@ -215,6 +215,17 @@ def next_row_kernels(dev, peak_gbs):
                           "dense_equivalent_tflops": round(plan.flops / (ms * 1e-3) / 1e12, 1)}
     del rec, xb, plan
     torch.cuda.empty_cache()
+    if cpu_leg:  # the reference's CPU path for the recogniser next to it: fp32 torch on the host cores, bounded sample
+        import os
+        from oracle import svtrv2_oracle as svo
+        sd = svo.make_state_dict("base", 0)
+        xs = torch.randn(16, 3, 32, 256)
+        svo.svtrv2_forward(sd, xs[:2], "base")
+        t0 = time.perf_counter()
+        svo.svtrv2_forward(sd, xs, "base")
+        dt = time.perf_counter() - t0
+        out["svtrv2_base"]["cpu_baseline"] = {"value": round(16 / dt, 2), "unit": "crops/s", "cores": os.cpu_count(), "kind": "port",
+                                              "sample": f"one forward of 16 crops (fp32 torch CPU oracle restatement), {dt:.2f} s"}
     return out
 
 
@@ -628,7 +639,7 @@ def main():
                 "components_per_image": int(post.fetch(post.run_device(pm, want_labels=False))[1].mean()),
                 "top_launches_ms": [[n, round(ms, 3)] for n, _, ms, _ in top],
                 "clocks": clocks}
-        line["next_rows"] = next_row_kernels(dev, pk["hbm_gbs"])
+        line["next_rows"] = next_row_kernels(dev, pk["hbm_gbs"], cpu_leg=not args.no_cpu_baseline and world == 1)
         if not args.no_cpu_baseline and world == 1:
             ips, cores, sec = cpu_reference_run(sd_cpu, steps=2, warmup=1)
             line["cpu_baseline"] = {"value": round(ips, 4), "unit": "images/s", "cores": cores, "kind": "port",

@@ -262,6 +262,21 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+    const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(smem_row));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ffma2_bcast(float& d0, float& d1, float a0, float a1, float b, float c) {
+    // (d0, d1) = (a0, a1) * b + c on the packed-fp32 pipe
+    uint64_t r, av, bv, cv;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(av) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(bv) : "f"(b));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(cv) : "f"(c));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(av), "l"(bv), "l"(cv));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(r));
+}
+
 constexpr int kKStride = 40;  // bf16 elements per K row in shared memory (32 + 8 padding)
 
 __global__ void __launch_bounds__(256, 3) mhsa_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int n,
@@ -308,11 +323,12 @@ __global__ void __launch_bounds__(256, 3) mhsa_mma_kernel(const __nv_bfloat16* _
             for (int t = 0; t < 8; ++t) {
                 sc[t][0] = sc[t][1] = sc[t][2] = sc[t][3] = 0.0f;
                 if (t < tiles) {
-                    const __nv_bfloat16* kr = s_k + (k0 + t * 8 + g) * kKStride + tq * 2;
-#pragma unroll
-                    for (int ks = 0; ks < 2; ++ks)
-                        mma_bf16_16816(sc[t], qa[ks], *reinterpret_cast<const uint32_t*>(kr + ks * 16),
-                                       *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 8));
+                    // one ldmatrix.x4 = the B fragments of both k-steps of this 8-key tile: matrices at channel offsets
+                    // 0 / 8 / 16 / 24, row = key (80-byte row stride: the eight 16-byte rows fall in distinct bank groups)
+                    uint32_t kb[4];
+                    ldmatrix_x4(kb, s_k + (k0 + t * 8 + (lane & 7)) * kKStride + (lane >> 3) * 8);
+                    mma_bf16_16816(sc[t], qa[0], kb[0], kb[1]);
+                    mma_bf16_16816(sc[t], qa[1], kb[2], kb[3]);
                 }
             }
             // running maxima on the RAW scores (scale > 0 keeps the order); exp2(score * c - max * c) is one FFMA + one
@@ -337,8 +353,10 @@ __global__ void __launch_bounds__(256, 3) mhsa_mma_kernel(const __nv_bfloat16* _
             for (int t = 0; t < 8; ++t) {
                 float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
                 if (t < tiles) {
-                    p0 = ex2_approx(fmaf(sc[t][0], scale_log2e, nm0)); p1 = ex2_approx(fmaf(sc[t][1], scale_log2e, nm0));
-                    p2 = ex2_approx(fmaf(sc[t][2], scale_log2e, nm1)); p3 = ex2_approx(fmaf(sc[t][3], scale_log2e, nm1));
+                    float a0, a1, a2, a3;
+                    ffma2_bcast(a0, a1, sc[t][0], sc[t][1], scale_log2e, nm0);
+                    ffma2_bcast(a2, a3, sc[t][2], sc[t][3], scale_log2e, nm1);
+                    p0 = ex2_approx(a0); p1 = ex2_approx(a1); p2 = ex2_approx(a2); p3 = ex2_approx(a3);
                 }
                 l0 += p0 + p1;  // fp32 row sums; P itself is rounded to bf16 for the tensor core (relative 2^-9, unbiased)
                 l1 += p2 + p3;
@@ -348,11 +366,14 @@ __global__ void __launch_bounds__(256, 3) mhsa_mma_kernel(const __nv_bfloat16* _
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
                 if (kk * 2 < tiles) {
+                    // two ldmatrix.x4 = the B fragments of the four 8-channel output tiles for this 16-key step (matrix j =
+                    // channel tile j, row = channel, 16 bytes = 8 keys; low and high key halves)
+                    uint32_t vlo[4], vhi[4];
+                    const __nv_bfloat16* vr = s_vt + ((lane >> 3) * 8 + (lane & 7)) * vt_stride + k0 + kk * 16;
+                    ldmatrix_x4(vlo, vr);
+                    ldmatrix_x4(vhi, vr + 8);
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) {  // 8 output channels per tile
-                        const __nv_bfloat16* vr = s_vt + (t * 8 + g) * vt_stride + k0 + kk * 16 + tq * 2;
-                        mma_bf16_16816(o[t], pa[kk], *reinterpret_cast<const uint32_t*>(vr), *reinterpret_cast<const uint32_t*>(vr + 8));
-                    }
+                    for (int t = 0; t < 4; ++t) mma_bf16_16816(o[t], pa[kk], vlo[t], vhi[t]);
                 }
         }
         l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
