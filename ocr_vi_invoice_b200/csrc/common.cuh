@@ -212,6 +212,30 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {  // explicit ld.shared
 __device__ __forceinline__ uint4 ldg128(const void* p) {
     return __ldg(reinterpret_cast<const uint4*>(p));
 }
+// ---------------------------------------------------------------------------------- packed fp32 (FFMA2 / FMUL2, sm_100)
+__device__ __forceinline__ uint64_t pair2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpair2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+// the two bf16 channels of a 32-bit word as a (lo, hi) fp32 pair
+__device__ __forceinline__ uint64_t bf16pair(uint32_t u) {
+    return pair2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+__device__ __forceinline__ uint64_t fma2_f32(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t mul2_f32(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 __device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {

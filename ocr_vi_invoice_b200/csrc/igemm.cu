@@ -312,7 +312,9 @@ __device__ __forceinline__ void epilogue_head_dot(const IgemmParams& p, uint32_t
                                                   int ox, bool valid, int sub) {
     // ss (shared): scale[256] | tail weights w2[64][4] | shift[256]   (staged once per CTA, see the kernel prologue)
     const uint32_t sc = ss_s + sub * 256, sh = ss_s + 2048 + sub * 256, w2 = ss_s + 1024;
-    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    // accumulators (0, 1) and (2, 3) as fp32 pairs on the packed pipe (FFMA2): per lane the same IEEE fma sequence as
+    // db_head_kernel, so the logits stay bit-identical to the unfused path; 16 + 4 FMAs per 4 channels become 8 + 2
+    uint64_t acc01 = pair2(0.0f, 0.0f), acc23 = pair2(0.0f, 0.0f);
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         uint32_t v[32];
@@ -322,8 +324,9 @@ __device__ __forceinline__ void epilogue_head_dot(const IgemmParams& p, uint32_t
         for (int i = 0; i < 32; i += 4) {
             const int c = half * 32 + i;
             const float4 s4 = lds_f4(sc + c * 4), h4 = lds_f4(sh + c * 4);
-            float t0 = fmaf(__uint_as_float(v[i + 0]), s4.x, h4.x), t1 = fmaf(__uint_as_float(v[i + 1]), s4.y, h4.y);
-            float t2 = fmaf(__uint_as_float(v[i + 2]), s4.z, h4.z), t3 = fmaf(__uint_as_float(v[i + 3]), s4.w, h4.w);
+            float t0, t1, t2, t3;
+            unpair2(fma2_f32(pair2(__uint_as_float(v[i + 0]), __uint_as_float(v[i + 1])), pair2(s4.x, s4.y), pair2(h4.x, h4.y)), t0, t1);
+            unpair2(fma2_f32(pair2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])), pair2(s4.z, s4.w), pair2(h4.z, h4.w)), t2, t3);
             if (p.flags & B200_EPI_RELU) {
                 t0 = fmaxf(t0, 0.0f); t1 = fmaxf(t1, 0.0f); t2 = fmaxf(t2, 0.0f); t3 = fmaxf(t3, 0.0f);
             }
@@ -332,13 +335,15 @@ __device__ __forceinline__ void epilogue_head_dot(const IgemmParams& p, uint32_t
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float4 w = lds_f4(w2 + (c + j) * 16);
-                acc[0] = fmaf(r[j], w.x, acc[0]);
-                acc[1] = fmaf(r[j], w.y, acc[1]);
-                acc[2] = fmaf(r[j], w.z, acc[2]);
-                acc[3] = fmaf(r[j], w.w, acc[3]);
+                const uint64_t rr = pair2(r[j], r[j]);
+                acc01 = fma2_f32(rr, pair2(w.x, w.y), acc01);
+                acc23 = fma2_f32(rr, pair2(w.z, w.w), acc23);
             }
         }
     }
+    float acc[4];
+    unpair2(acc01, acc[0], acc[1]);
+    unpair2(acc23, acc[2], acc[3]);
     if (valid) {
         const float bias = __ldg(reinterpret_cast<const float*>(p.offsets) + 256);
         float* out = reinterpret_cast<float*>(p.y);
