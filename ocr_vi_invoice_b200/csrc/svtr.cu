@@ -105,69 +105,53 @@ template <int kLnChunks>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         int64_t rows, int d, int x_ld, int y_ld, float eps) {
-    // two rows per half-warp and iteration (kLnChunks <= 3): twice the bytes in flight per thread -- the kernel is
-    // latency-bound, not issue-bound (ncu: long-scoreboard stalls, 3.9 TB/s with one row)
-    constexpr int kRows = kLnChunks <= 3 ? 2 : 1;
     const int sub = threadIdx.x & 15;
     const int chunks = d >> 3;
     const int64_t stride = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 4;
     const int64_t rows_pad = (rows + 1) & ~static_cast<int64_t>(1);  // both halves of a warp iterate together (shuffles)
-    for (int64_t r0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 4; r0 < rows_pad; r0 += kRows * stride) {
-        float v[kRows][kLnChunks][8];
-        float sum[kRows];
-        bool live[kRows];
+    for (int64_t r = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 4; r < rows_pad; r += stride) {
+        const bool live = r < rows;
+        const __nv_bfloat16* xr = x + (live ? r : 0) * x_ld;
+        float v[kLnChunks][8];
+        float sum = 0.0f;
 #pragma unroll
-        for (int q = 0; q < kRows; ++q) {
-            const int64_t r = r0 + q * stride;
-            live[q] = r < rows;
-            const __nv_bfloat16* xr = x + (live[q] ? r : 0) * x_ld;
-            sum[q] = 0.0f;
+        for (int k = 0; k < kLnChunks; ++k) {
+            const int c = sub + 16 * k;
+            if (c < chunks) {
+                unpack8_bf16(__ldg(reinterpret_cast<const uint4*>(xr) + c), v[k]);
 #pragma unroll
-            for (int k = 0; k < kLnChunks; ++k) {
-                const int c = sub + 16 * k;
-                if (c < chunks) unpack8_bf16(__ldg(reinterpret_cast<const uint4*>(xr) + c), v[q][k]);
+                for (int j = 0; j < 8; ++j) sum += v[k][j];
             }
         }
 #pragma unroll
-        for (int q = 0; q < kRows; ++q) {
+        for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mean = sum / static_cast<float>(d);
+        float sq = 0.0f;
 #pragma unroll
-            for (int k = 0; k < kLnChunks; ++k)
-                if (sub + 16 * k < chunks)
+        for (int k = 0; k < kLnChunks; ++k)
+            if (sub + 16 * k < chunks)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) sum[q] += v[q][k][j];
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) sum[q] += __shfl_xor_sync(0xffffffffu, sum[q], o);
-        }
-#pragma unroll
-        for (int q = 0; q < kRows; ++q) {
-            const float mean = sum[q] / static_cast<float>(d);
-            float sq = 0.0f;
-#pragma unroll
-            for (int k = 0; k < kLnChunks; ++k)
-                if (sub + 16 * k < chunks)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float t = v[q][k][j] - mean;
-                        sq = fmaf(t, t, sq);
-                    }
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-            const float rstd = rsqrtf(sq / static_cast<float>(d) + eps);
-            if (!live[q]) continue;
-            __nv_bfloat16* yr = y + (r0 + q * stride) * y_ld;
-#pragma unroll
-            for (int k = 0; k < kLnChunks; ++k) {
-                const int c = sub + 16 * k;
-                if (c < chunks) {
-                    float o8[8];
-                    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c + 1);
-                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c), b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c + 1);
-                    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-                    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) o8[j] = fmaf((v[q][k][j] - mean) * rstd, g[j], b[j]);
-                    *(reinterpret_cast<uint4*>(yr) + c) = pack8_bf16(o8);
+                for (int j = 0; j < 8; ++j) {
+                    const float t = v[k][j] - mean;
+                    sq = fmaf(t, t, sq);
                 }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        const float rstd = rsqrtf(sq / static_cast<float>(d) + eps);
+        if (!live) continue;
+        __nv_bfloat16* yr = y + r * y_ld;
+#pragma unroll
+        for (int k = 0; k < kLnChunks; ++k) {
+            const int c = sub + 16 * k;
+            if (c < chunks) {
+                float o8[8];
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c + 1);
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c), b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c + 1);
+                const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o8[j] = fmaf((v[k][j] - mean) * rstd, g[j], b[j]);
+                *(reinterpret_cast<uint4*>(yr) + c) = pack8_bf16(o8);
             }
         }
     }
