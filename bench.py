@@ -639,7 +639,10 @@ def main():
                 "components_per_image": int(post.fetch(post.run_device(pm, want_labels=False))[1].mean()),
                 "top_launches_ms": [[n, round(ms, 3)] for n, _, ms, _ in top],
                 "clocks": clocks}
-        line["next_rows"] = next_row_kernels(dev, pk["hbm_gbs"], cpu_leg=not args.no_cpu_baseline and world == 1)
+        try:  # auxiliary measurements of the rows after the detector: never lose the headline line over them
+            line["next_rows"] = next_row_kernels(dev, pk["hbm_gbs"], cpu_leg=not args.no_cpu_baseline and world == 1)
+        except Exception as e:  # noqa: BLE001
+            line["next_rows"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         if not args.no_cpu_baseline and world == 1:
             ips, cores, sec = cpu_reference_run(sd_cpu, steps=2, warmup=1)
             line["cpu_baseline"] = {"value": round(ips, 4), "unit": "images/s", "cores": cores, "kind": "port",
