@@ -283,3 +283,39 @@ def test_ocr_pipeline_page_to_text():
         x[:n] = torch.from_numpy(want).to(dev)
         lp = rec(x)
         assert rec.decode_probs(lp)[:n] == texts or rec.decode_probs(rec(ocr.cropper._buf["out"][:x.shape[0]]))[:n] == texts
+
+
+def test_ocr_pipeline_no_boxes():
+    """A page on which nothing passes box_thresh: no crops, no recogniser launch, empty lists (pipeline2.py:332-334)."""
+    from oracle import svtrv2_oracle as so
+    from oracle.weights import make_state_dict
+    from ocr_vi_invoice_b200.model.det.dbnet import DBNetPP
+    from ocr_vi_invoice_b200.model.rec2.svtrv2 import SVTRv2
+    from ocr_vi_invoice_b200.pipeline import OCRPipeline
+    from ocr_vi_invoice_b200.postprocess import DBPostProcessor
+    dev = torch.device(DEV, 0)
+    det = DBNetPP(pretrained=False)
+    det.load_state_dict(make_state_dict(seed=3, offset_px=0.5), strict=True)
+    rec = SVTRv2(variant="base")
+    rec.load_state_dict(so.make_state_dict("base", 5), strict=True)
+    post = DBPostProcessor(thresh=0.3, box_thresh=1.5, device=dev)  # a mean probability can never reach 1.5
+    ocr = OCRPipeline(det.to(dev).eval(), post, rec.to(dev).eval(), dev, det_size=128)
+    boxes, texts = ocr(torch.full((90, 120, 3), 255, dtype=torch.uint8, device=dev))
+    assert boxes == [] and texts == []
+
+
+@pytest.mark.parametrize("variant", ["tiny", "small", "base"])
+def test_reference_api_checks(variant):
+    """Mirror of the reference's tests/test_model.py:252-321 (test_svtrv2_forward inference half, test_svtrv2_decode):
+    default-initialised model, batch 4 of 32 x 256, (T, B, V) log-probabilities <= 0, decode_greedy gives B strings."""
+    from ocr_vi_invoice_b200.model.rec2.svtrv2 import SVTRv2
+    torch.manual_seed(0)
+    model = SVTRv2(variant=variant, in_channels=3, dropout=0.0).to(DEV)
+    model.eval()
+    x = torch.randn(4, 3, 32, 256, device=DEV)
+    with torch.no_grad():
+        log_probs = model(x)
+    assert log_probs.shape == (256 // 4, 4, model.tokenizer.num_classes)
+    assert log_probs.max() <= 0, "Log probs must be <= 0"
+    texts = model.decode_greedy(x[:2])
+    assert isinstance(texts, list) and len(texts) == 2 and all(isinstance(t, str) for t in texts)

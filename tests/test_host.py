@@ -149,3 +149,20 @@ def test_svtrv2_dropin_state_dict_matches_reference_key_set():
     import torch
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         model.eval()(torch.zeros(1, 3, 32, 256))
+
+
+def test_svtrv2_parameter_counts_like_reference_test():
+    """Mirror of the reference's tests/test_model.py:190-249 (test_svtrv2_parameters): per-component trainable parameter
+    counts of the three variants (numbers produced by the reference's own classes)."""
+    from ocr_vi_invoice_b200.model.rec2.svtrv2 import SVTRv2
+    count = lambda mod: sum(p.numel() for p in mod.parameters() if p.requires_grad)
+    want = {
+        "tiny": (6736656, 19584, [211776, 1214976, 2369280], [74112, 295680], 512, 1580288, 910824, 59624),
+        "small": (10893744, 43200, [391392, 2559744, 4738560], [166464, 443136], 512, 1580288, 910824, 59624),
+        "base": (22630864, 76032, [620160, 4510208, 10646784], [295680, 885888], 768, 3550080, 1955944, 89320),
+    }
+    for v, (total, stem, stages, merges, bnorm, frm, sgm, head) in want.items():
+        m = SVTRv2(variant=v, in_channels=3, dropout=0.0)
+        assert count(m) == total and count(m.stem) == stem
+        assert [count(s) for s in m.stages] == stages and [count(x) for x in m.merges] == merges
+        assert count(m.backbone_norm) == bnorm and count(m.frm) == frm and count(m.sgm) == sgm and count(m.head) == head
