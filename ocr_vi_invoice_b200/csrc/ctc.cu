@@ -42,10 +42,19 @@ __global__ void __launch_bounds__(kCtcThreads) ctc_greedy_kernel(const float* __
     for (int t = warp; t < T; t += kWarps) {
         const float* row = lp + t * stride_t + b * stride_b;
         Best best{-INFINITY, 0x7fffffff, false};
-        for (int c = lane; c < C; c += 32) {
-            const float v = __ldg(row + c);
-            const Best cand{v, c, isnan(v)};
-            if (beats(cand, best)) best = cand;
+        for (int c0 = 0; c0 < C; c0 += 256) {  // eight independent loads in flight per lane, then the compare chain
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int c = c0 + k * 32 + lane;
+                v[k] = c < C ? __ldg(row + c) : -INFINITY;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int c = c0 + k * 32 + lane;
+                const Best cand{v[k], c < C ? c : 0x7fffffff, isnan(v[k])};
+                if (beats(cand, best)) best = cand;
+            }
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
