@@ -561,6 +561,27 @@ def main():
         torch.cuda.synchronize()
         postproc_ms = ev[0].elapsed_time(ev[1]) / 3
         fg_frac = float((pm > 0.3).float().mean().item())
+        # the same kernels on text-like maps (random-init weights give an all-foreground map = one component, the slow case):
+        # probability 0.9 inside the text-line boxes of the synthetic invoices, 0.05 outside
+        text_ms, text_comps = None, None
+        try:
+            import numpy as np
+            from ocr_vi_invoice_b200.synth import synthetic_invoice
+            tm = np.full((b, H, W), 0.05, dtype=np.float32)
+            for i in range(b):
+                for (x0, y0, x1, y1) in synthetic_invoice(H, W, seed=i)[1]:
+                    tm[i, y0:y1, x0:x1] = 0.9
+            tmd = torch.from_numpy(tm).to(dev)
+            post.run_device(tmd, want_labels=False)
+            ev[0].record()
+            for _ in range(3):
+                tbuf = post.run_device(tmd, want_labels=False)
+            ev[1].record()
+            torch.cuda.synchronize()
+            text_ms = ev[0].elapsed_time(ev[1]) / 3
+            text_comps = float(post.fetch(tbuf)[1].mean())
+        except Exception:  # noqa: BLE001
+            pass
         info = model.plan_info(b, H, W, dev)
         pk = peaks()
         tot_ms = sum(l[2] for l in launches)
@@ -636,6 +657,9 @@ def main():
                 "roofline": roofline, "dcn": dcn_line, "hbm_bound_convs": hbm_line, "kernel_time_shares": shares,
                 "forward_ms_sum_of_launches": round(tot_ms, 3), "postproc_ms": round(postproc_ms, 3),
                 "postproc_gbs": round(b * H * W * 8 / (postproc_ms * 1e-3) / 1e9, 1), "prob_map_foreground_frac": round(fg_frac, 3),
+                "postproc_text_maps": {"ms": None if text_ms is None else round(text_ms, 3),
+                                       "components_per_image": text_comps,
+                                       "what": "same post-processing on maps rendered from the synthetic invoices' text-line boxes"},
                 "components_per_image": int(post.fetch(post.run_device(pm, want_labels=False))[1].mean()),
                 "top_launches_ms": [[n, round(ms, 3)] for n, _, ms, _ in top],
                 "clocks": clocks}
