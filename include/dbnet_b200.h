@@ -87,7 +87,8 @@ typedef struct b200_igemm_desc {
     int32_t shuf_c;        /* channels per sub-pixel for B200_EPI_SHUFFLE2                        */
     int32_t block_n;       /* 32, 64, 128 or 256; 0 = choose                                      */
     int32_t x_ld;          /* elements between consecutive input pixels; 0 = in_c (dense NHWC)    */
-    int32_t reserved1;
+    int32_t stride_w;      /* 0 = same as `stride`; 1 with stride == 2 = stride (2, 1): rows halved, width kept
+                              (PatchMerging of the recogniser, model/rec2/svtrv2.py:128); CONV mode, 3x3 only  */
     const void*  x;        /* input activations, NHWC bf16                                        */
     const void*  w;        /* weights [n_pad][taps*in_c] bf16, K order (tap, cin)                 */
     const float* scale;    /* [n_pad] per-column multiplier (folded BN gamma/sqrt(var+eps)), or 1 */

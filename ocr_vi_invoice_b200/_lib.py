@@ -25,7 +25,7 @@ class IgemmDesc(C.Structure):
         ("mode", C.c_int32), ("batch", C.c_int32), ("in_h", C.c_int32), ("in_w", C.c_int32),
         ("in_c", C.c_int32), ("out_c", C.c_int32), ("n_pad", C.c_int32), ("ksize", C.c_int32),
         ("stride", C.c_int32), ("flags", C.c_int32), ("out_ld", C.c_int32), ("res_ld", C.c_int32),
-        ("shuf_c", C.c_int32), ("block_n", C.c_int32), ("x_ld", C.c_int32), ("reserved1", C.c_int32),
+        ("shuf_c", C.c_int32), ("block_n", C.c_int32), ("x_ld", C.c_int32), ("stride_w", C.c_int32),
         ("x", C.c_void_p), ("w", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
         ("residual", C.c_void_p), ("y", C.c_void_p), ("offsets", C.c_void_p),
     ]

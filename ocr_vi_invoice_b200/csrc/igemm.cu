@@ -55,6 +55,7 @@ __host__ __device__ constexpr int base_warps(bool gather) { return kEpiWarp0 + 4
 struct IgemmParams {
     int mode, batch, in_h, in_w, in_c, out_h, out_w, out_c;
     int ksize, stride, flags, block_n;
+    int stride_w;  // column stride (== stride except for the (2, 1) PatchMerging conv)
     int tile_w, tile_h, tiles_x, tiles_y;
     int num_n_blocks, num_tiles, k_blocks, cchunks;
     int out_ld, res_ld, shuf_c;
@@ -437,8 +438,10 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
             tma_prefetch_desc(&tm.a[0]);
             if (p.stride == 2 && p.ksize == 3) {
                 tma_prefetch_desc(&tm.a[1]);
-                tma_prefetch_desc(&tm.a[2]);
-                tma_prefetch_desc(&tm.a[3]);
+                if (p.stride_w == 2) {
+                    tma_prefetch_desc(&tm.a[2]);
+                    tma_prefetch_desc(&tm.a[3]);
+                }
             }
         }
         if (p.epi_tma) tma_prefetch_desc(&tm.out[0]);
@@ -554,6 +557,11 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                             if (p.stride == 1) {
                                 ax += kx - 1;
                                 ay += ky - 1;
+                            } else if (p.stride_w == 1) {
+                                // stride (2, 1): input pixel (2*oy + ky - 1, ox + kx - 1) on the row-parity view
+                                view = (ky + 1) & 1;
+                                ax += kx - 1;
+                                ay += (ky == 0) ? -1 : 0;
                             } else {
                                 // input pixel (2*oy + ky - 1, 2*ox + kx - 1) on the (row parity, column parity) view
                                 view = (((ky + 1) & 1) << 1) | ((kx + 1) & 1);
@@ -1098,6 +1106,9 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     if (!d->x || !d->w || !d->scale || !d->shift || !d->y) return set_error("igemm: null tensor pointer");
     if (d->out_c <= 0 || (d->out_c % 8) != 0) return set_error("igemm: out_c must be a positive multiple of 8");
     if (d->stride != 1 && d->stride != 2) return set_error("igemm: stride must be 1 or 2");
+    const int stride_w = d->stride_w ? d->stride_w : d->stride;
+    if (stride_w != d->stride && !(d->stride == 2 && stride_w == 1 && d->mode == B200_IGEMM_CONV && d->ksize == 3))
+        return set_error("igemm: stride_w is for the 3x3 stride (2, 1) convolution only");
     int taps;
     if (d->mode == B200_IGEMM_STEM) {
         if (d->ksize != 7 || d->stride != 2 || (d->in_h & 1) || (d->in_w & 1))
@@ -1107,7 +1118,7 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
         if (d->ksize != 1 && d->ksize != 3) return set_error("igemm: ksize must be 1 or 3");
         if (d->mode == B200_IGEMM_DCN && d->ksize != 3) return set_error("igemm: DCN is 3x3");
         if (d->in_c <= 0 || (d->in_c % 64) != 0) return set_error("igemm: in_c must be a multiple of 64");
-        if (d->stride == 2 && ((d->in_h & 1) || (d->in_w & 1)))
+        if (d->stride == 2 && ((d->in_h & 1) || (stride_w == 2 && (d->in_w & 1))))
             return set_error("igemm: stride 2 needs even input size");
         taps = d->ksize * d->ksize;
     }
@@ -1158,7 +1169,8 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     p.in_c = d->in_c;
     p.x_ld = x_ld;
     p.out_h = d->in_h / d->stride;
-    p.out_w = d->in_w / d->stride;
+    p.out_w = d->in_w / stride_w;
+    p.stride_w = stride_w;
     p.out_c = d->out_c;
     p.ksize = d->ksize;
     p.stride = d->stride;
@@ -1350,6 +1362,13 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
         if (d->stride == 1) {
             err |= encode_nhwc(&op->tm.a[0], d->x, C, W, H, d->batch, LD, 1, 1, W, H * W, p.tile_w,
                                share ? p.tile_h + 2 : p.tile_h, "activations");
+        } else if (stride_w == 1) {
+            // stride (2, 1): two row-parity views, full width
+            for (int v = 0; v < 2 && !err; ++v) {
+                const char* base = reinterpret_cast<const char*>(d->x) + (uint64_t)v * W * LD * 2;
+                err |= encode_nhwc(&op->tm.a[v], base, C, W, H / 2, d->batch, LD, 1, 2, W, H * W, p.tile_w, p.tile_h,
+                                   "row-strided activations");
+            }
         } else {
             // stride 2: four (row parity, column parity) strided views of the NHWC tensor
             const int nviews = (d->ksize == 3) ? 4 : 1;

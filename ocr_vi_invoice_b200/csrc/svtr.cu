@@ -9,7 +9,8 @@
 //   gelu_kernel           nn.GELU, exact erf form (:33,51,54,114,117)
 //   mhsa_kernel           softmax(q k^T * scale) v per (sequence, head), head_dim 32 (:79-86, :208-215)
 //   frm_select_kernel     FRM vertical cross-attention of the selecting token over the H rows of a column (:236-243)
-//   decimate_rows_kernel  PatchMerging's stride (2, 1): the rows 0, 2, 4, .. of a stride-1 conv output (:128,135)
+//   decimate_rows_kernel  rows 0, 2, 4, .. of an NHWC map (the first PatchMerging path; the plan now uses the GEMM kernel's
+//                         stride (2, 1) mode, the entry point stays for callers that hold a stride-1 output)
 //   log_softmax_tbc       F.log_softmax over classes + the (B, T, C) -> (T, B, C) permute (:536-537)
 // First correct path: CUDA-core attention (fp32 accumulate, K / V of one head resident in shared memory as fp32); moving it
 // to tcgen05 is the next step for this row.

@@ -239,15 +239,15 @@ class _Plan:
             self.steps.append(fn)
             self.names.append(name)
 
-        def gemm(name, key, x, y, *, rows=None, geom=None, in_c, out_c, ksize=1, stride=1, flags=0, residual=None):
+        def gemm(name, key, x, y, *, rows=None, geom=None, in_c, out_c, ksize=1, stride=1, stride_w=0, flags=0, residual=None):
             """rows: token-matrix Linear (image = 1 x rows/64 x 64); geom = (batch, h, w): a real convolution."""
             w, s, t = W.G[key]
             if geom is None:
                 assert rows % 128 == 0
                 geom = (1, rows // 64, 64)  # any factorisation works for a 1x1 conv; 2 rows x 64 tokens = one 128-row tile
             op = ops.Igemm(ops.IGEMM_CONV, x, w, s, t, y, batch=geom[0], in_h=geom[1], in_w=geom[2], in_c=in_c, out_c=out_c,
-                           ksize=ksize, stride=stride, flags=flags, residual=residual, res_ld=out_c if residual is not None else 0,
-                           name=name)
+                           ksize=ksize, stride=stride, stride_w=stride_w, flags=flags, residual=residual,
+                           res_ld=out_c if residual is not None else 0, name=name)
             self.flops += op.flops
             add(name, op)
 
@@ -289,12 +289,10 @@ class _Plan:
                 gemm(p + ".fc2", p + ".fc2", hid, other, rows=rows, in_c=hidw, out_c=d, flags=ops.EPI_RES, residual=x)
                 x, other = other, x
             self.taps[f"stage{si}"] = (x, len(self.steps), real[si])
-            if si < 2:  # PatchMerging: stride-1 3x3 conv + BN, then every second row
+            if si < 2:  # PatchMerging: 3x3 conv with stride (2, 1) + BN (two row-parity TMA views, full width)
                 dn = dims[si + 1]
-                full = bf(b, h, w, dn)
-                gemm(f"merges.{si}", f"merges.{si}", x, full, geom=(b, h, w), in_c=d, out_c=dn, ksize=3)
                 nx = bf(b, h // 2, w, dn)
-                add(f"merges.{si}.rows", lambda f=full, y=nx, hh=h, ww=w, c=dn: ops.decimate_rows(f, y, b, hh, ww, c))
+                gemm(f"merges.{si}", f"merges.{si}", x, nx, geom=(b, h, w), in_c=d, out_c=dn, ksize=3, stride=2, stride_w=1)
                 x, h = nx, h // 2
         d = dims[2]
         rows = b * h * w

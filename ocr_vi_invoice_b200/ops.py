@@ -102,7 +102,7 @@ class Igemm:
                  y: torch.Tensor, *, batch: int, in_h: int, in_w: int, in_c: int, out_c: int, ksize: int,
                  stride: int, flags: int = 0, residual: Optional[torch.Tensor] = None,
                  offsets: Optional[torch.Tensor] = None, out_ld: Optional[int] = None, res_ld: int = 0,
-                 shuf_c: int = 0, block_n: int = 0, x_ld: int = 0, name: str = ""):
+                 shuf_c: int = 0, block_n: int = 0, x_ld: int = 0, stride_w: int = 0, name: str = ""):
         lib = _lib.load()
         self.name = name
         self._keep = (x, w, scale, shift, y, residual, offsets)
@@ -114,13 +114,14 @@ class Igemm:
         d = _lib.IgemmDesc(
             mode=mode, batch=batch, in_h=in_h, in_w=in_w, in_c=in_c, out_c=out_c, n_pad=n_pad, ksize=ksize,
             stride=stride, flags=flags, out_ld=out_ld, res_ld=res_ld, shuf_c=shuf_c, block_n=block_n, x_ld=x_ld,
+            stride_w=stride_w,
             x=_lib.ptr(x), w=_lib.ptr(w), scale=_lib.ptr(scale), shift=_lib.ptr(shift),
             residual=_lib.ptr(residual), y=_lib.ptr(y), offsets=_lib.ptr(offsets))
         h = C.c_void_p()
         _lib.check(lib.b200_igemm_create(C.byref(d), C.byref(h)), f"igemm_create({name})")
         self._h = h
         self._lib = lib
-        self.flops = 2.0 * batch * (in_h // stride) * (in_w // stride) * out_c * w.shape[1]
+        self.flops = 2.0 * batch * (in_h // stride) * (in_w // (stride_w or stride)) * out_c * w.shape[1]
 
     def info(self) -> dict:
         vals = [C.c_int32() for _ in range(7)]

@@ -155,6 +155,24 @@ def test_gelu_epilogue_conv_and_linear():
         assert _rel(y.cpu(), ref) < 4e-3, (cin, cout, stride)
 
 
+def test_conv_stride_2_1():
+    """PatchMerging's 3x3 conv with stride (2, 1) (two row-parity TMA views) vs torch, 128 -> 256 and 256 -> 384 channels."""
+    from ocr_vi_invoice_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    for cin, cout, hh, ww in ((128, 256, 8, 64), (256, 384, 4, 64), (64, 128, 16, 32)):
+        b = 3
+        xi = _bf(torch.randn(b, hh, ww, cin, generator=g)).to(DEV)
+        wt = torch.randn(cout, cin, 3, 3, generator=g) * (cin * 9) ** -0.5
+        sc, sh = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.3
+        w = ops.pack_conv_weight(wt.to(DEV))
+        y = torch.full((b, hh // 2, ww, cout), 7.0, dtype=torch.bfloat16, device=DEV)
+        ops.Igemm(ops.IGEMM_CONV, xi, w, ops.pad_vec(sc.to(DEV), w.shape[0], 1.0), ops.pad_vec(sh.to(DEV), w.shape[0]), y, batch=b,
+                  in_h=hh, in_w=ww, in_c=cin, out_c=cout, ksize=3, stride=2, stride_w=1)()
+        ref = F.conv2d(xi.float().cpu().permute(0, 3, 1, 2), _bf(wt).float(), None, (2, 1), 1)
+        ref = (ref * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)).permute(0, 2, 3, 1)
+        assert _rel(y.cpu(), ref) < 4e-3, (cin, cout)
+
+
 def _golden_model():
     from oracle import svtrv2_oracle as so
     from ocr_vi_invoice_b200.model.rec2.svtrv2 import SVTRv2
