@@ -325,7 +325,6 @@ class _Plan:
         nc = W.num_classes
         self.ld = (nc + 7) // 8 * 8
         self.logits = torch.empty(trows, self.ld, device=dev, dtype=torch.float32)
-        w_head = W.G["head"][0]
         op = ops.Igemm(ops.IGEMM_CONV, t2, *W.G["head"], self.logits, batch=1, in_h=trows // 64, in_w=64, in_c=d, out_c=self.ld,
                        ksize=1, stride=1, flags=ops.EPI_OUT_F32, name="head")
         self.flops += op.flops
