@@ -104,7 +104,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_run(state_dict, steps, warmup, sample_hw=(1024, 1024), k=50.0):
+def cpu_reference_run(state_dict, steps, warmup, sample_hw=(1024, 1024), k=50.0, budget_s=0.0):
     """The reference's CPU implementation of the path, timed: fp32 torch + torchvision.ops.deform_conv2d forward
     (oracle/dbnet_oracle.py restates model/det/*.py; the deformable op is the installed third-party one the
     reference calls) + the CPU post-processing restatement.  One synthetic image per step."""
@@ -122,15 +122,21 @@ def cpu_reference_run(state_dict, steps, warmup, sample_hw=(1024, 1024), k=50.0)
         deform = None
     x = torch.from_numpy(synthetic_batch(1, sample_hw[0], sample_hw[1], seed=7))
     times = []
+    t_start = time.perf_counter()
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         out = dbo.dbnet_forward(state_dict, x, k=k, deform=deform)
         ppo.postprocess(out["binary"][0, 0].numpy(), 0.3, 0.5, 1000, 1.6, 10)
+        dt = time.perf_counter() - t0
         if i >= warmup:
-            times.append(time.perf_counter() - t0)
+            times.append(dt)
+        # the whole run must end within a few minutes whatever the host: stop early (never before one timed step) if
+        # the next step would cross the budget; the caller reports the steps actually timed
+        if budget_s and times and (time.perf_counter() - t_start) + dt > budget_s:
+            break
     scale = (sample_hw[0] * sample_hw[1]) / float(H * W)
     ips = len(times) / sum(times) * scale  # images/sec in 1024^2-image units
-    return ips, cores, sum(times) / len(times)
+    return ips, cores, sum(times) / len(times), len(times)
 
 
 def next_row_kernels(dev, peak_gbs, cpu_leg=False):
@@ -430,9 +436,11 @@ def main():
         from ocr_vi_invoice_b200.model.det.dbnet import DBNetPP
         model = randomize_(DBNetPP(pretrained=False), 0).eval()
         sd = {k: v.detach() for k, v in model.state_dict().items()}
-        steps = max(1, min(args.steps, 5))
-        warm = min(args.warmup, 1)
-        ips, cores, sec = cpu_reference_run(sd, steps, warm)
+        # exactly --steps K after --warmup W, one synthetic 1024x1024 image per step (a bounded sample of the 16-image
+        # batch: ~2.5 s on 16 host cores, so the default K = 20, W = 5 ends in about a minute); a slower host stops at
+        # a 240 s budget and reports the steps it timed
+        warm = max(0, args.warmup)
+        ips, cores, sec, steps = cpu_reference_run(sd, max(1, args.steps), warm, budget_s=240.0)
         line = {"impl": "reference", "metric": "images/sec", "value": round(ips, 4), "unit": "images/s",
                 "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": round(sec * 1e3, 2),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
@@ -539,7 +547,7 @@ def main():
     if rank == 0:
         sampler.start()
     dev_ms, _, _ = timed(step_device, args.steps)
-    detector = Detector(model, post, dev, use_cuda_graph=not args.no_graph)  # switches the model to ('binary',)
+    detector = Detector(model, post, dev, use_cuda_graph=not args.no_graph)  # runs the model with want=('binary',) per call
     run_e2e(2)
     _, e2e_ms, recs = timed(lambda: run_e2e(args.steps), 1)  # wall clock: includes host-side work of the API
     run_e2e(2, host_u8)
@@ -668,7 +676,7 @@ def main():
         except Exception as e:  # noqa: BLE001
             line["next_rows"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         if not args.no_cpu_baseline and world == 1:
-            ips, cores, sec = cpu_reference_run(sd_cpu, steps=2, warmup=1)
+            ips, cores, sec, _ = cpu_reference_run(sd_cpu, steps=2, warmup=1)
             line["cpu_baseline"] = {"value": round(ips, 4), "unit": "images/s", "cores": cores, "kind": "port",
                                     "sample": "2 timed steps of 1 synthetic 1024x1024 image (after 1 warm-up): fp32 torch "
                                               "CPU forward (oracle restatement + torchvision deform_conv2d) + CPU "

@@ -90,7 +90,9 @@ typedef struct b200_igemm_desc {
     int32_t stride_w;      /* 0 = same as `stride`; 1 with stride == 2 = stride (2, 1): rows halved, width kept
                               (PatchMerging of the recogniser, model/rec2/svtrv2.py:128); CONV mode, 3x3 only  */
     const void*  x;        /* input activations, NHWC bf16                                        */
-    const void*  w;        /* weights [n_pad][taps*in_c] bf16, K order (tap, cin)                 */
+    const void*  w;        /* weights [n_pad][taps*in_c] bf16, K order (64-channel chunk, tap, channel in chunk),
+                              i.e. [n_pad][in_c/64][taps][64] -- what ops.pack_conv_weight() produces (STEM: see
+                              ops.pack_stem_weight; DCN v2 launches: ops.pack_dcn_weight)                    */
     const float* scale;    /* [n_pad] per-column multiplier (folded BN gamma/sqrt(var+eps)), or 1 */
     const float* shift;    /* [n_pad] per-column addend (folded BN beta-mean*scale, or bias)      */
     const void*  residual; /* NHWC bf16 or NULL                                                   */

@@ -529,23 +529,19 @@ extern "C" int b200_mhsa(const void* qkv, void* out, int n_seq, int n, int d, fl
     if (n_seq > 65535) return set_error("b200_mhsa: at most 65535 sequences per launch");
     if ((n % 16) == 0 && !getenv("B200_MHSA_SIMT")) {  // tensor-core path
         const int smem_mma = (n * kKStride + 32 * (n + 8)) * 2;
-        static int configured_mma = 0;
-        if (smem_mma > 48 * 1024 && smem_mma > configured_mma) {
-            if (check_cuda(cudaFuncSetAttribute(mhsa_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (768 * kKStride + 32 * 776) * 2),
-                           "b200_mhsa smem opt-in")) return 1;
-            configured_mma = (768 * kKStride + 32 * 776) * 2;
-        }
+        // the opt-in is per device (and per function): set it on every call that needs it, like b200_igemm_create does --
+        // a process-wide flag would leave the second GPU of a two-device process without it
+        if (smem_mma > 48 * 1024 &&
+            check_cuda(cudaFuncSetAttribute(mhsa_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (768 * kKStride + 32 * 776) * 2),
+                       "b200_mhsa smem opt-in")) return 1;
         const int warps = n / 16 < 8 ? n / 16 : 8;  // 8 warps x 84 registers: three blocks per SM hide the mma / exp latencies
         mhsa_mma_kernel<<<dim3(d / 32, n_seq), warps * 32, smem_mma, ST(stream)>>>(
             reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), n, d, scale * 1.4426950408889634f);
         return check_cuda(cudaGetLastError(), "b200_mhsa launch");
     }
     const int smem = n * 64 * static_cast<int>(sizeof(float));
-    static int configured = 0;
-    if (smem > configured) {
-        if (check_cuda(cudaFuncSetAttribute(mhsa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 768 * 64 * 4), "b200_mhsa smem opt-in")) return 1;
-        configured = 768 * 64 * 4;
-    }
+    if (smem > 48 * 1024 &&
+        check_cuda(cudaFuncSetAttribute(mhsa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 768 * 64 * 4), "b200_mhsa smem opt-in")) return 1;
     const int threads = n < 128 ? ((n + 31) / 32) * 32 : 128;
     dim3 grid((n + threads - 1) / threads, d / 32, n_seq);
     mhsa_kernel<<<grid, threads, smem, ST(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), n, d, scale);

@@ -77,9 +77,13 @@ class ResNet(nn.Module):
         if in_channels != 3:
             raise NotImplementedError("B200 DBNet++ path: the stem kernel is specialised for 3 input channels")
         if pretrained:
-            raise RuntimeError(
-                "pretrained=True would download ImageNet weights (model/det/backbone.py:17); there is no network "
-                "here -- construct with pretrained=False and load a checkpoint with load_state_dict")
+            # model/det/backbone.py:17 would download torchvision's ImageNet weights here.  The reference's own callers
+            # build DBNetPP() with this default and then load a checkpoint (src/det/val.py:147-150), so the drop-in must
+            # construct: warn, keep the random init (no network, nothing is downloaded) and expect load_state_dict.
+            import warnings
+            warnings.warn("B200 DBNet++ path: pretrained=True does not download ImageNet weights (no network access); "
+                          "the backbone keeps its random init until load_state_dict() is called", RuntimeWarning,
+                          stacklevel=3)
         self.model = _ResNet50()
         self.out_channels = [256, 512, 1024, 2048]
         self.dcn = bool(dcn)

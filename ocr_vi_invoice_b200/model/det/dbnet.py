@@ -70,11 +70,18 @@ class DBNetPP(nn.Module):
 
     @torch.no_grad()
     def forward(self, x):
+        return self.run(x, want=self.output_maps, use_graph=self.use_cuda_graph)
+
+    @torch.no_grad()
+    def run(self, x, want=MAP_NAMES, use_graph: bool = False):
+        """forward() with the two execution options passed per call (what pipeline.Detector uses, so that wrapping a
+        model never changes what a later plain `model(x)` returns): `want` restricts the maps written, `use_graph`
+        replays the captured launch list (the outputs then alias plan-owned buffers the next call overwrites)."""
         self._check_input(x)
         with torch.cuda.device(x.device):
             plan = self._get_plan(x)
             xin = x.contiguous() if x.dtype == torch.uint8 else x.float().contiguous()
-            return plan.run(xin, want=self.output_maps, use_graph=self.use_cuda_graph)
+            return plan.run(xin, want=tuple(want), use_graph=use_graph)
 
     @torch.no_grad()
     def forward_with_taps(self, x):

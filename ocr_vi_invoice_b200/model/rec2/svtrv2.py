@@ -400,6 +400,12 @@ class SVTRv2(nn.Module):
 
     @torch.no_grad()
     def forward(self, x, targets=None):
+        return self.run(x, targets, use_graph=self.use_cuda_graph)
+
+    @torch.no_grad()
+    def run(self, x, targets=None, use_graph: bool = False):
+        """forward() with the graph option passed per call (pipeline.OCRPipeline uses it; the module's own
+        use_cuda_graph attribute is what a plain model(x) follows)."""
         if targets is not None or self.training:
             raise RuntimeError("B200 SVTRv2 path is inference-only: call model.eval() and pass no targets "
                                "(the SGM branch and training, src/rec2/train.py, are out of scope)")
@@ -410,13 +416,28 @@ class SVTRv2(nn.Module):
         if x.shape[2] % 32 or x.shape[3] % 128 or x.shape[2] > 256 or x.shape[3] > 2048:
             raise ValueError("B200 SVTRv2 path: crops must be (3, H, W) with H a multiple of 32 and W a multiple of 128 "
                              "(the pipeline's 32 x 256): whole 128-token tiles at every stage")
+        self._check_attention_lengths(x.shape[2], x.shape[3])
         with torch.cuda.device(x.device):
-            lp = self._plan(x).run(x.float().contiguous(), use_graph=self.use_cuda_graph)
-            return lp if self.use_cuda_graph else lp.clone()
+            lp = self._plan(x).run(x.float().contiguous(), use_graph=use_graph)
+            return lp if use_graph else lp.clone()
+
+    MAX_ATTENTION_TOKENS = 768  # b200_mhsa keeps K / V of one (sequence, head) in shared memory
+
+    def _check_attention_lengths(self, H: int, W: int) -> None:
+        """Reject crop sizes whose attention sequences b200_mhsa cannot hold BEFORE any plan / buffer is built
+        (stage i attends over its whole (H / 4 / 2^i) x (W / 4) token map in the blocks after the first num_local)."""
+        for si in range(3):
+            n = (H // (4 << si)) * (W // 4)
+            if self.cfg["num_blocks"][si] > self.cfg["num_local"][si] and n > self.MAX_ATTENTION_TOKENS:
+                raise ValueError(f"B200 SVTRv2 path: a {H} x {W} crop gives stage {si} global attention over {n} tokens; "
+                                 f"the attention kernel holds at most {self.MAX_ATTENTION_TOKENS} (e.g. 32 x 768 or 64 x 384)")
+        if W // 4 > self.MAX_ATTENTION_TOKENS:
+            raise ValueError(f"B200 SVTRv2 path: the FRM's row attention over {W // 4} tokens exceeds {self.MAX_ATTENTION_TOKENS}")
 
     @torch.no_grad()
     def forward_with_taps(self, x):
         """forward + (B, N, D) fp32 copies of the stage outputs, for the parity tests."""
+        self._check_attention_lengths(x.shape[2], x.shape[3])
         with torch.cuda.device(x.device):
             taps = {}
             lp = self._plan(x).run(x.float().contiguous(), taps).clone()

@@ -217,12 +217,19 @@ def postproc_workspace_bytes(batch: int, h: int, w: int, max_candidates: int) ->
     return n
 
 
+def _min_area_threshold(min_area) -> int:
+    """The reference drops a box when `area < min_area` with a FLOAT min_area (pipeline2.py --det_min_area type=float,
+    test.py:81); box areas here are integers, so `area >= min_area` is `area >= ceil(min_area)` (10.5 drops area 10)."""
+    import math
+    return max(0, int(math.ceil(float(min_area))))
+
+
 def postproc(prob, labels, boxes, counts, ncomp, workspace, batch, h, w, thresh, box_thresh, unclip_ratio, min_area,
              max_candidates) -> None:
     _lib.check(_lib.load().b200_postproc(_lib.ptr(prob), _lib.ptr(labels), _lib.ptr(boxes), _lib.ptr(counts),
                                          _lib.ptr(ncomp), _lib.ptr(workspace), workspace.numel() * workspace.element_size(),
                                          batch, h, w, float(thresh), float(box_thresh), float(unclip_ratio),
-                                         int(min_area), int(max_candidates), _lib.current_stream()), "postproc")
+                                         _min_area_threshold(min_area), int(max_candidates), _lib.current_stream()), "postproc")
 
 
 def _rec_images(pages, scales):

@@ -57,8 +57,10 @@ class Detector:
         if self.device.type != "cuda":
             raise RuntimeError("Detector needs a CUDA device (no CPU fallback)")
         self.model, self.post = model, post
-        model.use_cuda_graph = use_cuda_graph
-        model.output_maps = ("binary",)  # the box list only needs the probability map (pipeline2.py:318)
+        # per-call options (DBNetPP.run): the caller's module keeps its own use_cuda_graph / output_maps, so a later
+        # plain model(x) still returns the five-key dict of the reference forward
+        self.use_cuda_graph = bool(use_cuda_graph)
+        self.want = ("binary",)  # the box list only needs the probability map (pipeline2.py:318)
         self._copy_stream = torch.cuda.Stream(device=self.device)
         self._dev_buf = [None, None]
         self._consumed = [None, None]  # per slot: event after which the main stream no longer reads the slot
@@ -89,7 +91,7 @@ class Detector:
             cropper = self._cropper = getattr(self, "_cropper", None) or RecognitionCropper(device=self.device)
         with torch.cuda.device(self.device):
             resized, scales = resize_image_for_det(page, image_size)
-            out = self.model(resized[None])
+            out = self.model.run(resized[None], want=self.want, use_graph=self.use_cuda_graph)
             det = self.post.run_device(out["binary"][:, 0], want_labels=False)
             crops = cropper.from_detector(det, [page], [scales], int(self.post.max_candidates))
         return crops, det
@@ -114,7 +116,7 @@ class Detector:
             while cur is not None:
                 x, ready = cur
                 main.wait_event(ready)
-                out = self.model(x)  # copies x into the plan's input buffer, then replays the captured graph
+                out = self.model.run(x, want=self.want, use_graph=self.use_cuda_graph)  # copies x into the plan's input buffer, then replays the captured graph
                 ev = torch.cuda.Event()
                 ev.record(main)
                 self._consumed[slot] = ev
@@ -145,8 +147,8 @@ class OCRPipeline:
     def __init__(self, det_model: DBNetPP, post: DBPostProcessor, rec_model, device=None, det_size: int = 640,
                  rec_size: Tuple[int, int] = (32, 256), rec_bucket: int = 32, capacity: int = 1024):
         self.detector = Detector(det_model, post, device, use_cuda_graph=False)
-        self.rec_model = rec_model
-        rec_model.use_cuda_graph = True  # one captured graph per batch bucket; the strings are read before the next call
+        self.rec_model = rec_model  # run with use_graph=True per call: one captured graph per batch bucket, the strings
+                                    # are read before the next call (the caller's module attributes are left alone)
         self.det_size = det_size
         self.rec_bucket = int(rec_bucket)
         self.cropper = RecognitionCropper(rec_size, capacity=capacity, device=self.detector.device)
@@ -170,5 +172,5 @@ class OCRPipeline:
         # the recogniser's plan is keyed by batch size: round the batch up to a bucket (slots past n hold stale crops
         # of the capacity buffer; their strings are dropped)
         nb = min(-(-n // self.rec_bucket) * self.rec_bucket, self.cropper.capacity)
-        texts = self.rec_model.decode_probs(self.rec_model(crops["out"][:nb]))[:n]
+        texts = self.rec_model.decode_probs(self.rec_model.run(crops["out"][:nb], use_graph=True))[:n]
         return boxes, texts

@@ -290,8 +290,10 @@ def test_detector_stream_matches_direct_calls():
         for (ba, sa), (bb, sb) in zip(a, b):
             assert len(ba) == len(bb) and sa == sb
             assert all(np.array_equal(x, y) for x, y in zip(ba, bb))
-    m.use_cuda_graph = False
-    m.output_maps = ("binary", "thresh", "thresh_binary", "bin_logits", "thresh_logits")
+    # wrapping the model in a Detector leaves the module's own forward contract alone (five keys, fresh tensors)
+    assert m.use_cuda_graph is False
+    again = m(batches[0].cuda())
+    assert set(again) == {"binary", "thresh", "thresh_binary", "bin_logits", "thresh_logits"}
 
 
 def test_uint8_input_matches_host_normalisation():

@@ -46,6 +46,17 @@ def test_rendered_maps_bit_exact(seed):
     assert sum(len(r) for r in recs) > 30
 
 
+def test_fractional_min_area_like_reference():
+    """pipeline2.py passes --det_min_area as a float: 10.5 must drop a box of area 10 (test.py:81 `area < min_area`)."""
+    from oracle import postproc_oracle as ppo
+    prob = np.zeros((64, 96), np.float32)
+    prob[10:13, 10:16] = 0.9    # 6 x 3 pixels: (w-1)(h-1) = 10
+    prob[30:34, 30:40] = 0.9    # 10 x 4 pixels: area 27
+    r10 = _assert_same(prob, min_area=10, box_thresh=0.5)
+    r105 = _assert_same(prob, min_area=10.5, box_thresh=0.5)
+    assert len(r10[0]) == 2 and len(r105[0]) == 1
+
+
 def test_edge_cases_bit_exact():
     rng = np.random.default_rng(0)
     _assert_same(np.zeros((64, 96), np.float32))                                   # empty map

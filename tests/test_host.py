@@ -44,8 +44,9 @@ def test_rejections(model):
         DBNetPP(backbone="resnet18", pretrained=False)
     with pytest.raises(NotImplementedError):
         DBNetPP(backbone="resnet101", pretrained=False)                              # backbone.py:21 raises too
-    with pytest.raises(RuntimeError, match="no network"):
-        DBNetPP()                                                                    # pretrained=True default
+    with pytest.warns(RuntimeWarning, match="does not download"):
+        m = DBNetPP()                                                                # pretrained=True default: val.py:147
+    assert len(m.state_dict()) == 754                                                # constructs, then load_state_dict
     model.eval()
     with pytest.raises(RuntimeError, match="CUDA only"):
         model(torch.zeros(1, 3, 64, 64))

@@ -81,3 +81,4 @@ def test_bench_reference_arm_contract():
     assert line["impl"] == "reference" and line["metric"] == "images/sec" and line["unit"] == "images/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["n_gpus"] == 2
+    assert line["steps"] == 1 and line["warmup"] == 0  # the arm times exactly --steps K after --warmup W
