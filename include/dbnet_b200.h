@@ -40,7 +40,12 @@ enum {
     B200_IGEMM_CONV = 0, /* 1x1 / 3x3, stride 1 or 2, zero padding (k-1)/2; A operand by TMA     */
     B200_IGEMM_STEM = 1, /* 7x7 s2 p3 conv on the space-to-depth buffer of b200_stem_pack; A rows
                             (128 contiguous bytes each) copied by producer warps                 */
-    B200_IGEMM_DCN  = 2  /* modulated deformable conv v2, 3x3; A operand gathered + blended      */
+    B200_IGEMM_DCN  = 2, /* modulated deformable conv v2, 3x3; A operand gathered + blended      */
+    B200_IGEMM_DCN_TMEM = 3 /* the same operator for layers with out_c == n_pad in {128, 256} (ResNet-50 c3 / c4):
+                            sampled A operand written to tensor memory (tcgen05.st) and read by tcgen05.mma
+                            from there, sampling records staged by TMA.  The weights must be packed with the
+                            K permutation of ops.pack_dcn_weight (inside each 64-channel chunk, K position
+                            16j + 4m + r holds channel 32(j>>1) + 8m + 4(j&1) + r); flags: RELU only       */
 };
 
 enum {

@@ -12,7 +12,7 @@ from pathlib import Path
 
 _LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libdbnet_b200.so"
 
-IGEMM_CONV, IGEMM_STEM, IGEMM_DCN = 0, 1, 2
+IGEMM_CONV, IGEMM_STEM, IGEMM_DCN, IGEMM_DCN_TMEM = 0, 1, 2, 3
 EPI_RELU, EPI_RES, EPI_RES_UP2, EPI_OUT_F32, EPI_SHUFFLE2, EPI_DCN_COORDS, EPI_HEAD_DOT, EPI_GELU = 1, 2, 4, 8, 16, 32, 64, 128
 
 

@@ -63,6 +63,16 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// ---------------------------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the
+// stream is still running: everything before pdl_wait() (barrier init, TMEM allocation, descriptor prefetch, staging of
+// constant parameters) overlaps the predecessor's tail; pdl_wait() returns once the predecessor has completed and its
+// writes are visible.  pdl_launch_dependents() lets the NEXT kernel's blocks be scheduled as soon as every block of
+// this grid has issued it (they still wait in their own pdl_wait() for this grid to finish).  Both are no-ops in a
+// launch without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------- proxies / fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -51,7 +51,13 @@ class PreparedWeights:
                     om = blk.conv2.offset_mask_conv
                     w = ops.pack_conv_weight(to(om.weight), 32)
                     P[p + ".offset"] = (w, torch.ones(32, device=device), ops.pad_vec(to(om.bias), 32))
-                conv_bn(p + ".conv2", blk.conv2.weight, blk.bn2)
+                if self.dcn and li >= 2 and ops.dcn_tmem_supported(blk.conv2.weight.shape[0]):
+                    # c3 / c4: tensor-memory DCN kernel, weights in its K order
+                    w = ops.pack_dcn_weight(to(blk.conv2.weight))
+                    s, t = _bn_fold(blk.bn2)
+                    P[p + ".conv2"] = (w, ops.pad_vec(to(s), w.shape[0], 1.0), ops.pad_vec(to(t), w.shape[0]))
+                else:
+                    conv_bn(p + ".conv2", blk.conv2.weight, blk.bn2)
                 conv_bn(p + ".conv3", blk.conv3.weight, blk.bn3)
                 if blk.downsample is not None:
                     conv_bn(p + ".down", blk.downsample[0].weight, blk.downsample[1])
@@ -111,7 +117,8 @@ class Plan:
             self.steps.append(op)
             self.names.append(name)
             self.step_flops[name] = op.flops
-            self.step_kind[name] = {ops.IGEMM_CONV: "conv", ops.IGEMM_STEM: "stem", ops.IGEMM_DCN: "dcn"}[mode]
+            self.step_kind[name] = {ops.IGEMM_CONV: "conv", ops.IGEMM_STEM: "stem", ops.IGEMM_DCN: "dcn",
+                                    ops.IGEMM_DCN_TMEM: "dcn"}[mode]
             oh, ow = in_h // stride, in_w // stride
             out_px = b * oh * ow * (4 if flags & ops.EPI_SHUFFLE2 else 1)
             out_bytes = out_px * 4 * 4 if flags & ops.EPI_HEAD_DOT else y.element_size() * b * oh * ow * out_c
@@ -153,8 +160,8 @@ class Plan:
                     om = torch.empty(b, ho, wo, 9, 4, device=dev, dtype=torch.int32)
                     igemm(p + ".offset", ops.IGEMM_CONV, t1, p + ".offset", om, in_h=h, in_w=w, in_c=width, out_c=32,
                           ksize=3, stride=stride, flags=ops.EPI_DCN_COORDS, out_ld=32)
-                    igemm(p + ".dcn", ops.IGEMM_DCN, t1, p + ".conv2", t2, in_h=h, in_w=w, in_c=width, out_c=width,
-                          ksize=3, stride=stride, flags=ops.EPI_RELU, offsets=om)
+                    igemm(p + ".dcn", ops.IGEMM_DCN_TMEM if ops.dcn_tmem_supported(width) else ops.IGEMM_DCN, t1, p + ".conv2", t2,
+                          in_h=h, in_w=w, in_c=width, out_c=width, ksize=3, stride=stride, flags=ops.EPI_RELU, offsets=om)
                 else:
                     igemm(p + ".conv2", ops.IGEMM_CONV, t1, p + ".conv2", t2, in_h=h, in_w=w, in_c=width, out_c=width,
                           ksize=3, stride=stride, flags=ops.EPI_RELU)

@@ -12,10 +12,10 @@ import torch
 
 from . import _lib
 from ._lib import (EPI_DCN_COORDS, EPI_GELU, EPI_HEAD_DOT, EPI_OUT_F32, EPI_RELU, EPI_RES, EPI_RES_UP2, EPI_SHUFFLE2, IGEMM_CONV,
-                   IGEMM_DCN, IGEMM_STEM)
+                   IGEMM_DCN, IGEMM_DCN_TMEM, IGEMM_STEM)
 
 __all__ = [
-    "Igemm", "pack_conv_weight", "pack_stem_weight", "pack_convT_weight", "fold_bn", "pad_vec",
+    "Igemm", "pack_conv_weight", "pack_dcn_weight", "dcn_tmem_supported", "IGEMM_DCN_TMEM", "pack_stem_weight", "pack_convT_weight", "fold_bn", "pad_vec",
     "stem_pack", "stem_pack_u8", "resize_u8_linear", "maxpool3x3s2", "asf_fwd", "asf_combine", "db_head_fwd", "postproc", "rec_prep_boxes", "rec_prep_rects", "ctc_greedy", "svtr_stem1", "layernorm", "gelu", "mhsa", "frm_select", "decimate_rows", "log_softmax_tbc", "ref_conv2d", "ref_dcn2d",
     "EPI_RELU", "EPI_RES", "EPI_RES_UP2", "EPI_OUT_F32", "EPI_SHUFFLE2", "EPI_DCN_COORDS", "EPI_HEAD_DOT", "EPI_GELU", "db_maps", "dcn_coords", "IGEMM_CONV", "IGEMM_STEM", "IGEMM_DCN",
 ]
@@ -49,6 +49,32 @@ def pack_conv_weight(w: torch.Tensor, n_pad: Optional[int] = None) -> torch.Tens
     t = w.reshape(o, i // 64, 64, kh * kw).permute(0, 1, 3, 2)  # (o, chunk, tap, 64)
     out[:o] = t.reshape(o, kh * kw * i).to(torch.bfloat16)
     return out.contiguous()
+
+
+def dcn_k_permutation() -> torch.Tensor:
+    """perm[k'] = channel (inside a 64-channel chunk) that K position k' of the tensor-memory DCN kernel holds.
+
+    The producers of dcn2.cu hand a blended row to tcgen05.st.16x256b as four lanes x 32 bytes: lane m of the four holds
+    the 16-byte pieces m and m + 4 of the row (channels 8m..8m+7 and 32+8m..32+8m+7), and the store puts its registers
+    (2j, 2j+1) in TMEM columns 8j + 2m, 8j + 2m + 1, i.e. K positions 16j + 4m + (0..3).  So K position 16j + 4m + r
+    carries channel 32 (j >> 1) + 8m + 4 (j & 1) + r."""
+    k = torch.arange(64)
+    j, m, r = k >> 4, (k >> 2) & 3, k & 3
+    return 32 * (j >> 1) + 8 * m + 4 * (j & 1) + r
+
+
+def pack_dcn_weight(w: torch.Tensor, n_pad: Optional[int] = None) -> torch.Tensor:
+    """pack_conv_weight + the K permutation of the tensor-memory DCN kernel (IGEMM_DCN_TMEM) inside each 64-channel chunk."""
+    o, i, kh, kw = w.shape
+    base = pack_conv_weight(w, n_pad)  # [n_pad][chunk][tap][64]
+    perm = dcn_k_permutation().to(w.device)
+    return base.reshape(base.shape[0], i // 64, kh * kw, 64)[..., perm].reshape(base.shape[0], -1).contiguous()
+
+
+def dcn_tmem_supported(out_c: int) -> bool:
+    """Layers the tensor-memory DCN kernel takes: the whole output width is one UMMA N (ResNet-50 c3 / c4)."""
+    import os
+    return out_c in (128, 256) and not os.environ.get("B200_DCN_V1")
 
 
 def pack_stem_weight(w: torch.Tensor, n_pad: int = 64) -> torch.Tensor:

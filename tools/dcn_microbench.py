@@ -80,8 +80,12 @@ def main():
             sc, sh = torch.ones(n_pad, device=dev), torch.zeros(n_pad, device=dev)
             y = torch.empty(b, oh, oh, c, device=dev, dtype=torch.bfloat16)
             coords = torch.empty(b, oh, oh, 9, 4, device=dev, dtype=torch.int32)
-            op = ops.Igemm(ops.IGEMM_DCN, xn, wp, sc, sh, y, batch=b, in_h=hw, in_w=hw, in_c=c, out_c=c, ksize=3,
-                           stride=s, flags=0, offsets=coords, name=name)
+            if ops.dcn_tmem_supported(c):  # c3 / c4: tensor-memory kernel (B200_DCN_V1=1 times the first kernel instead)
+                op = ops.Igemm(ops.IGEMM_DCN_TMEM, xn, ops.pack_dcn_weight(wt, n_pad), sc, sh, y, batch=b, in_h=hw, in_w=hw,
+                               in_c=c, out_c=c, ksize=3, stride=s, flags=0, offsets=coords, name=name)
+            else:
+                op = ops.Igemm(ops.IGEMM_DCN, xn, wp, sc, sh, y, batch=b, in_h=hw, in_w=hw, in_c=c, out_c=c, ksize=3,
+                               stride=s, flags=0, offsets=coords, name=name)
             iters = max(5, min(50, int(2000 / (b * oh * oh * c * c / 2 ** 24 + 1))))
             t_coords = timed(lambda: ops.dcn_coords(om, coords, b, hw, hw, c, s), iters)
             t_dcn = timed(op, iters)
