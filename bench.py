@@ -487,12 +487,16 @@ def main():
         model(x_dev)
         torch.cuda.synchronize()
         plan = model._get_plan(x_dev)
-        idx = plan.names.index(args.profile_launch)
         n_ig = sum(1 for n in plan.names if n in plan.step_kind)
-        print(f"profile-launch {args.profile_launch}: plan step {idx}, {n_ig} igemm launches per forward", file=sys.stderr)
-        for _ in range(3):
-            plan.steps[idx]()
-        torch.cuda.synchronize()
+        # comma-separated plan step names: each runs 3x after the forward (ncu: -k regex:<kernel> and pick by launch index)
+        for name in args.profile_launch.split(","):
+            idx = plan.names.index(name)
+            print(f"profile-launch {name}: plan step {idx}, {n_ig} igemm launches per forward", file=sys.stderr)
+            torch.cuda.nvtx.range_push("profile:" + name)
+            for _ in range(3):
+                plan.steps[idx]()
+            torch.cuda.synchronize()
+            torch.cuda.nvtx.range_pop()
         return 0
 
     if args.shard_images:

@@ -532,7 +532,7 @@ int dcn2_create(const b200_igemm_desc* d, Dcn2Plan** out) {
     p.block_n = d->n_pad;
     p.x_ld = d->x_ld ? d->x_ld : d->in_c;
     p.nacc = (p.block_n <= 128) ? 2 : 1;
-    int max_tw = (p.out_w >= 128) ? 16 : 32;  // squarer tiles = smaller gather neighbourhood (more L1 hits)
+    int max_tw = 16;  // 16 x 8 tiles: the squarest = the smallest gather neighbourhood (measured: 32 x 4 is 3-6 % slower)
     if (const char* e = getenv("B200_CONV_TW")) { if (atoi(e) >= 8 && atoi(e) <= 128) max_tw = atoi(e); }
     p.tile_w = pick_tile_w2(p.out_h, p.out_w, max_tw);
     p.tile_h = 128 / p.tile_w;
@@ -546,10 +546,11 @@ int dcn2_create(const b200_igemm_desc* d, Dcn2Plan** out) {
     p.shift = d->shift;
     // shared memory: weight ring + epilogue staging + two record buffers; what the launch does not take stays L1, which the
     // corner gathers live on
-    p.b_stages = (p.block_n == 256) ? 3 : 4;
+    // (measured, batch 16: two 32 KB weight stages feed N = 256 as well as three; four shrink L1 and cost 10 %)
+    p.b_stages = (p.block_n == 256) ? 2 : 3;
     p.epi_bufs = 2;
     if (const char* e = getenv("B200_DCN2_BSTAGES")) { if (atoi(e) >= 2 && atoi(e) <= kMaxBStages) p.b_stages = atoi(e); }
-    if (const char* e = getenv("B200_DCN2_EPIBUFS")) { if (atoi(e) >= 1 && atoi(e) <= kMaxEpiBufs) p.epi_bufs = atoi(e); }
+    if (const char* e = getenv("B200_DCN2_EPIBUFS")) { if (atoi(e) >= 2 && atoi(e) <= kMaxEpiBufs) p.epi_bufs = atoi(e); }
     p.rec_lead = p.b_stages + 2;
     if (p.rec_lead > p.k_blocks - 1) p.rec_lead = p.k_blocks - 1;
     pl->smem_bytes = 1024 + p.b_stages * p.block_n * 128 + p.epi_bufs * kChunkBytes + 2 * kRecBytes + 8 * p.block_n + 512;

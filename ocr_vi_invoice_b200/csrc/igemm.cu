@@ -84,6 +84,8 @@ struct IgemmParams {
     int ss_half;   // floats between the scale and the shift vector in shared memory (n_pad, at least 256)
     int n_pad;     // GEMM columns of the layer (all n-blocks)
     int nacc;      // TMEM accumulators: 2 (tile i+1's MMAs overlap tile i's epilogue) or 1 (block_n = 512 fills TMEM)
+    int b_rows;    // weight rows one CTA stages per k-block: block_n, or block_n / 2 in pair mode (cta_group::2)
+    int num_units; // pair mode: units of work = (pair of pixel tiles, n-block); otherwise == num_tiles
 };
 
 struct TmapPack {
@@ -118,7 +120,7 @@ __device__ __forceinline__ SmemLayout carve(uint8_t* raw, const IgemmParams& p) 
     SmemLayout s;
     s.a = base;
     s.b = s.a + p.a_stages * p.a_bytes;
-    s.epi = s.b + (p.b_resident ? p.k_blocks : (p.a_kb > 1 ? p.b_stages * 3 : p.a_stages)) * p.block_n * 128;
+    s.epi = s.b + (p.b_resident ? p.k_blocks : (p.a_kb > 1 ? p.b_stages * 3 : p.a_stages)) * p.b_rows * 128;
     uint8_t* rest = s.epi + p.epi_bufs * kABytes;
     s.ss = reinterpret_cast<float*>(rest);
     uint8_t* bars = rest + 8 * p.ss_half;
@@ -417,7 +419,11 @@ __device__ __forceinline__ void gelu_as2(float& x0, float& x1) {
 // vector registers alive); 2 = DB-head tail folded in (B200_EPI_HEAD_DOT); 3 = GELU before the residual add
 // (B200_EPI_GELU, the recogniser's Linear / conv + GELU layers).  Own instantiations: the common epilogue must
 // not pay registers (spills) for the rare ones.
-template <int kVariant, int kEpi = 0>
+// kPair: cta_group::2 -- the two CTAs of a cluster run one 256-pixel x block_n UMMA per K step (variant 0 only): each stages
+// its own 128-pixel A tile and HALF of the weight rows, rank 0 issues the MMAs and multicasts the commits, each CTA's
+// epilogue drains its own TMEM.  Per k-block an SM pulls A + B/2 instead of A + B through the L2 fabric, which is what the
+// weight-heavy small-spatial layers (layer3 / layer4 1x1 convs, the top of the neck) are bound by (~42 B/clk per SM).
+template <int kVariant, int kEpi = 0, bool kPair = false>
 __global__ void __launch_bounds__((base_warps(kVariant == 1) + (kVariant == 1 ? kGatherWarps : 0)) * 32, 1)
 igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -428,8 +434,19 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
     constexpr int G = epi_groups(kGather);
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int b_bytes = p.block_n * 128;
+    const int b_bytes = p.b_rows * 128;
     const SmemLayout sm = carve<kGather>(smem_raw, p);
+    // unit of work u -> tile index of THIS CTA.  Pair mode: unit = (pixel-tile pair mp, n-block); rank r takes pixel tile
+    // 2 mp + r (an odd tile count leaves the last rank-1 tile outside the tensor: TMA zero-fills its loads, clips its stores)
+    const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
+    const int u_first = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int u_stride = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    const int num_units = kPair ? p.num_units : p.num_tiles;
+    auto unit_tile = [&](int u) -> int {
+        if (!kPair) return u;
+        const int mp = u / p.num_n_blocks;
+        return (2 * mp + static_cast<int>(cta_rank)) * p.num_n_blocks + (u - mp * p.num_n_blocks);
+    };
     const int stages = p.a_stages;  // A ring depth (the gather producers fill it too)
     const uint32_t tmem_cols = (p.nacc * p.block_n < 32) ? 32u : static_cast<uint32_t>(p.nacc * p.block_n);
 
@@ -467,7 +484,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
             }
             for (int a = 0; a < 2; ++a) {
                 mbar_init(&sm.tfull[a], 1);
-                mbar_init(&sm.tempty[a], 4 * G);
+                mbar_init(&sm.tempty[a], (kPair ? 2 : 1) * 4 * G);  // pair: the epilogue warps of BOTH CTAs release rank 0's barrier
             }
             mbar_init(sm.b_ready, 1);
             for (int a = 0; a < kMaxEpiBufs; ++a) {
@@ -478,8 +495,13 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
             fence_mbar_init();
         }
         __syncwarp();
-        tmem_alloc(sm.tmem_slot, tmem_cols);
-        tmem_relinquish();
+        if constexpr (kPair) {
+            tmem_alloc_2sm(sm.tmem_slot, tmem_cols);
+            tmem_relinquish_2sm();
+        } else {
+            tmem_alloc(sm.tmem_slot, tmem_cols);
+            tmem_relinquish();
+        }
     }
     if constexpr (kEpi == 2) {  // head tail: scale | w2 | shift (ss_half = 512)
         for (int i = threadIdx.x; i < 256; i += blockDim.x) {
@@ -496,6 +518,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (kPair) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them remotely
     tc_fence_after();
     const uint32_t tmem_base = *sm.tmem_slot;
     pdl_wait();  // the producing launches have completed: activations, residuals and sampling records may be read
@@ -522,7 +545,8 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
             // pays one barrier round trip per 3 k-blocks.  The weights travel on their own ring (warp 3).
             const uint32_t tx_bytes = (p.dbg & 2) ? 0u : static_cast<uint32_t>(p.a_bytes);
             const bool stem = (p.mode == B200_IGEMM_STEM);  // one box per tile: rows y0 .. y0+tile_h+2 of the view
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int u = u_first; u < num_units; u += u_stride) {
+                const int tile = unit_tile(u);
                 const TileCoord t = decode_tile(p, tile);
                 if (stem) {
                     B200_TIMED_WAIT(0, mbar_wait(&sm.a_empty[s], ph ^ 1));
@@ -550,8 +574,10 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
         } else {
             // One 128-pixel A tile and one weight k-block per stage, both landing on the stage's barrier.
             const int taps = p.k_blocks / p.cchunks;  // K is ordered (64-channel chunk, tap)
-            const uint32_t tx_bytes = ((kGather || (p.dbg & 2)) ? 0 : kABytes) + (p.b_resident ? 0 : b_bytes);
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            // pair mode: rank 0's barrier collects the bytes of both CTAs' A tiles and weight halves
+            const uint32_t tx_bytes = (kPair ? 2u : 1u) * (((kGather || (p.dbg & 2)) ? 0 : kABytes) + (p.b_resident ? 0 : b_bytes));
+            for (int u = u_first; u < num_units; u += u_stride) {
+                const int tile = unit_tile(u);
                 const TileCoord t = decode_tile(p, tile);
                 int tap = 0, c0 = 0;
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
@@ -578,7 +604,15 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                         }
                     }
                     B200_TIMED_WAIT(0, mbar_wait(&sm.a_empty[s], ph ^ 1));
-                    if (elect_one()) {
+                    if constexpr (kPair) {
+                        if (elect_one()) {
+                            if (cta_rank == 0) mbar_arrive_expect_tx(&sm.a_full[s], tx_bytes);
+                            const uint32_t bar0 = mapa_u32(smem_u32(&sm.a_full[s]), 0);
+                            tma_load_4d_2sm(sm.a + s * kABytes, &tm.a[view], bar0, c0, ax, ay, t.n);
+                            tma_load_2d_2sm(sm.b + s * b_bytes, &tm.b, bar0, kb * kBlockK,
+                                            t.nb * p.block_n + static_cast<int>(cta_rank) * p.b_rows);
+                        }
+                    } else if (elect_one()) {
                         mbar_arrive_expect_tx(&sm.a_full[s], tx_bytes);
                         if (!kGather && !(p.dbg & 2))
                             tma_load_4d(sm.a + s * kABytes, &tm.a[view], &sm.a_full[s], c0, ax, ay, t.n);
@@ -595,8 +629,8 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================================================================== MMA issuer
+    } else if (warp == 1 && (!kPair || cta_rank == 0)) {
+        // ===================================================================== MMA issuer (pair mode: rank 0 only)
         // The whole warp runs the loop converged and one elected lane issues: every operand of UTCHMMA / UTCBAR then
         // lives in uniform registers.  (Inside an `if (lane == 0)` region ptxas wraps each uniform-datapath
         // instruction in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop, ~80 cycles per MMA: small-N layers were bound by
@@ -619,7 +653,8 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
             const uint32_t wstep = (b_ring || akb == 4) ? be : 3 * be;
             int bs = 0;
             uint32_t bph = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            for (int u = u_first; u < num_units; u += u_stride, ++it) {
+                const int tile = unit_tile(u); (void)tile;
                 const int acc = it & 1;
                 B200_TIMED_WAIT(2, mbar_wait(&sm.tempty[acc], ((it >> 1) & 1) ^ 1));
                 tc_fence_after();
@@ -666,8 +701,9 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
             // N = 512 (gather variant only): two N = 256 instructions per K step, one accumulator
             const bool wide = kGather && p.block_n > 256;
             const int nacc = kGather ? p.nacc : 2;
-            const uint32_t idesc_l = wide ? umma_idesc_bf16(256u) : idesc;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const uint32_t idesc_l = kPair ? umma_idesc_bf16_2sm(static_cast<uint32_t>(p.block_n)) : (wide ? umma_idesc_bf16(256u) : idesc);
+            for (int u = u_first; u < num_units; u += u_stride, ++it) {
+                const int tile = unit_tile(u); (void)tile;
                 const int acc = (nacc == 2) ? (it & 1) : 0;
                 const uint32_t tph = (nacc == 2) ? ((it >> 1) & 1) : (it & 1);
                 B200_TIMED_WAIT(2, mbar_wait(&sm.tempty[acc], tph ^ 1));
@@ -678,7 +714,14 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                     tc_fence_after();
                     const uint64_t da = umma_desc_sw128(a0 + s * kABytes);
                     const uint64_t db = umma_desc_sw128(b0 + (p.b_resident ? kb : s) * b_bytes);
-                    if (elect_one()) {
+                    if constexpr (kPair) {
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < kBlockK / 16; ++k)  // one 256 x block_n UMMA: A rows and weight halves of both CTAs
+                                umma_bf16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc_l, (kb | k) ? 1u : 0u);
+                            umma_commit_2sm(&sm.a_empty[s]);  // frees the stage in both CTAs
+                        }
+                    } else if (elect_one()) {
                         if (!(p.dbg & 1)) {
 #pragma unroll
                             for (int k = 0; k < kBlockK / 16; ++k) {
@@ -692,7 +735,10 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                     __syncwarp();
                     if (++s == stages) { s = 0; ph ^= 1; }
                 }
-                if (elect_one()) umma_commit(&sm.tfull[acc]);
+                if (elect_one()) {
+                    if constexpr (kPair) umma_commit_2sm(&sm.tfull[acc]);
+                    else umma_commit(&sm.tfull[acc]);
+                }
                 __syncwarp();
             }
         }
@@ -705,23 +751,24 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
         if (p.epi_tma) {
             const int B = p.epi_bufs, L = (B > 1) ? 1 : 0;
             constexpr bool up2 = kUp2;
-            int ld_tile = blockIdx.x, ld_chunk = 0;
+            int ld_u = u_first, ld_chunk = 0;
             auto issue_load = [&](int slot) {
-                if (ld_tile >= p.num_tiles) return;
-                const TileCoord t = decode_tile(p, ld_tile);
+                if (ld_u >= num_units) return;
+                const TileCoord t = decode_tile(p, unit_tile(ld_u));
                 if (elect_one()) {
                     mbar_arrive_expect_tx(&sm.res_full[slot], p.res_bytes);
                     tma_load_4d(sm.epi + slot * kABytes, &tm.res, &sm.res_full[slot], t.nb * p.block_n + ld_chunk * 64,
                                 up2 ? (t.x0 >> 1) : t.x0, up2 ? (t.y0 >> 1) : t.y0, t.n);
                 }
                 __syncwarp();
-                if (++ld_chunk == chunks_of(p, t.nb)) { ld_chunk = 0; ld_tile += gridDim.x; }
+                if (++ld_chunk == chunks_of(p, t.nb)) { ld_chunk = 0; ld_u += u_stride; }
             };
             if (p.res_tma)
                 for (int i = 0; i < B; ++i) issue_load(i);
             int g = 0, slot = 0, rslot = 0;
             uint32_t par = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int u = u_first; u < num_units; u += u_stride) {
+                const int tile = unit_tile(u);
                 const TileCoord t = decode_tile(p, tile);
                 const int nchunks = chunks_of(p, t.nb);
                 for (int c = 0; c < nchunks; ++c, ++g) {
@@ -757,7 +804,8 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
             int s = 0;
             uint32_t ph = 0;
             const int bst = p.b_stages;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int u = u_first; u < num_units; u += u_stride) {
+                const int tile = unit_tile(u);
                 const int n0 = (tile % p.num_n_blocks) * p.block_n;
                 for (int kb9 = 0; kb9 < p.k_blocks; kb9 += 9) {
                     for (int kx = 0; kx < 3; ++kx) {
@@ -795,7 +843,8 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
         int next_mine = eg;  // next chunk index this group takes
         int slot = eg;       // its buffer (g % B) and the parity of that buffer's barriers ((g / B) & 1); GA <= B
         uint32_t par = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        for (int u = u_first; u < num_units; u += u_stride, ++it) {
+                const int tile = unit_tile(u); (void)tile;
             const TileCoord t = decode_tile(p, tile);
             const int as = (!kGather || p.nacc == 2) ? (it & 1) : 0;
             const uint32_t aph = (!kGather || p.nacc == 2) ? ((it >> 1) & 1) : (it & 1);
@@ -893,7 +942,10 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
             // accumulator fully read by this warp (or not needed): hand the TMEM buffer back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.tempty[as]);
+            if (lane == 0) {
+                if constexpr (kPair) mbar_arrive_cluster(mapa_u32(smem_u32(&sm.tempty[as]), 0));
+                else mbar_arrive(&sm.tempty[as]);
+            }
         }
     } else if (kGather) {
         // ===================================================================== gather producers (16 warps)
@@ -903,7 +955,8 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
         const int l8 = lane & 7;
         int s = 0;
         uint32_t ph = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int u = u_first; u < num_units; u += u_stride) {
+                const int tile = unit_tile(u);
             const TileCoord t = decode_tile(p, tile);
             int oy[kPasses], ox[kPasses];
             bool valid[kPasses];
@@ -1025,9 +1078,11 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
 #ifdef B200_PROF
     if ((p.dbg & 16) && blockIdx.x == 0 && threadIdx.x == 0) g_prof[9] += clock64() - prof_t0;
 #endif
+    if constexpr (kPair) cluster_sync_all();  // neither CTA leaves (or frees TMEM) while the pair's MMAs / multicasts may still touch it
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, tmem_cols);
+        if constexpr (kPair) tmem_dealloc_2sm(tmem_base, tmem_cols);
+        else tmem_dealloc(tmem_base, tmem_cols);
     }
 }
 
@@ -1091,6 +1146,7 @@ using namespace b200;
 struct b200_igemm {
     TmapPack tm;
     IgemmParams p;
+    int pair;  // cta_group::2 launch: clusters of two CTAs
     int gather;
     int grid;
     int threads;
@@ -1290,10 +1346,27 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     p.res_bytes = (d->flags & B200_EPI_RES_UP2) ? kABytes / 4 : kABytes;
 
     const int G = epi_groups(op->gather);
-    const int b_bytes = block_n * 128;
+    int b_bytes = block_n * 128;
     // Small weight matrices (stem, layer1, ConvT, ...) live in shared memory for the whole launch: no per-tile weight
     // TMA traffic, the ring carries activations only.
     p.b_resident = (p.num_n_blocks == 1 && p.k_blocks * b_bytes <= 72 * 1024 && d->mode != B200_IGEMM_DCN) ? 1 : 0;
+    // Pair mode (cta_group::2): layers whose weights stream per tile and whose k-blocks are "fat" in weights relative to
+    // activations -- what each SM pulls through the L2 fabric per k-block (A + B, ~42 B/clk per SM when every SM pulls)
+    // is what bounds them, and the pair halves the B part.  TMA-fed plain convs with the TMA-store epilogue only.
+    const int px_tiles = p.batch * p.tiles_x * p.tiles_y;
+    // Measured per layer (batch 16 @1024^2, pair on vs off): 3x3 256->256 at 256^2 0.851 -> 0.769 ms (1.6 PFLOP/s: the SS
+    // operand reads, A + B per instruction, drop from 12 to 8 KB), 128^2 0.209 -> 0.189, lat3 (K = 2048) 0.030 -> 0.027;
+    // but short-K layers lose to the cross-CTA hand-shakes per tile (conv3 with K = 256: 0.072 -> 0.079, lat0 0.239 ->
+    // 0.275), and K = 1024..2048 1x1 convs do not move.  Hence: at least 16 k-blocks per tile.
+    int pair_min_kb = 16;
+    if (const char* e = getenv("B200_PAIR_MIN_KB")) pair_min_kb = atoi(e);
+    bool pair = (d->mode == B200_IGEMM_CONV && !fat && !p.b_resident && p.epi_tma && block_n >= 128 && px_tiles >= 2 &&
+                 !(d->flags & (B200_EPI_GELU | B200_EPI_HEAD_DOT)) && p.k_blocks >= pair_min_kb);
+    if (const char* e = getenv("B200_PAIR")) pair = pair && atoi(e) != 0;
+    op->pair = pair ? 1 : 0;
+    p.b_rows = pair ? block_n / 2 : block_n;
+    p.num_units = pair ? ((px_tiles + 1) / 2) * p.num_n_blocks : p.num_tiles;
+    if (pair) b_bytes = p.b_rows * 128;
     p.ss_shared = 1;
     const int fixed = 1024 /*alignment*/ + 1024 /*barriers*/ + 8 * p.ss_half /*scale+shift*/ +
                       (p.b_resident ? p.k_blocks * b_bytes : 0);
@@ -1372,8 +1445,8 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
 
     op->threads = (base_warps(op->gather) + (op->gather ? kGatherWarps : 0)) * 32;
     if (getenv("B200_VERBOSE"))
-        fprintf(stderr, "igemm plan: mode %d k %d s %d N %d kb %d tile %dx%d share %d resident %d a_stages %d (x %d B) b_stages %d bufs %d ga %d smem %d\n",
-                p.mode, p.ksize, p.stride, p.block_n, p.k_blocks, p.tile_w, p.tile_h, p.a_kb, p.b_resident, p.a_stages,
+        fprintf(stderr, "igemm plan: mode %d k %d s %d N %d kb %d tile %dx%d share %d resident %d pair %d a_stages %d (x %d B) b_stages %d bufs %d ga %d smem %d\n",
+                p.mode, p.ksize, p.stride, p.block_n, p.k_blocks, p.tile_w, p.tile_h, p.a_kb, p.b_resident, op->pair, p.a_stages,
                 p.a_bytes, p.b_stages, p.epi_bufs, p.epi_active, op->smem_bytes);
 
     int dev = 0, sms = 0;
@@ -1383,6 +1456,10 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
         return set_error("igemm: cannot query device: %s", cudaGetErrorString(cudaGetLastError()));
     }
     op->grid = p.num_tiles < sms ? p.num_tiles : sms;
+    if (op->pair) {
+        const int clusters = p.num_units < sms / 2 ? p.num_units : sms / 2;
+        op->grid = 2 * clusters;
+    }
 
     // ---- tensor maps
     int err = 0;
@@ -1390,7 +1467,7 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     {
         const uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)d->n_pad};
         const uint64_t str[1] = {(uint64_t)ktot * 2};
-        const uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)(block_n > 256 ? 256 : block_n)};
+        const uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)(block_n > 256 ? 256 : p.b_rows)};
         err |= encode_map(&op->tm.b, d->w, 2, dims, str, box, "weights");
     }
     if (!err && !op->gather && d->mode != B200_IGEMM_STEM) {
@@ -1459,6 +1536,10 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
         e = cudaFuncSetAttribute(igemm_kernel<0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(igemm_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(igemm_kernel<0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(igemm_kernel<0, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) {
         delete op;
         return set_error("igemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -1473,9 +1554,20 @@ extern "C" int b200_igemm_launch(const b200_igemm* op, void* stream) {
     // Programmatic dependent launch (also inside stream capture, where it becomes a programmatic graph edge): the
     // kernel's prologue overlaps the tail of the previous launch of the stream; see pdl_wait() in the kernel.
     static const bool pdl = getenv("B200_PDL") != nullptr;  // measured (round 2): 1598 vs 1612 img/s without -- off by default
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int nattr = 0;
+    if (pdl) {
+        attr[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[nattr].val.programmaticStreamSerializationAllowed = 1;
+        ++nattr;
+    }
+    if (op->pair) {
+        attr[nattr].id = cudaLaunchAttributeClusterDimension;
+        attr[nattr].val.clusterDim.x = 2;
+        attr[nattr].val.clusterDim.y = 1;
+        attr[nattr].val.clusterDim.z = 1;
+        ++nattr;
+    }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(op->grid);
@@ -1483,9 +1575,13 @@ extern "C" int b200_igemm_launch(const b200_igemm* op, void* stream) {
     cfg.dynamicSmemBytes = op->smem_bytes;
     cfg.stream = reinterpret_cast<cudaStream_t>(stream);
     cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
+    cfg.numAttrs = nattr;
     cudaError_t e;
-    if (op->gather)
+    if (op->pair && (op->p.flags & B200_EPI_RES_UP2))
+        e = cudaLaunchKernelEx(&cfg, igemm_kernel<0, 1, true>, op->tm, op->p);
+    else if (op->pair)
+        e = cudaLaunchKernelEx(&cfg, igemm_kernel<0, 0, true>, op->tm, op->p);
+    else if (op->gather)
         e = cudaLaunchKernelEx(&cfg, igemm_kernel<1>, op->tm, op->p);
     else if ((op->p.flags & B200_EPI_GELU) && op->p.a_kb > 1)
         e = cudaLaunchKernelEx(&cfg, igemm_kernel<2, 3>, op->tm, op->p);

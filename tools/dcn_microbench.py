@@ -50,6 +50,8 @@ def main():
     ap.add_argument("--out", default="gpurun_out/dcn_microbench.csv")
     ap.add_argument("--batches", default="1,2,4,8,16,32,64")
     ap.add_argument("--peak", type=float, default=0.0, help="bf16 TFLOP/s to report fractions against")
+    ap.add_argument("--only", default="", help="substring filter on the shape name (e.g. 'layer3 s1'), for ncu captures")
+    ap.add_argument("--no-tv", action="store_true", help="skip the torchvision timings (ncu captures)")
     a = ap.parse_args()
     peak = a.peak
     if not peak:
@@ -63,6 +65,8 @@ def main():
     rows = ["shape,cin,cout,in_hw,stride,batch,gflop,ours_dcn_ms,ours_coords_ms,ours_tflops,ours_frac_of_peak,"
             "tv_fp32_ms,tv_fp16_ms,speedup_vs_fp32,speedup_vs_fp16,rel_rms_vs_tv_fp32"]
     for name, c, hw, s in SHAPES:
+        if a.only and a.only not in name:
+            continue
         for b in [int(v) for v in a.batches.split(",")]:
             g = torch.Generator(device=dev).manual_seed(0)
             x = torch.randn(b, c, hw, hw, device=dev, generator=g)
@@ -94,9 +98,12 @@ def main():
             out = y.permute(0, 3, 1, 2).float()
             rel = ((out - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
             assert rel < 2e-2, f"{name} b{b}: relative rms {rel}"
-            t32 = timed(lambda: tvops.deform_conv2d(x, offset, wt, None, stride=s, padding=1, mask=mask), max(3, iters // 5))
-            xh, oh16, wh, mh = x.half(), offset.half(), wt.half(), mask.half()
-            t16 = timed(lambda: tvops.deform_conv2d(xh, oh16, wh, None, stride=s, padding=1, mask=mh), max(3, iters // 5))
+            if a.no_tv:
+                t32 = t16 = float("nan")
+            else:
+                t32 = timed(lambda: tvops.deform_conv2d(x, offset, wt, None, stride=s, padding=1, mask=mask), max(3, iters // 5))
+                xh, oh16, wh, mh = x.half(), offset.half(), wt.half(), mask.half()
+                t16 = timed(lambda: tvops.deform_conv2d(xh, oh16, wh, None, stride=s, padding=1, mask=mh), max(3, iters // 5))
             gflop = 2.0 * b * oh * oh * c * c * 9 / 1e9
             tf = gflop / t_dcn
             rows.append(f"{name},{c},{c},{hw},{s},{b},{gflop:.2f},{t_dcn:.4f},{t_coords:.4f},{tf:.1f},{tf / peak:.3f},"
