@@ -160,6 +160,21 @@ int b200_asf_combine(const void* p2, const void* p3, const void* p4, const void*
                      const float* z2, const float* z3, const float* z4, const float* z5, int zld,
                      const float* b_att, void* out, int batch, int h2, int w2, int h3, int w3,
                      int h4, int w4, int h5, int w5, void* stream);
+/* The same blend on the tensor cores (asf_mma.cu): per 16 x 8 output tile one 128 x 256 x 112 UMMA chain
+ * out = S * P, where P holds the (at most 10 x 6 / 6 x 4 / 4 x 3) source pixels of p3 / p4 / p5 the tile can touch --
+ * loaded by TMA and used as an MN-major operand as they land -- and S the softmax x bilinear weights (bf16); p2 enters
+ * in the epilogue.  A plan bakes the TMA descriptors for fixed tensors; same arguments and result as
+ * b200_asf_combine (up to the bf16 rounding of the twelve weights per pixel).  b200_asf_plan_supported() says
+ * whether the level sizes fit the kernel's windows (each level about half the previous one, none smaller than
+ * its window); otherwise use b200_asf_combine. */
+typedef struct b200_asf_plan b200_asf_plan;
+int b200_asf_plan_supported(int h2, int w2, int h3, int w3, int h4, int w4, int h5, int w5);
+int b200_asf_plan_create(const void* p2, const void* p3, const void* p4, const void* p5,
+                         const float* z2, const float* z3, const float* z4, const float* z5, int zld,
+                         const float* b_att, void* out, int batch, int h2, int w2, int h3, int w3,
+                         int h4, int w4, int h5, int w5, b200_asf_plan** plan);
+int b200_asf_plan_launch(const b200_asf_plan* plan, void* stream);
+int b200_asf_plan_destroy(b200_asf_plan* plan);
 /* DBHead tail (model/det/head.py:15,23,28-48): last ConvTranspose2d(64->1, 2x2 s2) of both branches,
  * sigmoid, differentiable-binarisation step.  t_bin/t_thr: NHWC bf16, 64 channels each (already
  * BN+ReLU'd), `ld` elements between consecutive pixels (64 for two dense tensors, 128 when both branches

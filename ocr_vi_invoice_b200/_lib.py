@@ -69,6 +69,10 @@ SYMBOLS = {
     "b200_maxpool3x3s2": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "b200_asf_fwd": (_i, [_p] * 7 + [_i] * 9 + [_p]),
     "b200_asf_combine": (_i, [_p] * 8 + [_i] + [_p, _p] + [_i] * 9 + [_p]),
+    "b200_asf_plan_supported": (_i, [_i] * 8),
+    "b200_asf_plan_create": (_i, [_p] * 8 + [_i] + [_p, _p] + [_i] * 9 + [C.POINTER(_p)]),
+    "b200_asf_plan_launch": (_i, [_p, _p]),
+    "b200_asf_plan_destroy": (_i, [_p]),
     "b200_db_head_fwd": (_i, [_p, _p, _p, _f, _p, _f, _f, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "b200_dcn_coords": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "b200_postproc_workspace_bytes": (_i64, [_i, _i, _i, _i]),

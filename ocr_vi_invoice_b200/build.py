@@ -12,7 +12,7 @@ from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB = CSRC / "libdbnet_b200.so"
-SOURCES = ["api.cu", "igemm.cu", "dcn2.cu", "ref.cu", "elementwise.cu", "postproc.cu", "recprep.cu", "ctc.cu", "svtr.cu"]
+SOURCES = ["api.cu", "igemm.cu", "dcn2.cu", "asf_mma.cu", "ref.cu", "elementwise.cu", "postproc.cu", "recprep.cu", "ctc.cu", "svtr.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -205,7 +205,10 @@ class Plan:
             igemm(f"asf.z{i}", ops.IGEMM_CONV, ps[i], f"asf.z{i}", z, in_h=sizes[i][0], in_w=sizes[i][1], in_c=256, out_c=8,
                   ksize=1, stride=1, flags=ops.EPI_OUT_F32, out_ld=8)
             zs.append(z)
-        self.steps.append(lambda: ops.asf_combine(ps, zs, 8, W.b_att, fused, b, sizes))
+        if ops.AsfPlan.supported(sizes):  # bilinear upsampling + attention-weighted sum as one UMMA chain per tile
+            self.steps.append(ops.AsfPlan(ps, zs, 8, W.b_att, fused, b, sizes))
+        else:                             # tiny maps (a level smaller than its gather window): CUDA-core blend
+            self.steps.append(lambda: ops.asf_combine(ps, zs, 8, W.b_att, fused, b, sizes))
         self.names.append("asf")
         if keep_taps:
             self.taps["asf"] = (fused, 256)

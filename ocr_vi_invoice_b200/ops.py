@@ -16,7 +16,7 @@ from ._lib import (EPI_DCN_COORDS, EPI_GELU, EPI_HEAD_DOT, EPI_OUT_F32, EPI_RELU
 
 __all__ = [
     "Igemm", "pack_conv_weight", "pack_dcn_weight", "dcn_tmem_supported", "IGEMM_DCN_TMEM", "pack_stem_weight", "pack_convT_weight", "fold_bn", "pad_vec",
-    "stem_pack", "stem_pack_u8", "resize_u8_linear", "maxpool3x3s2", "asf_fwd", "asf_combine", "db_head_fwd", "postproc", "rec_prep_boxes", "rec_prep_rects", "ctc_greedy", "svtr_stem1", "layernorm", "gelu", "mhsa", "frm_select", "decimate_rows", "log_softmax_tbc", "ref_conv2d", "ref_dcn2d",
+    "stem_pack", "stem_pack_u8", "resize_u8_linear", "maxpool3x3s2", "asf_fwd", "asf_combine", "AsfPlan", "db_head_fwd", "postproc", "rec_prep_boxes", "rec_prep_rects", "ctc_greedy", "svtr_stem1", "layernorm", "gelu", "mhsa", "frm_select", "decimate_rows", "log_softmax_tbc", "ref_conv2d", "ref_dcn2d",
     "EPI_RELU", "EPI_RES", "EPI_RES_UP2", "EPI_OUT_F32", "EPI_SHUFFLE2", "EPI_DCN_COORDS", "EPI_HEAD_DOT", "EPI_GELU", "db_maps", "dcn_coords", "IGEMM_CONV", "IGEMM_STEM", "IGEMM_DCN",
 ]
 
@@ -211,6 +211,34 @@ def asf_combine(ps, zs, zld: int, b_att, out, batch: int, sizes) -> None:
     _lib.check(_lib.load().b200_asf_combine(*[_lib.ptr(t) for t in ps], *[_lib.ptr(t) for t in zs], zld, _lib.ptr(b_att),
                                             _lib.ptr(out), batch, h2, w2, h3, w3, h4, w4, h5, w5, _lib.current_stream()),
                "asf_combine")
+
+
+class AsfPlan:
+    """ScaleFeatureSelection blend on the tensor cores (b200_asf_plan_*): TMA descriptors baked for fixed tensors."""
+
+    def __init__(self, ps, zs, zld: int, b_att, out, batch: int, sizes):
+        lib = _lib.load()
+        (h2, w2), (h3, w3), (h4, w4), (h5, w5) = sizes
+        self._keep = (tuple(ps), tuple(zs), b_att, out)
+        h = C.c_void_p()
+        _lib.check(lib.b200_asf_plan_create(*[_lib.ptr(t) for t in ps], *[_lib.ptr(t) for t in zs], zld, _lib.ptr(b_att),
+                                            _lib.ptr(out), batch, h2, w2, h3, w3, h4, w4, h5, w5, C.byref(h)), "asf_plan_create")
+        self._h, self._lib = h, lib
+
+    @staticmethod
+    def supported(sizes) -> bool:
+        import os
+        (h2, w2), (h3, w3), (h4, w4), (h5, w5) = sizes
+        return bool(_lib.load().b200_asf_plan_supported(h2, w2, h3, w3, h4, w4, h5, w5)) and not os.environ.get("B200_ASF_SIMT")
+
+    def __call__(self) -> None:
+        _lib.check(self._lib.b200_asf_plan_launch(self._h, _lib.current_stream()), "asf_plan_launch")
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._lib.b200_asf_plan_destroy(h)
+            self._h = None
 
 
 def dcn_coords(raw: torch.Tensor, coords: torch.Tensor, batch: int, in_h: int, in_w: int, x_ld: int, stride: int) -> None:

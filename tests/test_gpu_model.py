@@ -110,6 +110,45 @@ def test_db_head_kernel(size):
     assert torch.equal(only["binary"], maps["binary"])
 
 
+@pytest.mark.parametrize("size", [(1, 24, 32), (2, 40, 56), (3, 64, 64), (16, 256, 256)])
+def test_asf_tensor_core_plan(size):
+    """b200_asf_plan_* (bilinear upsampling + attention-weighted sum as one UMMA chain per tile, level windows used as
+    MN-major operands) == the reference ScaleFeatureSelection; the twelve weights per pixel are rounded to bf16, so the
+    bound is a little wider than for the fp32-weight CUDA-core blend, which it is also compared with."""
+    from ocr_vi_invoice_b200 import ops
+    b, h2, w2 = size
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(17)
+    sizes = [(h2, w2), (h2 // 2, w2 // 2), (h2 // 4, w2 // 4), (h2 // 8, w2 // 8)]
+    assert ops.AsfPlan.supported(sizes)
+    ps = [torch.randn(b, 256, h, w, device=dev, generator=g).to(torch.bfloat16) for h, w in sizes]
+    w_att = torch.randn(4, 1024, device=dev, generator=g) * 0.05
+    b_att = torch.randn(4, device=dev, generator=g) * 0.1
+    zs = []
+    for i, p in enumerate(ps):
+        z = torch.zeros(b, sizes[i][0], sizes[i][1], 8, device=dev)
+        z[..., :4] = torch.einsum("bchw,oc->bhwo", p.float(), w_att[:, 256 * i:256 * (i + 1)])
+        zs.append(z.contiguous())
+    pn = [nhwc(p.float()) for p in ps]
+    out = torch.full((b, h2, w2, 256), float("nan"), device=dev, dtype=torch.bfloat16)
+    plan = ops.AsfPlan(pn, zs, 8, b_att, out, b, sizes)
+    plan()
+    plan()  # twice: barrier phases / TMEM are left clean
+    simt = torch.empty_like(out)
+    ops.asf_combine(pn, zs, 8, b_att, simt, b, sizes)
+    torch.cuda.synchronize()
+    got = nchw(out)
+    assert torch.isfinite(got).all()
+    if b * h2 * w2 <= 1 << 16:
+        ups = [ps[0].float()] + [F.interpolate(p.float(), size=(h2, w2), mode="bilinear", align_corners=True) for p in ps[1:]]
+        score = F.softmax(F.conv2d(torch.cat(ups, 1), w_att.view(4, 1024, 1, 1), b_att), dim=1)
+        ref = sum(u * score[:, i:i + 1] for i, u in enumerate(ups))
+        assert rel_rms(got, ref) < 5e-3
+        torch.testing.assert_close(got, ref, rtol=1.6e-2, atol=3e-2)
+    assert rel_rms(got, nchw(simt)) < 4e-3
+    torch.testing.assert_close(got, nchw(simt), rtol=1.6e-2, atol=3e-2)
+
+
 def _model(seed, offset_px=1.5):
     from ocr_vi_invoice_b200.model.det.dbnet import DBNetPP
     from oracle.weights import make_state_dict
