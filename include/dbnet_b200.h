@@ -59,7 +59,9 @@ enum {
                                * ConvTranspose2d is not stored; BN + ReLU + bf16 rounding + the LAST
                                * ConvTranspose2d(64 -> 1, k2 s2) (head.py:15,23) run in the epilogue and y receives
                                * the fp32 logit map (batch, 4*in_h, 4*in_w).  `offsets` = float[257]: tail weights
-                               * w[c*4 + dy*2+dx], then the bias.                                             */
+                               * w[c*4 + dy*2+dx], then the bias.  The BN shift is added by an extra UMMA step and the
+                               * tail is a second UMMA (weights rounded to bf16): `scale` must be all ones -- fold the BN
+                               * scale into the weights.                                                      */
     B200_EPI_GELU       = 128, /* v = GELU(v) (erf form) BEFORE the residual add: the recogniser's Linear / conv +
                                   GELU layers (model/rec2/svtrv2.py:33,51,54,117); bf16 outputs, out_c % 64 == 0 */
     B200_EPI_DCN_COORDS = 32  /* offset_mask_conv only (out_c = 32): instead of the raw 27 channels, store

@@ -45,6 +45,8 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     for src in SOURCES:
         obj = CSRC / (src[:-3] + ".o")
         cmd = [_nvcc(), *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        if os.environ.get("B200_PROF_BUILD"):  # development: per-role wait counters (B200_DEBUG=16, tools/epi_bench.py)
+            cmd.insert(1, "-DB200_PROF")
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -305,57 +305,77 @@ __device__ __forceinline__ void epilogue_direct32(const IgemmParams& p, const ui
     }
 }
 
+// Per-launch constants an epilogue reads with WARP-UNIFORM or compile-time indices travel as a kernel parameter, i.e. in
+// the constant bank: an ld.shared.v4 of an address all 32 lanes share still costs four L1-data-pipe wavefronts (one per
+// quarter warp), and the head-tail epilogue issued ~100 of them per 64 channels (ncu: LSU wavefronts 78 % of elapsed,
+// tensor pipe 11 %).  Constant-bank operands cost none.  Only the head-tail instantiation carries a payload.
+struct HeadConsts {
+    float w2[256];     // last ConvTranspose2d(64 -> 1): [channel][dy2 * 2 + dx2]
+    float scale[256];  // folded BN of the first transposed conv, [sub-pixel][channel]
+    float shift[256];
+    float bias;
+};
+struct NoConsts {};
+template <int kEpi> struct EpiConsts { using type = NoConsts; };
+template <> struct EpiConsts<2> { using type = HeadConsts; };
+
 // ------------------------------------------------------------------------------------------ head tail epilogue
 // B200_EPI_HEAD_DOT: the tile is ConvTranspose2d(64 -> 64, k2 s2) of one DB-head branch (N = 4 sub-pixels x 64 channels).
-// Instead of storing the 64-channel bf16 map, each thread folds BN + ReLU, rounds to bf16 exactly as the stored map
-// would be, and applies the LAST ConvTranspose2d(64 -> 1, k2 s2) (model/det/head.py:15,23) in registers: four fp32 logits
-// per sub-pixel, i.e. a 4 x 4 patch of the full-resolution logit map per input pixel.  Channel order and fmaf sequence
-// are those of db_head_kernel (elementwise.cu), so the logits are bit-identical to the unfused path.
-// aux = float[257]: w2[c * 4 + (dy2 * 2 + dx2)], then the bias.
-__device__ __forceinline__ void epilogue_head_dot(const IgemmParams& p, uint32_t ss_s, uint32_t taddr, int n, int oy,
-                                                  int ox, bool valid, int sub) {
-    // ss (shared): scale[256] | tail weights w2[64][4] | shift[256]   (staged once per CTA, see the kernel prologue)
-    const uint32_t sc = ss_s + sub * 256, sh = ss_s + 2048 + sub * 256, w2 = ss_s + 1024;
-    // accumulators (0, 1) and (2, 3) as fp32 pairs on the packed pipe (FFMA2): per lane the same IEEE fma sequence as
-    // db_head_kernel, so the logits stay bit-identical to the unfused path; 16 + 4 FMAs per 4 channels become 8 + 2
-    uint64_t acc01 = pair2(0.0f, 0.0f), acc23 = pair2(0.0f, 0.0f);
+// The 64-channel bf16 map is never stored.  Epilogue group `sub` (one of the four sub-pixels) folds BN + ReLU, rounds to
+// bf16 exactly as the stored map would be and writes the 128 x 64 tile into a swizzled staging buffer -- which is a valid
+// K-major A operand: the LAST ConvTranspose2d(64 -> 1, k2 s2) (model/det/head.py:15,23) is then a SECOND UMMA
+// (128 x 16 x 64, four useful columns = the 2 x 2 output sub-pixels, weights rounded to bf16) issued by warp 3 into its own
+// TMEM columns, and the group reads the four fp32 logits back one tile later (software-pipelined, double-buffered staging
+// and D2), adds the bias and stores the 4 x 4 patch of the full-resolution logit map.  History: 256 FMAs per thread on the
+// CUDA cores with ld.shared operands 0.142 ms -> constant-bank operands 0.118 ms (issue-bound) -> this.
+// First half: accumulators -> BN + ReLU -> bf16 staging rows.  scale / shift come from the constant bank (HeadConsts).
+__device__ __forceinline__ void head_tail_stage(const IgemmParams& p, uint32_t taddr, uint32_t rowaddr, uint32_t swz, int sub,
+                                                uint64_t* tempty, int lane) {
+    // The accumulators already hold BN(conv): the BN scale is folded into the weights and the shift was added by one extra
+    // K = 16 UMMA step (ones column x [shift_hi, shift_lo] rows, see the kernel prologue), so nothing per-column is
+    // fetched here -- with 16 epilogue warps, 128 ld.shared.v4 (four L1 wavefronts each, even when all lanes read one
+    // address) or constant-bank loads per thread and tile were what bounded this kernel (0.14 / 0.12 ms).
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         uint32_t v[32];
         tmem_ld32(taddr + sub * 64 + half * 32, v);
         tmem_ld_wait();
+        if (half == 1) {  // main accumulator fully read by this warp: the next tile's MMAs may overwrite it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty);
+        }
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-            const int c = half * 32 + i;
-            const float4 s4 = lds_f4(sc + c * 4), h4 = lds_f4(sh + c * 4);
-            float t0, t1, t2, t3;
-            unpair2(fma2_f32(pair2(__uint_as_float(v[i + 0]), __uint_as_float(v[i + 1])), pair2(s4.x, s4.y), pair2(h4.x, h4.y)), t0, t1);
-            unpair2(fma2_f32(pair2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])), pair2(s4.z, s4.w), pair2(h4.z, h4.w)), t2, t3);
+        for (int j = 0; j < 4; ++j) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j * 8 + i]);
             if (p.flags & B200_EPI_RELU) {
-                t0 = fmaxf(t0, 0.0f); t1 = fmaxf(t1, 0.0f); t2 = fmaxf(t2, 0.0f); t3 = fmaxf(t3, 0.0f);
-            }
-            const uint32_t p01 = pack_bf16(t0, t1), p23 = pack_bf16(t2, t3);  // the rounding the stored bf16 map had
-            const float r[4] = {bf16lo(p01), bf16hi(p01), bf16lo(p23), bf16hi(p23)};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float4 w = lds_f4(w2 + (c + j) * 16);
-                const uint64_t rr = pair2(r[j], r[j]);
-                acc01 = fma2_f32(rr, pair2(w.x, w.y), acc01);
-                acc23 = fma2_f32(rr, pair2(w.z, w.w), acc23);
+                for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.0f);
             }
+            uint4 o;
+            o.x = pack_bf16(f[0], f[1]);
+            o.y = pack_bf16(f[2], f[3]);
+            o.z = pack_bf16(f[4], f[5]);
+            o.w = pack_bf16(f[6], f[7]);
+            sts128(rowaddr + ((static_cast<uint32_t>(half * 4 + j) ^ swz) << 4), o);
         }
     }
-    float acc[4];
-    unpair2(acc01, acc[0], acc[1]);
-    unpair2(acc23, acc[2], acc[3]);
+}
+// Second half: the four dot products of one pixel (TMEM columns dy2 * 2 + dx2) + bias -> 2 x 2 patch of the logit map.
+__device__ __forceinline__ void head_tail_store(const IgemmParams& p, float bias, uint32_t d2addr, int n, int oy, int ox, bool valid,
+                                                int sub) {
+    uint32_t v[4];
+    tmem_ld4(d2addr, v);
+    tmem_ld_wait();
     if (valid) {
-        const float bias = __ldg(reinterpret_cast<const float*>(p.offsets) + 256);
         float* out = reinterpret_cast<float*>(p.y);
         const int ow = 4 * p.out_w;
         const int64_t row = (static_cast<int64_t>(n) * (4 * p.out_h) + 4 * oy + 2 * (sub >> 1));
         float* o = out + row * ow + 4 * ox + 2 * (sub & 1);
-        *reinterpret_cast<float2*>(o) = make_float2(acc[0] + bias, acc[1] + bias);
-        *reinterpret_cast<float2*>(o + ow) = make_float2(acc[2] + bias, acc[3] + bias);
+        *reinterpret_cast<float2*>(o) = make_float2(__uint_as_float(v[0]) + bias, __uint_as_float(v[1]) + bias);
+        *reinterpret_cast<float2*>(o + ow) = make_float2(__uint_as_float(v[2]) + bias, __uint_as_float(v[3]) + bias);
     }
 }
 
@@ -425,7 +445,7 @@ __device__ __forceinline__ void gelu_as2(float& x0, float& x1) {
 // weight-heavy small-spatial layers (layer3 / layer4 1x1 convs, the top of the neck) are bound by (~42 B/clk per SM).
 template <int kVariant, int kEpi = 0, bool kPair = false>
 __global__ void __launch_bounds__((base_warps(kVariant == 1) + (kVariant == 1 ? kGatherWarps : 0)) * 32, 1)
-igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
+igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __grid_constant__ typename EpiConsts<kEpi>::type ec) {
     extern __shared__ uint8_t smem_raw[];
     constexpr bool kGather = (kVariant == 1);
     constexpr bool kShare = (kVariant == 2);
@@ -448,7 +468,8 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
         return (2 * mp + static_cast<int>(cta_rank)) * p.num_n_blocks + (u - mp * p.num_n_blocks);
     };
     const int stages = p.a_stages;  // A ring depth (the gather producers fill it too)
-    const uint32_t tmem_cols = (p.nacc * p.block_n < 32) ? 32u : static_cast<uint32_t>(p.nacc * p.block_n);
+    // head tail (kEpi 2): one 256-column accumulator + 4 sub-pixels x 2 x 16 columns for the second UMMA's results
+    const uint32_t tmem_cols = (kEpi == 2) ? 512u : ((p.nacc * p.block_n < 32) ? 32u : static_cast<uint32_t>(p.nacc * p.block_n));
 
     // Programmatic dependent launch: the next launch of the stream may be scheduled onto SMs as this grid's blocks
     // retire; its prologue (below, up to pdl_wait) then overlaps our tail.  Nothing before pdl_wait() touches
@@ -503,12 +524,38 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
             tmem_relinquish();
         }
     }
-    if constexpr (kEpi == 2) {  // head tail: scale | w2 | shift (ss_half = 512)
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-            sm.ss[i] = __ldg(p.scale + i);
-            sm.ss[256 + i] = __ldg(reinterpret_cast<const float*>(p.offsets) + i);
-            sm.ss[512 + i] = __ldg(p.shift + i);
+    if constexpr (kEpi == 2) {
+        // B operand of the second UMMA: w2 as bf16 [16 rows (4 used: dy2 * 2 + dx2)][64 channels], K-major, 128B swizzle
+        uint8_t* w2s = reinterpret_cast<uint8_t*>(sm.ss);
+        for (int i = threadIdx.x; i < 2048 / 16; i += blockDim.x) reinterpret_cast<uint4*>(w2s)[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+        if (threadIdx.x < 256) {
+            const int nn = threadIdx.x >> 6, k = threadIdx.x & 63;
+            const __nv_bfloat16 hb = __float2bfloat16_rn(ec.w2[k * 4 + nn]);
+            *reinterpret_cast<__nv_bfloat16*>(w2s + nn * 128 + (((k >> 3) ^ nn) << 4) + (k & 7) * 2) = hb;
         }
+        // BN shift by UMMA: A = [128 x 16] with columns 0 and 1 = 1, B = [256 x 16] with column 0 = bf16(shift), column 1 =
+        // bf16(shift - column 0) (two bf16 terms: fp32-grade shift).  Both K-major WITHOUT swizzle (tools/noswizzle_probe.cu):
+        // element (r, k) at (r % 8) * 16 + (r / 8) * 128 + (k / 8) * LBO + (k % 8) * 2, LBO = 2048 (A) / 4096 (B).
+        uint8_t* ones = w2s + 2048;
+        uint8_t* shb = w2s + 8192;
+        for (int i = threadIdx.x; i < (4096 + 8192) / 16; i += blockDim.x)
+            reinterpret_cast<uint4*>(i < 256 ? ones : shb - 4096)[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+        if (threadIdx.x < 128) {
+            const int r = threadIdx.x;
+            *reinterpret_cast<uint32_t*>(ones + (r & 7) * 16 + (r >> 3) * 128) = 0x3F803F80u;  // (1.0, 1.0) bf16
+        }
+        if (threadIdx.x < 256) {
+            const int nn = threadIdx.x;
+            const float sh = ec.shift[nn];
+            const __nv_bfloat16 hi = __float2bfloat16_rn(sh);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(sh - __bfloat162float(hi));
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(shb + (nn & 7) * 16 + (nn >> 3) * 128);
+            dst[0] = hi;
+            dst[1] = lo;
+        }
+        fence_proxy_async_smem();
     }
     if (p.epi_tma) {  // the layer's whole scale / shift vectors, staged once (no per-tile reloads, no named barriers)
         for (int i = threadIdx.x; i < p.n_pad; i += blockDim.x) {
@@ -700,7 +747,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
         } else {
             // N = 512 (gather variant only): two N = 256 instructions per K step, one accumulator
             const bool wide = kGather && p.block_n > 256;
-            const int nacc = kGather ? p.nacc : 2;
+            const int nacc = kGather ? p.nacc : (kEpi == 2 ? 1 : 2);
             const uint32_t idesc_l = kPair ? umma_idesc_bf16_2sm(static_cast<uint32_t>(p.block_n)) : (wide ? umma_idesc_bf16(256u) : idesc);
             for (int u = u_first; u < num_units; u += u_stride, ++it) {
                 const int tile = unit_tile(u); (void)tile;
@@ -736,6 +783,14 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                     if (++s == stages) { s = 0; ph ^= 1; }
                 }
                 if (elect_one()) {
+                    if constexpr (kEpi == 2) {  // + BN shift: ones column x shift rows (no-swizzle K-major operands, one K = 16 step)
+                        const uint32_t cst = smem_u32(sm.ss);
+                        auto noswz = [](uint32_t a, uint32_t lbo) {
+                            return static_cast<uint64_t>((a & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo >> 4) << 16) |
+                                   (static_cast<uint64_t>(128 >> 4) << 32) | (static_cast<uint64_t>(1) << 46);
+                        };
+                        umma_bf16(d_tmem, noswz(cst + 2048, 2048), noswz(cst + 8192, 4096), idesc_l, 1u);
+                    }
                     if constexpr (kPair) umma_commit_2sm(&sm.tfull[acc]);
                     else umma_commit(&sm.tfull[acc]);
                 }
@@ -798,7 +853,31 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
             __syncwarp();
         }
     } else if (warp < kEpiWarp0) {
-        // ===================================================================== weight producer of the share mode (warp 3)
+        // ===================================================================== warp 3
+        if constexpr (kEpi == 2) {
+            // head tail: second UMMA per (tile, sub-pixel): staged bf16 tile x w2 -> 16 TMEM columns (see head_tail_stage)
+            const uint32_t idesc16 = umma_idesc_bf16(16u);
+            const uint64_t dw = umma_desc_sw128(smem_u32(sm.ss));
+            const uint32_t a2 = smem_u32(sm.epi);
+            int it = 0;
+            for (int u = u_first; u < num_units; u += u_stride, ++it) {
+#pragma unroll 1
+                for (int sub = 0; sub < 4; ++sub) {
+                    const int b = sub * 2 + (it & 1);
+                    mbar_wait(&sm.out_ready[b], (it >> 1) & 1);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_sw128(a2 + static_cast<uint32_t>(b) * kABytes);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k)
+                            umma_bf16(tmem_base + 256u + static_cast<uint32_t>(b * 16), da + 2 * k, dw + 2 * k, idesc16, k ? 1u : 0u);
+                        umma_commit(&sm.slot_free[b]);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        // weight producer of the share mode:
         // One stage = the three weight k-blocks (ky = 0..2) of one (chunk, kx); the matrix itself stays (chunk, ky, kx).
         if constexpr (kShare) if (!p.b_resident) {
             int s = 0;
@@ -838,6 +917,41 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
         constexpr bool up2 = kUp2;
         const int rrow = up2 ? ((ty >> 1) * (p.tile_w >> 1) + (tx >> 1)) : row;
         const uint32_t rswz = static_cast<uint32_t>(rrow & 7);
+        if constexpr (kEpi == 2) {
+            // head tail: group eg = sub-pixel.  Per tile: stage the BN + ReLU'd bf16 tile for the second UMMA, then finish
+            // the PREVIOUS tile (its four dot products have had a whole tile's time to come back).
+            const int sub = eg;
+            const uint32_t a2 = smem_u32(sm.epi) + static_cast<uint32_t>(row) * 128;
+            const uint32_t d2 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + 256u;
+            const uint32_t tmain = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+            int itx = 0, pn = 0, poy = 0, pox = 0;
+            bool pvalid = false;
+            for (int u = u_first; u < num_units; u += u_stride, ++itx) {
+                const TileCoord t = decode_tile(p, unit_tile(u));
+                const int oy = t.y0 + ty, ox = t.x0 + tx;
+                const int b = sub * 2 + (itx & 1);
+                mbar_wait(&sm.tfull[0], itx & 1);
+                tc_fence_after();
+                head_tail_stage(p, tmain, a2 + static_cast<uint32_t>(b) * kABytes, swz, sub, &sm.tempty[0], lane);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.out_ready[b]);
+                if (itx > 0) {
+                    const int pb = sub * 2 + ((itx - 1) & 1);
+                    mbar_wait(&sm.slot_free[pb], ((itx - 1) >> 1) & 1);
+                    tc_fence_after();
+                    head_tail_store(p, ec.bias, d2 + static_cast<uint32_t>(pb * 16), pn, poy, pox, pvalid, sub);
+                }
+                pn = t.n; poy = oy; pox = ox;
+                pvalid = (oy < p.out_h) && (ox < p.out_w);
+            }
+            if (itx > 0) {
+                const int pb = sub * 2 + ((itx - 1) & 1);
+                mbar_wait(&sm.slot_free[pb], ((itx - 1) >> 1) & 1);
+                tc_fence_after();
+                head_tail_store(p, ec.bias, d2 + static_cast<uint32_t>(pb * 16), pn, poy, pox, pvalid, sub);
+            }
+        } else {
         int it = 0;
         int g = 0;          // CTA-wide 64-column chunk counter (every group counts the same sequence)
         int next_mine = eg;  // next chunk index this group takes
@@ -855,10 +969,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                    static_cast<uint32_t>(as * p.block_n);
             if (!p.epi_tma) {
-                if constexpr (kEpi == 2) {
-                    // every group takes one of the four sub-pixels of every tile (16 warps hide the load latency)
-                    epilogue_head_dot(p, smem_u32(sm.ss), taddr, t.n, oy, ox, valid, eg);
-                } else if ((it % G) != eg) {
+                if ((it % G) != eg) {
                     // direct stores: the groups take alternate tiles
                 } else {
                     for (int c = 0; c < p.block_n; c += 32) {
@@ -947,6 +1058,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p) {
                 else mbar_arrive(&sm.tempty[as]);
             }
         }
+        }  // kEpi != 2
     } else if (kGather) {
         // ===================================================================== gather producers (16 warps)
         constexpr int kPasses = kBlockM / (kGatherWarps * 4);  // 2: a pass = 64 rows, 8 lanes x 16 B per row
@@ -1152,6 +1264,7 @@ struct b200_igemm {
     int threads;
     int smem_bytes;
     Dcn2Plan* d2;  // B200_IGEMM_DCN_TMEM: the launch belongs to dcn2.cu
+    HeadConsts* hc;  // B200_EPI_HEAD_DOT: constant-bank payload (host copy, passed by value at launch)
 };
 
 static int pick_tile_w(int out_h, int out_w, int max_tw) {
@@ -1269,7 +1382,7 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     p.flags = d->flags;
     p.block_n = block_n;
     p.n_pad = d->n_pad;
-    p.ss_half = (d->flags & B200_EPI_HEAD_DOT) ? 512 : (d->n_pad > 256 ? d->n_pad : 256);
+    p.ss_half = (d->flags & B200_EPI_HEAD_DOT) ? 2048 : (d->n_pad > 256 ? d->n_pad : 256);  // HEAD_DOT: 16 KB of UMMA constants
     p.nacc = block_n > 256 ? 1 : 2;
     // 3x3 stride-1 convs share one (tile_h+2)-row activation box between the taps ky = 0..2 of a kernel column
     // ("share mode"): tall tiles (8 rows x 16 pixels) make that 2.4x less L2->SM traffic and a third of the barrier
@@ -1402,7 +1515,10 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     };
     int bufs = 0, ga = 1;
     bool ok;
-    if (!p.epi_tma) {
+    if (d->flags & B200_EPI_HEAD_DOT) {
+        bufs = 8;  // staging tiles of the second UMMA: 4 sub-pixels x 2 (see head_tail_stage)
+        ok = rings(cap - fixed - bufs * kABytes);
+    } else if (!p.epi_tma) {
         ok = rings(cap - fixed);
     } else {
         // Split the shared memory between mainloop stages and epilogue buffers by where the time goes:
@@ -1444,6 +1560,27 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     op->smem_bytes = fixed + a_st * a_bytes + (p.b_resident ? 0 : (fat ? b_st * 3 : a_st) * b_bytes) + bufs * kABytes;
 
     op->threads = (base_warps(op->gather) + (op->gather ? kGatherWarps : 0)) * 32;
+    if (d->flags & B200_EPI_HEAD_DOT) {  // constants of the head-tail epilogue: one small synchronous read-back at plan time
+        op->hc = new (std::nothrow) HeadConsts;
+        cudaError_t ce = op->hc ? cudaSuccess : cudaErrorMemoryAllocation;
+        if (ce == cudaSuccess) ce = cudaMemcpy(op->hc->w2, d->offsets, 256 * sizeof(float), cudaMemcpyDeviceToHost);
+        if (ce == cudaSuccess) ce = cudaMemcpy(&op->hc->bias, reinterpret_cast<const float*>(d->offsets) + 256, sizeof(float), cudaMemcpyDeviceToHost);
+        if (ce == cudaSuccess) ce = cudaMemcpy(op->hc->scale, d->scale, 256 * sizeof(float), cudaMemcpyDeviceToHost);
+        if (ce == cudaSuccess) ce = cudaMemcpy(op->hc->shift, d->shift, 256 * sizeof(float), cudaMemcpyDeviceToHost);
+        if (ce != cudaSuccess) {
+            delete op->hc;
+            delete op;
+            return set_error("igemm: reading the head-tail constants failed: %s", cudaGetErrorString(ce));
+        }
+        for (int i = 0; i < 256; ++i) {
+            if (op->hc->scale[i] != 1.0f) {
+                delete op->hc;
+                delete op;
+                return set_error("igemm: HEAD_DOT applies the shift inside the UMMA chain: fold the BN scale into the weights and "
+                                 "pass scale = 1 (scale[%d] = %g)", i, (double)op->hc->scale[i]);
+            }
+        }
+    }
     if (getenv("B200_VERBOSE"))
         fprintf(stderr, "igemm plan: mode %d k %d s %d N %d kb %d tile %dx%d share %d resident %d pair %d a_stages %d (x %d B) b_stages %d bufs %d ga %d smem %d\n",
                 p.mode, p.ksize, p.stride, p.block_n, p.k_blocks, p.tile_w, p.tile_h, p.a_kb, p.b_resident, op->pair, p.a_stages,
@@ -1578,23 +1715,23 @@ extern "C" int b200_igemm_launch(const b200_igemm* op, void* stream) {
     cfg.numAttrs = nattr;
     cudaError_t e;
     if (op->pair && (op->p.flags & B200_EPI_RES_UP2))
-        e = cudaLaunchKernelEx(&cfg, igemm_kernel<0, 1, true>, op->tm, op->p);
+        e = cudaLaunchKernelEx(&cfg, igemm_kernel<0, 1, true>, op->tm, op->p, NoConsts{});
     else if (op->pair)
-        e = cudaLaunchKernelEx(&cfg, igemm_kernel<0, 0, true>, op->tm, op->p);
+        e = cudaLaunchKernelEx(&cfg, igemm_kernel<0, 0, true>, op->tm, op->p, NoConsts{});
     else if (op->gather)
-        e = cudaLaunchKernelEx(&cfg, igemm_kernel<1>, op->tm, op->p);
+        e = cudaLaunchKernelEx(&cfg, igemm_kernel<1>, op->tm, op->p, NoConsts{});
     else if ((op->p.flags & B200_EPI_GELU) && op->p.a_kb > 1)
-        e = cudaLaunchKernelEx(&cfg, igemm_kernel<2, 3>, op->tm, op->p);
+        e = cudaLaunchKernelEx(&cfg, igemm_kernel<2, 3>, op->tm, op->p, NoConsts{});
     else if (op->p.flags & B200_EPI_GELU)
-        e = cudaLaunchKernelEx(&cfg, igemm_kernel<0, 3>, op->tm, op->p);
+        e = cudaLaunchKernelEx(&cfg, igemm_kernel<0, 3>, op->tm, op->p, NoConsts{});
     else if (op->p.a_kb > 1)
-        e = cudaLaunchKernelEx(&cfg, igemm_kernel<2>, op->tm, op->p);
+        e = cudaLaunchKernelEx(&cfg, igemm_kernel<2>, op->tm, op->p, NoConsts{});
     else if (op->p.flags & B200_EPI_HEAD_DOT)
-        e = cudaLaunchKernelEx(&cfg, igemm_kernel<0, 2>, op->tm, op->p);
+        e = cudaLaunchKernelEx(&cfg, igemm_kernel<0, 2>, op->tm, op->p, *op->hc);
     else if (op->p.flags & B200_EPI_RES_UP2)
-        e = cudaLaunchKernelEx(&cfg, igemm_kernel<0, 1>, op->tm, op->p);
+        e = cudaLaunchKernelEx(&cfg, igemm_kernel<0, 1>, op->tm, op->p, NoConsts{});
     else
-        e = cudaLaunchKernelEx(&cfg, igemm_kernel<0>, op->tm, op->p);
+        e = cudaLaunchKernelEx(&cfg, igemm_kernel<0>, op->tm, op->p, NoConsts{});
     if (e != cudaSuccess) {
         cudaGetLastError();
         return set_error("igemm launch failed: %s", cudaGetErrorString(e));
@@ -1611,6 +1748,7 @@ extern "C" int b200_igemm_debug_counters(unsigned long long* out) {
 
 extern "C" int b200_igemm_destroy(b200_igemm* op) {
     if (op && op->d2) dcn2_destroy(op->d2);
+    if (op) delete op->hc;
     delete op;
     return 0;
 }

@@ -79,9 +79,11 @@ class PreparedWeights:
         st, tt = _bn_fold(ht[0].bn)
         P["head.0"] = (w0.contiguous(), torch.cat([to(sb), to(st)]).contiguous(), torch.cat([to(tb), to(tt)]).contiguous())
         for br, seq in (("bin", hb), ("thr", ht)):
-            w = ops.pack_convT_weight(to(seq[1].weight), 256)
+            # BN scale folded into the transposed conv's weights (fp32, before the bf16 rounding): the fused head-tail
+            # epilogue adds the shift inside the UMMA chain and fetches no per-column constants (B200_EPI_HEAD_DOT)
             s, t = _bn_fold(seq[2], to(seq[1].bias))
-            P[f"head.{br}.1"] = (w, to(s).repeat(4).contiguous(), to(t).repeat(4).contiguous())
+            w = ops.pack_convT_weight(to(seq[1].weight) * to(s).view(1, -1, 1, 1), 256)
+            P[f"head.{br}.1"] = (w, torch.ones(256, device=device), to(t).repeat(4).contiguous())
             # last ConvTranspose2d(64 -> 1): [ci][dy*2+dx] fp32, consumed by the head-tail kernel
             P[f"head.{br}.4"] = (to(seq[4].weight).reshape(64, 4).contiguous(), float(seq[4].bias.detach().float().item()))
         self.P = P

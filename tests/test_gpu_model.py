@@ -253,7 +253,16 @@ def test_dbnet_vs_oracle_batch2_odd_tiles():
     out4 = m(x.cuda())
     torch.cuda.synchronize()
     for k in out:
-        assert torch.equal(out[k], out2[k]) and torch.equal(out[k], out3[k]) and torch.equal(out[k], out4[k])
+        assert torch.equal(out2[k], out3[k]) and torch.equal(out2[k], out4[k])
+    # tapped run = unfused head tail (64-channel map stored, last transposed conv on the CUDA cores with fp32 weights);
+    # plain run = tail folded into the first transposed conv's epilogue as a second UMMA (bf16 weights, tensor-core
+    # accumulation order): same rounding of the 64-channel map, logits equal up to the bf16 rounding of 64 weights
+    for k in ("bin_logits", "thresh_logits"):
+        assert rel_rms(out2[k], out[k]) < 4e-3, (k, rel_rms(out2[k], out[k]))
+    for k in ("binary", "thresh"):
+        assert (out2[k] - out[k]).abs().max().item() < 2e-2, (k, (out2[k] - out[k]).abs().max().item())
+    # the DB step (k = 50) turns a 1e-3 probability difference near binary == thresh into a visible one: mean, not max
+    assert (out2["thresh_binary"] - out["thresh_binary"]).abs().mean().item() < 5e-3
     m.use_cuda_graph = False
 
 
@@ -385,7 +394,12 @@ def test_config2_full_size_properties():
     rep = m(x)
     torch.cuda.synchronize()
     for k in out:
-        assert torch.equal(out[k], rep[k]), f"graph replay differs in {k}"
+        if not torch.equal(out[k], rep[k]):
+            d = (out[k] != rep[k])
+            idx = d.nonzero()
+            raise AssertionError(f"graph replay differs in {k}: {int(d.sum())} elements, images {sorted(set(idx[:, 0].tolist()))}, "
+                                 f"rows {int(idx[:, 2].min())}..{int(idx[:, 2].max())}, cols {int(idx[:, 3].min())}..{int(idx[:, 3].max())}, "
+                                 f"max |diff| {float((out[k] - rep[k]).abs().max()):.3g}")
     m.use_cuda_graph = False
     for i in (0, 7, 15):
         alone = m(x[i:i + 1].contiguous())

@@ -62,6 +62,44 @@ def run_head_dot(iters=20):
     print(f"head-dot convT   {e0.elapsed_time(e1) / iters:7.3f} ms  {op.info()}", flush=True)
 
 
+def run_offset(name, b, h, w, ci, s, iters=20):
+    """offset_mask_conv (3x3 -> 27, N padded to 32) with the sampling-record epilogue."""
+    dev = "cuda"
+    x = torch.randn(b, h, w, ci, device=dev).to(torch.bfloat16)
+    wt = (torch.randn(32, 9 * ci, device=dev) / (9 * ci) ** 0.5).to(torch.bfloat16)
+    sc, sh = torch.ones(32, device=dev), torch.zeros(32, device=dev)
+    oh, ow = h // s, w // s
+    y = torch.empty(b, oh, ow, 9, 4, device=dev, dtype=torch.int32)
+    op = ops.Igemm(ops.IGEMM_CONV, x, wt, sc, sh, y, batch=b, in_h=h, in_w=w, in_c=ci, out_c=32, ksize=3, stride=s,
+                   flags=ops.EPI_DCN_COORDS, out_ld=32, name=name)
+    for _ in range(3):
+        op()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        op()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    if int(os.environ.get("B200_DEBUG", "0")) & 16:
+        import ctypes as C
+        from ocr_vi_invoice_b200 import _lib
+        buf = (C.c_ulonglong * 16)()
+        _lib.load().b200_igemm_debug_counters(buf)
+        op(); torch.cuda.synchronize()
+        _lib.load().b200_igemm_debug_counters(buf)
+        names = ["A.empty", "B.empty", "mma.tempty", "mma.a_full", "mma.b_full", "dma.out_ready", "dma.wait_read", "epi.tfull", "epi.slot", "total", "mma.issue"]
+        print("   " + "  ".join(f"{n}={buf[i]}" for i, n in enumerate(names)))
+    print(f"{name:28s} {ms:7.3f} ms  {op.flops / ms / 1e9:8.1f} TF/s  {op.info()}", flush=True)
+
+
+if __name__ == "__main__" and os.environ.get("EPI_SET") == "offset":
+    run_offset("layer2 offset s1", 16, 128, 128, 128, 1)
+    run_offset("layer2 offset s2", 16, 256, 256, 128, 2)
+    run_offset("layer3 offset s1", 16, 64, 64, 256, 1)
+    run_offset("layer4 offset s1", 16, 32, 32, 512, 1)
+    sys.exit(0)
 if __name__ == "__main__" and os.environ.get("EPI_SET") == "head":
     run_head_dot()
     sys.exit(0)
