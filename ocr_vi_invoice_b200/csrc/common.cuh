@@ -70,8 +70,13 @@ __device__ __forceinline__ bool elect_one() {
 // writes are visible.  pdl_launch_dependents() lets the NEXT kernel's blocks be scheduled as soon as every block of
 // this grid has issued it (they still wait in their own pdl_wait() for this grid to finish).  Both are no-ops in a
 // launch without the attribute.
+#ifdef B200_ENABLE_PDL
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#else
+__device__ __forceinline__ void pdl_wait() {}
+__device__ __forceinline__ void pdl_launch_dependents() {}
+#endif
 
 // ---------------------------------------------------------------------------------- proxies / fences
 __device__ __forceinline__ void fence_proxy_async_smem() {

@@ -954,8 +954,14 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
         } else {
         int it = 0;
         int g = 0;          // CTA-wide 64-column chunk counter (every group counts the same sequence)
-        int next_mine = eg;  // next chunk index this group takes
-        int slot = eg;       // its buffer (g % B) and the parity of that buffer's barriers ((g / B) & 1); GA <= B
+        // Chunk g lives in staging buffer g % B; a buffer ALWAYS belongs to the same group (buffer s -> group s % GA).
+        // Round-robin by chunk index (g % GA) let two different groups take consecutive uses of one buffer whenever B is not
+        // a multiple of GA, and an mbarrier wait only sees the phase PARITY: the group of use k+1 could reach its wait while
+        // the residual box of use k had not landed yet (barrier still in phase k, bit != the parity it waits for -> the wait
+        // passes at once) and run over the buffer.  Seen as one CTA's chunk g half wrong and chunk g + B wrong, once in ~1000
+        // launches of the 64 -> 256 residual conv (B = 7, GA = 4); found with tools/stress_mix.py.  With one owner per buffer
+        // the uses of a buffer are in that group's program order, so a waiter is never a phase ahead.
+        int slot = 0, owner = 0;  // buffer of chunk g, the group that owns it, and the parity of its barriers ((g / B) & 1)
         uint32_t par = 0;
         for (int u = u_first; u < num_units; u += u_stride, ++it) {
                 const int tile = unit_tile(u); (void)tile;
@@ -983,12 +989,16 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
                 const int nchunks = chunks_of(p, t.nb);
                 const uint32_t ss_s = ss_s0 + static_cast<uint32_t>(t.nb * p.block_n) * 4;
                 for (int c = 0; c < nchunks; ++c, ++g) {
-                    if (g != next_mine) continue;
-                    next_mine += GA;
-                    const uint32_t buf = smem_u32(sm.epi) + static_cast<uint32_t>(slot) * kABytes;
+                    const int my_slot = slot;
+                    const uint32_t my_par = par;
+                    const bool is_mine = (owner == eg);
+                    if (++owner == GA) owner = 0;
+                    if (++slot == B) { slot = 0; owner = 0; par ^= 1; }
+                    if (!is_mine) continue;
+                    const uint32_t buf = smem_u32(sm.epi) + static_cast<uint32_t>(my_slot) * kABytes;
                     const uint32_t mine = buf + static_cast<uint32_t>(row) * 128;
                     const uint32_t rsd = buf + static_cast<uint32_t>(rrow) * 128;
-                    B200_TIMED_WAIT(8, if (p.res_tma) mbar_wait(&sm.res_full[slot], par); else mbar_wait(&sm.slot_free[slot], par ^ 1));
+                    B200_TIMED_WAIT(8, if (p.res_tma) mbar_wait(&sm.res_full[my_slot], my_par); else mbar_wait(&sm.slot_free[my_slot], my_par ^ 1));
                     uint4 rup[kUp2 ? 8 : 1];
                     if constexpr (up2) {  // the 4 KB half-resolution box is shared by four pixels: read it before anyone overwrites
 #pragma unroll
@@ -1045,9 +1055,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&sm.out_ready[slot]);
-                    slot += GA;
-                    if (slot >= B) { slot -= B; par ^= 1; }
+                    if (lane == 0) mbar_arrive(&sm.out_ready[my_slot]);
                 }
             }
             // accumulator fully read by this warp (or not needed): hand the TMEM buffer back to the MMA warp
@@ -1547,6 +1555,21 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
             return set_error("igemm: not enough shared memory for an epilogue buffer");
         }
         if (ga > bufs - 1) ga = bufs > 1 ? bufs - 1 : 1;
+        // A staging buffer belongs to one epilogue group (buffer s -> group s % ga, see the kernel): a buffer count that is a
+        // multiple of ga keeps the groups evenly loaded.  Give up a pipeline stage for one more buffer if that gets there
+        // (64 -> 256 residual conv: 4 stages + 7 buffers -> 3 stages + 8 buffers), else keep the uneven split.
+        if (ok && ga > 1 && bufs > ga && (bufs % ga) != 0 && !getenv("B200_EPI_UNEVEN")) {
+            const int up = (bufs / ga + 1) * ga, need = (up - bufs) * kABytes;
+            const int stage_bytes = a_bytes + (p.b_resident ? 0 : (fat ? 0 : b_bytes));
+            const int give = (need + stage_bytes - 1) / stage_bytes;
+            const int min_st = (p.k_blocks >= 4 && !fat) ? 3 : 2;
+            if (!fat && up <= kMaxEpiBufs && a_st - give >= min_st) {
+                a_st -= give;
+                if (!p.b_resident) b_st = a_st;
+                bufs = up;
+            }
+        }
+        if (const char* e = getenv("B200_EPI_BUFS")) { if (atoi(e) >= 2 && atoi(e) <= bufs) { bufs = atoi(e); if (ga > bufs - 1) ga = bufs - 1; } }
     }
     if (!ok) {
         delete op;

@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--test-model", action="store_true")
     ap.add_argument("--poison", action="store_true")
     ap.add_argument("--cycles", type=int, default=0)
+    ap.add_argument("--burst", type=int, default=3)
+    ap.add_argument("--pack", type=int, default=0, help="GiB block to pre-cache so plan buffers are carved back to back")
     ap.add_argument("--heat", type=int, default=0, help="8192^3 bf16 matmuls between cycles")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
@@ -38,6 +40,12 @@ def main():
     else:
         model = randomize_(DBNetPP(pretrained=False), 0).to(dev).eval()
         x = torch.from_numpy(synthetic_batch(min(a.batch, 4), a.size, a.size, seed=0)).repeat((a.batch + 3) // 4, 1, 1, 1)[:a.batch].to(dev)
+    if a.pack:
+        # make the caching allocator carve every plan buffer out of ONE cached block: buffers then sit back to back with no
+        # slack between them (as inside a long-lived process), so an out-of-bounds access of a kernel hits a live neighbour
+        big = torch.empty(a.pack << 30, dtype=torch.uint8, device=dev)
+        big.fill_(0x7f)
+        del big
     if a.cycles:
         # the sequence of tests/test_gpu_model.py::test_config2_full_size_properties, over and over on fresh plans: first eager
         # forward vs CUDA-graph replays, with per-step checksums to localise a difference; optional heating in between
@@ -136,6 +144,32 @@ def main():
                 print(f"replay {r}: {k} differs in {int(d.sum())} elements, first {idx[0].tolist()} last {idx[-1].tolist()}", flush=True)
                 break
     print("graph replays identical to eager" if not ndiff else f"GRAPH REPLAY DIFFERS: {ndiff}")
+    # back-to-back forwards with no host synchronisation in between (what a serving loop does): replay, replay, check
+    nb = 0
+    for r in range(a.runs):
+        for _ in range(a.burst):
+            rep = model(x)
+        torch.cuda.synchronize()
+        cs = [checksum(t) for _, t in outs]
+        bad_steps = [name for (name, _), c0, c1 in zip(outs, ref, cs) if c0 != c1]
+        if bad_steps or not torch.equal(rep["binary"], eager["binary"]):
+            nb += 1
+            d = (rep["binary"] != eager["binary"])
+            imgs = sorted(set(d.nonzero()[:, 0].tolist())) if d.any() else []
+            print(f"burst {r}: differs; first step {bad_steps[:3]}; images {imgs}", flush=True)
+    print(f"back-to-back replays: {nb} bad bursts of {a.runs}")
+    model.use_cuda_graph = False
+    nb = 0
+    for r in range(a.runs):
+        for _ in range(a.burst):
+            rep = model(x)
+        torch.cuda.synchronize()
+        cs = [checksum(t) for _, t in outs]
+        bad_steps = [name for (name, _), c0, c1 in zip(outs, ref, cs) if c0 != c1]
+        if bad_steps or not torch.equal(rep["binary"], eager["binary"]):
+            nb += 1
+            print(f"eager burst {r}: differs; first step {bad_steps[:3]}", flush=True)
+    print(f"back-to-back eager forwards: {nb} bad bursts of {a.runs}")
 
 
 if __name__ == "__main__":
