@@ -9,7 +9,7 @@ N>1 (launched under torchrun by the driver): every rank runs the same per-GPU ba
 independent: weak scaling, no data-path collective); time = max over ranks, value = N*16*K / time.
 
 Keys beyond the base contract: `roofline` (dominant kernel = the TMA-fed tcgen05 conv kernel, tensor-bound),
-`dcn` (the fused deformable-conv kernel's own tensor-pipe figure, BASELINE's second metric), `cpu_baseline`
+`dcn` (the fused deformable-conv kernels' own tensor-pipe figure, BASELINE's second metric, also per backbone stage), `cpu_baseline`
 (the oracle = the reference's fp32 torch/torchvision CPU path, timed on this box's cores on a bounded sample),
 `e2e` (host pinned fp32 batch -> H2D -> forward -> post-processing -> D2H of the box records, through the
 drop-in DBNetPP / DBPostProcessor API), `clocks`, `gpu_launches`.
@@ -604,16 +604,27 @@ def main():
         conv, dcn = by_kind.get("conv", {"ms": 1e-9, "flops": 0, "n": 0}), by_kind.get("dcn", {"ms": 1e-9, "flops": 0, "n": 0})
         conv_tf = conv["flops"] / (conv["ms"] * 1e-3) / 1e12
         dcn_tf = dcn["flops"] / (dcn["ms"] * 1e-3) / 1e12
-        roofline = {"kernel": "igemm_kernel<0|2> (TMA-fed tcgen05 conv, %d launches/step)" % conv["n"], "bound": "tensor",
+        roofline = {"kernel": "igemm_kernel<0|2> (TMA-fed tcgen05 conv family incl. the cta_group::2 pair mode and the UMMA head tail, "
+                              "%d launches/step)" % conv["n"], "bound": "tensor",
                     "achieved": round(conv_tf, 2), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                     "frac": round(conv_tf / pk["tf_sustained"], 4), "traffic": None,
                     "peak_source": pk["source"] + " sustained (kernel timed inside a long step)",
                     "share_of_step": round(conv["ms"] / tot_ms, 4),
                     "algorithmic_gflop_per_step": round(conv["flops"] / 1e9, 1)}
-        dcn_line = {"kernel": "igemm_kernel<1> (fused sampling + tcgen05 DCN, %d launches/step)" % dcn["n"],
+        dcn_line = {"kernel": "dcn2_kernel (c3 / c4: sampled A operand in tensor memory) + igemm_kernel<1> (c5, N = 512): fused "
+                              "sampling + tcgen05 DCN, %d launches/step" % dcn["n"],
                     "achieved": round(dcn_tf, 2), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                     "frac": round(dcn_tf / pk["tf_sustained"], 4), "share_of_step": round(dcn["ms"] / tot_ms, 4),
                     "algorithmic_gflop_per_step": round(dcn["flops"] / 1e9, 1)}
+        # per backbone stage (BASELINE configs[2] quotes the stage shapes): algorithmic FLOPs / summed launch time
+        stages = {}
+        for name, kind, ms, fl in launches:
+            if kind == "dcn":
+                st_ = {"layer2": "c3", "layer3": "c4", "layer4": "c5"}.get(name.split(".")[0], name)
+                a_ = stages.setdefault(st_, [0.0, 0.0, 0])
+                a_[0] += ms; a_[1] += fl; a_[2] += 1
+        dcn_line["by_stage"] = {k: {"launches": v[2], "ms": round(v[0], 4), "tflops": round(v[1] / (v[0] * 1e-3) / 1e12, 1),
+                                    "frac": round(v[1] / (v[0] * 1e-3) / 1e12 / pk["tf_sustained"], 4)} for k, v in stages.items()}
         # ncu DRAM traffic of the heaviest launch of the dominant kernel (committed capture; null if absent)
         traffic = None
         tfile = ROOT / "profiles" / "ncu_traffic.json"
