@@ -64,6 +64,12 @@ enum {
                                * scale into the weights.                                                      */
     B200_EPI_GELU       = 128, /* v = GELU(v) (erf form) BEFORE the residual add: the recogniser's Linear / conv +
                                   GELU layers (model/rec2/svtrv2.py:33,51,54,117); bf16 outputs, out_c % 64 == 0 */
+    B200_EPI_CHAIN      = 256, /* a SECOND 1x1 GEMM chained onto the epilogue (torchvision Bottleneck: conv3 + bn3 + identity + ReLU
+                                  of one block, resnet.py:157-163, followed by conv1 + bn1 + ReLU of the NEXT block, :146-148):
+                                  y = the normal output (bf16, 256 channels, with RES + RELU as flagged); every staged 64-channel
+                                  chunk of y is also the A operand of y2[pixel][chain_n] += chunk x chain_w^T, and after the tile's
+                                  last chunk y2 = relu?(y2 * chain_scale + chain_shift) is stored as bf16: the block output is never
+                                  re-read.  CONV mode, 1x1, out_c == n_pad == 256, chain_n == 64, residual required.          */
     B200_EPI_DCN_COORDS = 32  /* offset_mask_conv only (out_c = 32): instead of the raw 27 channels, store
                                  the b200_dcn_coord records of the 9 taps, y = [pixel][9] records, so
                                  the DCN producers do no coordinate arithmetic (dcn.py:44-46 fused)    */
@@ -106,6 +112,15 @@ typedef struct b200_igemm_desc {
     void*        y;        /* output                                                              */
     const void*  offsets;  /* DCN: b200_dcn_coord [batch*out_h*out_w][9], written by an offset conv with
                               B200_EPI_DCN_COORDS or by b200_dcn_coords() from raw offsets        */
+    /* B200_EPI_CHAIN only (NULL / 0 otherwise) */
+    const void*  chain_w;     /* [chain_n][out_c] bf16, K-major (what ops.pack_conv_weight gives for the next 1x1 conv) */
+    const float* chain_scale; /* [chain_n] */
+    const float* chain_shift; /* [chain_n] */
+    void*        chain_y;     /* second output, NHWC bf16, chain_ld elements per pixel               */
+    int32_t      chain_n;     /* 64                                                                  */
+    int32_t      chain_ld;
+    int32_t      chain_relu;  /* ReLU on the second output                                           */
+    int32_t      chain_reserved;
 } b200_igemm_desc;
 
 typedef struct b200_igemm b200_igemm; /* opaque: TMA descriptors + launch geometry */

@@ -13,7 +13,7 @@ from pathlib import Path
 _LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libdbnet_b200.so"
 
 IGEMM_CONV, IGEMM_STEM, IGEMM_DCN, IGEMM_DCN_TMEM = 0, 1, 2, 3
-EPI_RELU, EPI_RES, EPI_RES_UP2, EPI_OUT_F32, EPI_SHUFFLE2, EPI_DCN_COORDS, EPI_HEAD_DOT, EPI_GELU = 1, 2, 4, 8, 16, 32, 64, 128
+EPI_RELU, EPI_RES, EPI_RES_UP2, EPI_OUT_F32, EPI_SHUFFLE2, EPI_DCN_COORDS, EPI_HEAD_DOT, EPI_GELU, EPI_CHAIN = 1, 2, 4, 8, 16, 32, 64, 128, 256
 
 
 class B200Error(RuntimeError):
@@ -28,6 +28,8 @@ class IgemmDesc(C.Structure):
         ("shuf_c", C.c_int32), ("block_n", C.c_int32), ("x_ld", C.c_int32), ("stride_w", C.c_int32),
         ("x", C.c_void_p), ("w", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
         ("residual", C.c_void_p), ("y", C.c_void_p), ("offsets", C.c_void_p),
+        ("chain_w", C.c_void_p), ("chain_scale", C.c_void_p), ("chain_shift", C.c_void_p), ("chain_y", C.c_void_p),
+        ("chain_n", C.c_int32), ("chain_ld", C.c_int32), ("chain_relu", C.c_int32), ("chain_reserved", C.c_int32),
     ]
 
 

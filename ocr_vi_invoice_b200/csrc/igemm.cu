@@ -86,13 +86,20 @@ struct IgemmParams {
     int nacc;      // TMEM accumulators: 2 (tile i+1's MMAs overlap tile i's epilogue) or 1 (block_n = 512 fills TMEM)
     int b_rows;    // weight rows one CTA stages per k-block: block_n, or block_n / 2 in pair mode (cta_group::2)
     int num_units; // pair mode: units of work = (pair of pixel tiles, n-block); otherwise == num_tiles
+    // B200_EPI_CHAIN (kEpi == 4): a second 1x1 GEMM over the staged output chunks
+    int chain_n;        // its N (64)
+    int chain_bytes;    // resident second weight matrix: chunks x chain_n x 128 bytes, after the first one in shared memory
+    int chain_relu;
+    const float* chain_scale;
+    const float* chain_shift;
 };
 
 struct TmapPack {
     CUtensorMap a[4];
     CUtensorMap b;
-    CUtensorMap out[4];
+    CUtensorMap out[4];  // (B200_EPI_CHAIN: out[1] = the second output)
     CUtensorMap res;
+    CUtensorMap b2;      // B200_EPI_CHAIN: second weight matrix, box {64, chain_n}
 };
 
 struct SmemLayout {
@@ -120,7 +127,7 @@ __device__ __forceinline__ SmemLayout carve(uint8_t* raw, const IgemmParams& p) 
     SmemLayout s;
     s.a = base;
     s.b = s.a + p.a_stages * p.a_bytes;
-    s.epi = s.b + (p.b_resident ? p.k_blocks : (p.a_kb > 1 ? p.b_stages * 3 : p.a_stages)) * p.b_rows * 128;
+    s.epi = s.b + (p.b_resident ? p.k_blocks : (p.a_kb > 1 ? p.b_stages * 3 : p.a_stages)) * p.b_rows * 128 + p.chain_bytes;
     uint8_t* rest = s.epi + p.epi_bufs * kABytes;
     s.ss = reinterpret_cast<float*>(rest);
     uint8_t* bars = rest + 8 * p.ss_half;
@@ -437,8 +444,9 @@ __device__ __forceinline__ void gelu_as2(float& x0, float& x1) {
 // others registers or instructions (the MMA warp and the epilogue warps are latency-critical).
 // kEpi: 0 = common epilogue; 1 = adds a nearest-upsampled half-resolution residual (FPN top-down path, keeps eight more
 // vector registers alive); 2 = DB-head tail folded in (B200_EPI_HEAD_DOT); 3 = GELU before the residual add
-// (B200_EPI_GELU, the recogniser's Linear / conv + GELU layers).  Own instantiations: the common epilogue must
-// not pay registers (spills) for the rare ones.
+// (B200_EPI_GELU, the recogniser's Linear / conv + GELU layers); 4 = a second 1x1 GEMM chained onto the staged output chunks
+// (B200_EPI_CHAIN: conv3 + residual + ReLU of one Bottleneck and conv1 + BN + ReLU of the next in one launch).  Own
+// instantiations: the common epilogue must not pay registers (spills) for the rare ones.
 // kPair: cta_group::2 -- the two CTAs of a cluster run one 256-pixel x block_n UMMA per K step (variant 0 only): each stages
 // its own 128-pixel A tile and HALF of the weight rows, rank 0 issues the MMAs and multicasts the commits, each CTA's
 // epilogue drains its own TMEM.  Per k-block an SM pulls A + B/2 instead of A + B through the L2 fabric, which is what the
@@ -469,7 +477,8 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
     };
     const int stages = p.a_stages;  // A ring depth (the gather producers fill it too)
     // head tail (kEpi 2): one 256-column accumulator + 4 sub-pixels x 2 x 16 columns for the second UMMA's results
-    const uint32_t tmem_cols = (kEpi == 2) ? 512u : ((p.nacc * p.block_n < 32) ? 32u : static_cast<uint32_t>(p.nacc * p.block_n));
+    // chain (kEpi 4): one 256-column accumulator + 2 x chain_n columns for the second GEMM
+    const uint32_t tmem_cols = (kEpi == 2 || kEpi == 4) ? 512u : ((p.nacc * p.block_n < 32) ? 32u : static_cast<uint32_t>(p.nacc * p.block_n));
 
     // Programmatic dependent launch: the next launch of the stream may be scheduled onto SMs as this grid's blocks
     // retire; its prologue (below, up to pdl_wait) then overlaps our tail.  Nothing before pdl_wait() touches
@@ -490,6 +499,10 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
         }
         if (p.epi_tma) tma_prefetch_desc(&tm.out[0]);
         if (p.res_tma) tma_prefetch_desc(&tm.res);
+        if constexpr (kEpi == 4) {
+            tma_prefetch_desc(&tm.out[1]);
+            tma_prefetch_desc(&tm.b2);
+        }
     }
     if (warp == 1) {
         if (lane == 0) {
@@ -506,6 +519,12 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
             for (int a = 0; a < 2; ++a) {
                 mbar_init(&sm.tfull[a], 1);
                 mbar_init(&sm.tempty[a], (kPair ? 2 : 1) * 4 * G);  // pair: the epilogue warps of BOTH CTAs release rank 0's barrier
+            }
+            if constexpr (kEpi == 4) {
+                for (int a = 0; a < 2; ++a) {
+                    mbar_init(&sm.b_full[a], 1);   // d2_full: the chained GEMM's accumulator of tile parity a is complete
+                    mbar_init(&sm.b_empty[a], 4);  // d2_empty: the four warps of the group that drained it
+                }
             }
             mbar_init(sm.b_ready, 1);
             for (int a = 0; a < kMaxEpiBufs; ++a) {
@@ -562,6 +581,12 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
             sm.ss[i] = __ldg(p.scale + i);
             sm.ss[p.ss_half + i] = __ldg(p.shift + i);
         }
+        if constexpr (kEpi == 4) {  // the chained GEMM's columns follow the layer's own: "columns n_pad .. n_pad + chain_n"
+            for (int i = threadIdx.x; i < p.chain_n; i += blockDim.x) {
+                sm.ss[p.n_pad + i] = __ldg(p.chain_scale + i);
+                sm.ss[p.ss_half + p.n_pad + i] = __ldg(p.chain_shift + i);
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -578,9 +603,14 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
         // (converged warp, one elected lane issues -- see the MMA warp)
         if (p.b_resident) {  // small weight matrix: fetch it once, every tile multiplies against the same copy
             if (elect_one()) {
-                mbar_arrive_expect_tx(sm.b_ready, p.k_blocks * b_bytes);
+                mbar_arrive_expect_tx(sm.b_ready, p.k_blocks * b_bytes + p.chain_bytes);
                 for (int kb = 0; kb < p.k_blocks; ++kb)
                     tma_load_2d(sm.b + kb * b_bytes, &tm.b, sm.b_ready, kb * kBlockK, 0);
+                if constexpr (kEpi == 4) {  // second weight matrix, one [chain_n x 64] k-block per output chunk
+                    uint8_t* w2 = sm.epi - p.chain_bytes;
+                    for (int c = 0; c < p.n_pad / 64; ++c)
+                        tma_load_2d(w2 + c * p.chain_n * 128, &tm.b2, sm.b_ready, c * kBlockK, 0);
+                }
             }
             __syncwarp();
         }
@@ -747,7 +777,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
         } else {
             // N = 512 (gather variant only): two N = 256 instructions per K step, one accumulator
             const bool wide = kGather && p.block_n > 256;
-            const int nacc = kGather ? p.nacc : (kEpi == 2 ? 1 : 2);
+            const int nacc = kGather ? p.nacc : ((kEpi == 2 || kEpi == 4) ? 1 : 2);
             const uint32_t idesc_l = kPair ? umma_idesc_bf16_2sm(static_cast<uint32_t>(p.block_n)) : (wide ? umma_idesc_bf16(256u) : idesc);
             for (int u = u_first; u < num_units; u += u_stride, ++it) {
                 const int tile = unit_tile(u); (void)tile;
@@ -803,7 +833,56 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
         // buffer g % B.  After the store of chunk g is queued, the store of chunk g-1 has surely read its buffer
         // (wait_group.read 1), so that buffer is recycled: the residual box of chunk g-1+B is loaded into it (B-1 chunks
         // of prefetch), or it is marked free.
-        if (p.epi_tma) {
+        if constexpr (kEpi == 4) {
+            // Chain: a tile is 4 main chunks (residual prefetched, stored to y, multiplied by warp 3) + 1 tail chunk (the
+            // chained GEMM's 64 columns: no residual, stored to the second output).  A main chunk's buffer is recycled when
+            // BOTH its store has read it and its UMMAs have completed (chain_done = slot_free barrier).
+            const int B = p.epi_bufs, NC = p.n_pad >> 6;
+            int ld_u = u_first, ld_chunk = 0;
+            auto issue_load = [&](int slot) {
+                if (ld_u >= num_units) return;
+                if (ld_chunk < NC) {
+                    const TileCoord t = decode_tile(p, unit_tile(ld_u));
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&sm.res_full[slot], p.res_bytes);
+                        tma_load_4d(sm.epi + slot * kABytes, &tm.res, &sm.res_full[slot], ld_chunk * 64, t.x0, t.y0, t.n);
+                    }
+                } else if (elect_one()) {
+                    mbar_arrive(&sm.res_full[slot]);  // tail chunk: nothing to load, the buffer is simply free
+                }
+                __syncwarp();
+                if (++ld_chunk == NC + 1) { ld_chunk = 0; ld_u += u_stride; }
+            };
+            for (int i = 0; i < B; ++i) issue_load(i);
+            int g = 0, slot = 0, rslot = 0;
+            uint32_t par = 0, cd_par = 0;  // cd_par: per-buffer parity of the chain_done barrier (bit s)
+            bool prev_main = false;
+            for (int u = u_first; u < num_units; u += u_stride) {
+                const TileCoord t = decode_tile(p, unit_tile(u));
+                for (int c = 0; c <= NC; ++c, ++g) {
+                    mbar_wait(&sm.out_ready[slot], par);
+                    if (elect_one()) {
+                        if (c < NC) tma_store_4d(&tm.out[0], sm.epi + slot * kABytes, c * 64, t.x0, t.y0, t.n);
+                        else tma_store_4d(&tm.out[1], sm.epi + slot * kABytes, 0, t.x0, t.y0, t.n);
+                        bulk_commit();
+                        if (g >= 1) bulk_wait_read1();
+                    }
+                    __syncwarp();
+                    if (g >= 1) {
+                        if (prev_main) {  // chunk g-1 was multiplied too
+                            mbar_wait(&sm.slot_free[rslot], (cd_par >> rslot) & 1u);
+                            cd_par ^= 1u << rslot;
+                        }
+                        issue_load(rslot);
+                        if (++rslot == B) rslot = 0;
+                    }
+                    prev_main = (c < NC);
+                    if (++slot == B) { slot = 0; par ^= 1; }
+                }
+            }
+            if (elect_one()) bulk_wait_all();
+            __syncwarp();
+        } else if (p.epi_tma) {
             const int B = p.epi_bufs, L = (B > 1) ? 1 : 0;
             constexpr bool up2 = kUp2;
             int ld_u = u_first, ld_chunk = 0;
@@ -875,6 +954,35 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
                     }
                     __syncwarp();
                 }
+            }
+        }
+        if constexpr (kEpi == 4) {
+            // chain: y2[128 x chain_n] += staged chunk [128 x 64] x W2[chain_n x 64]^T for the tile's main chunks, in order
+            const int B = p.epi_bufs, NC = p.n_pad >> 6;
+            const uint32_t idesc2 = umma_idesc_bf16(static_cast<uint32_t>(p.chain_n));
+            const uint32_t a2 = smem_u32(sm.epi), w2 = smem_u32(sm.epi) - static_cast<uint32_t>(p.chain_bytes);
+            mbar_wait(sm.b_ready, 0);
+            int it = 0, slot = 0;
+            uint32_t par = 0;
+            for (int u = u_first; u < num_units; u += u_stride, ++it) {
+                mbar_wait(&sm.b_empty[it & 1], ((it >> 1) & 1) ^ 1);  // the tile two back has been drained from these columns
+                tc_fence_after();
+                const uint32_t d2 = tmem_base + 256u + static_cast<uint32_t>((it & 1) * p.chain_n);
+                for (int c = 0; c < NC; ++c) {
+                    mbar_wait(&sm.out_ready[slot], par);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_sw128(a2 + static_cast<uint32_t>(slot) * kABytes);
+                    const uint64_t db = umma_desc_sw128(w2 + static_cast<uint32_t>(c * p.chain_n * 128));
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k) umma_bf16(d2, da + 2 * k, db + 2 * k, idesc2, (c | k) ? 1u : 0u);
+                        umma_commit(&sm.slot_free[slot]);            // chain_done: the buffer may be recycled
+                        if (c == NC - 1) umma_commit(&sm.b_full[it & 1]);  // d2_full
+                    }
+                    __syncwarp();
+                    if (++slot == B) { slot = 0; par ^= 1; }
+                }
+                if (++slot == B) { slot = 0; par ^= 1; }  // the tile's tail chunk is not multiplied
             }
         }
         // weight producer of the share mode:
@@ -966,8 +1074,8 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
         for (int u = u_first; u < num_units; u += u_stride, ++it) {
                 const int tile = unit_tile(u); (void)tile;
             const TileCoord t = decode_tile(p, tile);
-            const int as = (!kGather || p.nacc == 2) ? (it & 1) : 0;
-            const uint32_t aph = (!kGather || p.nacc == 2) ? ((it >> 1) & 1) : (it & 1);
+            const int as = (kEpi == 4) ? 0 : ((!kGather || p.nacc == 2) ? (it & 1) : 0);
+            const uint32_t aph = (kEpi == 4) ? (it & 1) : ((!kGather || p.nacc == 2) ? ((it >> 1) & 1) : (it & 1));
             const int oy = t.y0 + ty, ox = t.x0 + tx;
             const bool valid = (oy < p.out_h) && (ox < p.out_w);
             B200_TIMED_WAIT(7, mbar_wait(&sm.tfull[as], aph));
@@ -1064,6 +1172,65 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
             if (lane == 0) {
                 if constexpr (kPair) mbar_arrive_cluster(mapa_u32(smem_u32(&sm.tempty[as]), 0));
                 else mbar_arrive(&sm.tempty[as]);
+            }
+            if constexpr (kEpi == 4) {
+                // tail chunk of the tile: the chained GEMM's chain_n (= 64) columns, BN + ReLU, bf16, staged for the DMA warp
+                if (eg < GA) {
+                    const int my_slot = slot;
+                    const uint32_t my_par = par;
+                    const bool is_mine = (owner == eg);
+                    if (++owner == GA) owner = 0;
+                    if (++slot == B) { slot = 0; owner = 0; par ^= 1; }
+                    ++g;
+                    if (is_mine) {
+                        const uint32_t mine = smem_u32(sm.epi) + static_cast<uint32_t>(my_slot) * kABytes + static_cast<uint32_t>(row) * 128;
+                        mbar_wait(&sm.res_full[my_slot], my_par);           // the buffer is free (plain arrival of the DMA warp)
+                        mbar_wait(&sm.b_full[it & 1], (it >> 1) & 1);       // d2_full
+                        tc_fence_after();
+                        const uint32_t t2 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + 256u + static_cast<uint32_t>((it & 1) * p.chain_n);
+                        const uint32_t ss2 = ss_s0 + static_cast<uint32_t>(p.n_pad) * 4;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            uint32_t v[32];
+                            tmem_ld32(t2 + h * 32, v);
+                            tmem_ld_wait();
+                            if (h == 1) {  // accumulator columns read: the tile after next may overwrite them
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(&sm.b_empty[it & 1]);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int piece = h * 4 + j;
+                                const uint32_t sca = ss2 + static_cast<uint32_t>(piece * 8) * 4;
+                                const float4 sc0 = lds_f4(sca), sc1 = lds_f4(sca + 16);
+                                const float4 sh0 = lds_f4(sca + ss_shift), sh1 = lds_f4(sca + ss_shift + 16);
+                                float f[8];
+                                f[0] = fmaf(__uint_as_float(v[j * 8 + 0]), sc0.x, sh0.x);
+                                f[1] = fmaf(__uint_as_float(v[j * 8 + 1]), sc0.y, sh0.y);
+                                f[2] = fmaf(__uint_as_float(v[j * 8 + 2]), sc0.z, sh0.z);
+                                f[3] = fmaf(__uint_as_float(v[j * 8 + 3]), sc0.w, sh0.w);
+                                f[4] = fmaf(__uint_as_float(v[j * 8 + 4]), sc1.x, sh1.x);
+                                f[5] = fmaf(__uint_as_float(v[j * 8 + 5]), sc1.y, sh1.y);
+                                f[6] = fmaf(__uint_as_float(v[j * 8 + 6]), sc1.z, sh1.z);
+                                f[7] = fmaf(__uint_as_float(v[j * 8 + 7]), sc1.w, sh1.w);
+                                if (p.chain_relu) {
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.0f);
+                                }
+                                uint4 o;
+                                o.x = pack_bf16(f[0], f[1]);
+                                o.y = pack_bf16(f[2], f[3]);
+                                o.z = pack_bf16(f[4], f[5]);
+                                o.w = pack_bf16(f[6], f[7]);
+                                sts128(mine + ((static_cast<uint32_t>(piece) ^ swz) << 4), o);
+                            }
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&sm.out_ready[my_slot]);
+                    }
+                }
             }
         }
         }  // kEpi != 2
@@ -1347,6 +1514,16 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
         (d->mode != B200_IGEMM_CONV || (d->out_c % 64) != 0 ||
          (d->flags & (B200_EPI_RELU | B200_EPI_RES_UP2 | B200_EPI_OUT_F32 | B200_EPI_SHUFFLE2 | B200_EPI_DCN_COORDS | B200_EPI_HEAD_DOT))))
         return set_error("igemm: GELU is for plain bf16 conv outputs with out_c a multiple of 64 (optionally + RES)");
+    if (d->flags & B200_EPI_CHAIN) {
+        if (d->mode != B200_IGEMM_CONV || d->ksize != 1 || d->stride != 1 || d->out_c != 256 || d->n_pad != 256 || d->chain_n != 64 ||
+            !(d->flags & B200_EPI_RES) || !d->chain_w || !d->chain_scale || !d->chain_shift || !d->chain_y || (d->chain_ld % 8) ||
+            d->chain_ld < d->chain_n || d->in_c > 256 ||
+            (d->flags & (B200_EPI_RES_UP2 | B200_EPI_OUT_F32 | B200_EPI_SHUFFLE2 | B200_EPI_DCN_COORDS | B200_EPI_HEAD_DOT | B200_EPI_GELU)))
+            return set_error("igemm: CHAIN is for a 1x1 stride-1 conv with out_c == n_pad == 256, in_c <= 256, a residual and chain_n == 64");
+        if ((reinterpret_cast<uintptr_t>(d->chain_w) | reinterpret_cast<uintptr_t>(d->chain_y) | reinterpret_cast<uintptr_t>(d->chain_scale) |
+             reinterpret_cast<uintptr_t>(d->chain_shift)) & 15)
+            return set_error("igemm: chain pointers must be 16-byte aligned");
+    }
     if ((d->flags & B200_EPI_DCN_COORDS) && (d->out_c != 32 || d->ksize != 3 || d->mode != B200_IGEMM_CONV))
         return set_error("igemm: DCN_COORDS is for the 3x3 offset conv with out_c == 32");
     int block_n = d->block_n;
@@ -1391,6 +1568,14 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     p.block_n = block_n;
     p.n_pad = d->n_pad;
     p.ss_half = (d->flags & B200_EPI_HEAD_DOT) ? 2048 : (d->n_pad > 256 ? d->n_pad : 256);  // HEAD_DOT: 16 KB of UMMA constants
+    if (d->flags & B200_EPI_CHAIN) {
+        p.ss_half = 512;  // the chained GEMM's scale / shift follow the layer's own 256
+        p.chain_n = d->chain_n;
+        p.chain_bytes = (d->n_pad / 64) * d->chain_n * 128;
+        p.chain_relu = d->chain_relu;
+        p.chain_scale = d->chain_scale;
+        p.chain_shift = d->chain_shift;
+    }
     p.nacc = block_n > 256 ? 1 : 2;
     // 3x3 stride-1 convs share one (tile_h+2)-row activation box between the taps ky = 0..2 of a kernel column
     // ("share mode"): tall tiles (8 rows x 16 pixels) make that 2.4x less L2->SM traffic and a third of the barrier
@@ -1482,15 +1667,19 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     int pair_min_kb = 16;
     if (const char* e = getenv("B200_PAIR_MIN_KB")) pair_min_kb = atoi(e);
     bool pair = (d->mode == B200_IGEMM_CONV && !fat && !p.b_resident && p.epi_tma && block_n >= 128 && px_tiles >= 2 &&
-                 !(d->flags & (B200_EPI_GELU | B200_EPI_HEAD_DOT)) && p.k_blocks >= pair_min_kb);
+                 !(d->flags & (B200_EPI_GELU | B200_EPI_HEAD_DOT | B200_EPI_CHAIN)) && p.k_blocks >= pair_min_kb);
     if (const char* e = getenv("B200_PAIR")) pair = pair && atoi(e) != 0;
     op->pair = pair ? 1 : 0;
     p.b_rows = pair ? block_n / 2 : block_n;
     p.num_units = pair ? ((px_tiles + 1) / 2) * p.num_n_blocks : p.num_tiles;
     if (pair) b_bytes = p.b_rows * 128;
     p.ss_shared = 1;
+    if ((d->flags & B200_EPI_CHAIN) && (!p.b_resident || !p.res_tma)) {
+        delete op;
+        return set_error("igemm: CHAIN needs resident weights and the TMA residual path");
+    }
     const int fixed = 1024 /*alignment*/ + 1024 /*barriers*/ + 8 * p.ss_half /*scale+shift*/ +
-                      (p.b_resident ? p.k_blocks * b_bytes : 0);
+                      (p.b_resident ? p.k_blocks * b_bytes : 0) + p.chain_bytes;
     // The DCN gather lives on L1 hits (K ordered chunk-major), so it keeps its carve-out <= 132 KB and leaves the
     // rest of the 256 KB to L1; everything else may use the full 227 KB opt-in.
     int cap = (d->mode == B200_IGEMM_DCN) ? (block_n > 256 ? 227 : 131) * 1024 : kMaxSmem;
@@ -1678,6 +1867,14 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
                                p.tile_h, "output");
         }
     }
+    if (!err && (d->flags & B200_EPI_CHAIN)) {
+        err |= encode_nhwc(&op->tm.out[1], d->chain_y, d->chain_n, p.out_w, p.out_h, d->batch, d->chain_ld, 1, 1, p.out_w,
+                           (uint64_t)p.out_h * p.out_w, p.tile_w, p.tile_h, "chained output");
+        const uint64_t dims[2] = {(uint64_t)d->n_pad, (uint64_t)d->chain_n};
+        const uint64_t str[1] = {(uint64_t)d->n_pad * 2};
+        const uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)d->chain_n};
+        if (!err) err |= encode_map(&op->tm.b2, d->chain_w, 2, dims, str, box, "chained weights");
+    }
     if (!err && p.res_tma) {
         if (d->flags & B200_EPI_RES_UP2)
             err |= encode_nhwc(&op->tm.res, d->residual, d->out_c, p.out_w / 2, p.out_h / 2, d->batch, d->res_ld, 1, 1,
@@ -1707,6 +1904,8 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
         e = cudaFuncSetAttribute(igemm_kernel<0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(igemm_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(igemm_kernel<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(igemm_kernel<0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e == cudaSuccess)
@@ -1752,6 +1951,8 @@ extern "C" int b200_igemm_launch(const b200_igemm* op, void* stream) {
         e = cudaLaunchKernelEx(&cfg, igemm_kernel<0, 1, true>, op->tm, op->p, NoConsts{});
     else if (op->pair)
         e = cudaLaunchKernelEx(&cfg, igemm_kernel<0, 0, true>, op->tm, op->p, NoConsts{});
+    else if (op->p.flags & B200_EPI_CHAIN)
+        e = cudaLaunchKernelEx(&cfg, igemm_kernel<0, 4>, op->tm, op->p, NoConsts{});
     else if (op->gather)
         e = cudaLaunchKernelEx(&cfg, igemm_kernel<1>, op->tm, op->p, NoConsts{});
     else if ((op->p.flags & B200_EPI_GELU) && op->p.a_kb > 1)

@@ -111,11 +111,11 @@ class Plan:
         P = W.P
 
         def igemm(name, mode, x, key, y, *, in_h, in_w, in_c, out_c, ksize, stride, flags=0, residual=None, res_ld=0,
-                  offsets=None, shuf_c=0, out_ld=None, x_ld=0):
+                  offsets=None, shuf_c=0, out_ld=None, x_ld=0, chain=None):
             w, s, t = P[key]
             op = ops.Igemm(mode, x, w, s, t, y, batch=b, in_h=in_h, in_w=in_w, in_c=in_c, out_c=out_c, ksize=ksize,
                            stride=stride, flags=flags, residual=residual, res_ld=res_ld, offsets=offsets, shuf_c=shuf_c,
-                           out_ld=out_ld, x_ld=x_ld, name=name)
+                           out_ld=out_ld, x_ld=x_ld, name=name, chain=chain)
             self.steps.append(op)
             self.names.append(name)
             self.step_flops[name] = op.flops
@@ -127,6 +127,8 @@ class Plan:
             in_px = b * in_h * in_w if ksize > 1 or stride == 1 else b * oh * ow  # a strided 1x1 reads only its pixels
             res_bytes = (2 * b * oh * ow * out_c if flags & ops.EPI_RES else 0) + (2 * b * oh * ow * out_c // 4 if flags & ops.EPI_RES_UP2 else 0)
             self.step_bytes[name] = float(in_px * in_c * 2 + out_bytes + res_bytes + w.numel() * 2)
+            if chain is not None:
+                self.step_bytes[name] += float(chain[3].numel() * 2 + chain[0].numel() * 2)
             self.flops += op.flops
             self.n_igemm += 1
             return op
@@ -147,15 +149,21 @@ class Plan:
         self.steps.append(lambda s=stem, o=x: ops.maxpool3x3s2(s, o, b, H // 2, Wd // 2, 64)); self.names.append("maxpool")
         cin = 64
         feats = []
+        import os
+        use_chain = not os.environ.get("B200_NO_CHAIN")
+        chained_t1 = None  # conv1 output of this block, already produced by the previous block's conv3 launch
         for li, nblocks, width in LAYER_CFG:
             cout = width * 4
             for bi in range(nblocks):
                 p = f"layer{li}.{bi}"
                 stride = 2 if (bi == 0 and li > 1) else 1
                 ho, wo = h // stride, w // stride
-                t1 = bf(b, h, w, width)
-                igemm(p + ".conv1", ops.IGEMM_CONV, x, p + ".conv1", t1, in_h=h, in_w=w, in_c=cin, out_c=width, ksize=1,
-                      stride=1, flags=ops.EPI_RELU)
+                if chained_t1 is not None:
+                    t1, chained_t1 = chained_t1, None
+                else:
+                    t1 = bf(b, h, w, width)
+                    igemm(p + ".conv1", ops.IGEMM_CONV, x, p + ".conv1", t1, in_h=h, in_w=w, in_c=cin, out_c=width, ksize=1,
+                          stride=1, flags=ops.EPI_RELU)
                 t2 = bf(b, ho, wo, width)
                 if W.dcn and li >= 2:
                     # offset_mask_conv with the sampling-record epilogue: [pixel][9 taps][16-byte record]
@@ -174,8 +182,15 @@ class Plan:
                 else:
                     idn = x
                 y = bf(b, ho, wo, cout)
+                chain = None
+                if use_chain and cout == 256 and bi + 1 < nblocks:
+                    # layer1: the next block's conv1 (256 -> 64) + bn1 + ReLU rides on this launch's staged output chunks
+                    # (B200_EPI_CHAIN): the 256-channel block output is written once and not read back by a conv1 launch
+                    w2, s2, t2_ = P[f"layer{li}.{bi + 1}.conv1"]
+                    chained_t1 = bf(b, ho, wo, width)
+                    chain = (w2, s2, t2_, chained_t1, True)
                 igemm(p + ".conv3", ops.IGEMM_CONV, t2, p + ".conv3", y, in_h=ho, in_w=wo, in_c=width, out_c=cout,
-                      ksize=1, stride=1, flags=ops.EPI_RES | ops.EPI_RELU, residual=idn, res_ld=cout)
+                      ksize=1, stride=1, flags=ops.EPI_RES | ops.EPI_RELU, residual=idn, res_ld=cout, chain=chain)
                 if keep_taps and W.dcn and li >= 2:
                     self.taps[f"backbone.model.{p}.bn2"] = (t2, width)
                 x, cin, h, w = y, cout, ho, wo

@@ -11,13 +11,13 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (EPI_DCN_COORDS, EPI_GELU, EPI_HEAD_DOT, EPI_OUT_F32, EPI_RELU, EPI_RES, EPI_RES_UP2, EPI_SHUFFLE2, IGEMM_CONV,
+from ._lib import (EPI_CHAIN, EPI_DCN_COORDS, EPI_GELU, EPI_HEAD_DOT, EPI_OUT_F32, EPI_RELU, EPI_RES, EPI_RES_UP2, EPI_SHUFFLE2, IGEMM_CONV,
                    IGEMM_DCN, IGEMM_DCN_TMEM, IGEMM_STEM)
 
 __all__ = [
     "Igemm", "pack_conv_weight", "pack_dcn_weight", "dcn_tmem_supported", "IGEMM_DCN_TMEM", "pack_stem_weight", "pack_convT_weight", "fold_bn", "pad_vec",
     "stem_pack", "stem_pack_u8", "resize_u8_linear", "maxpool3x3s2", "asf_fwd", "asf_combine", "AsfPlan", "db_head_fwd", "postproc", "rec_prep_boxes", "rec_prep_rects", "ctc_greedy", "svtr_stem1", "layernorm", "gelu", "mhsa", "frm_select", "decimate_rows", "log_softmax_tbc", "ref_conv2d", "ref_dcn2d",
-    "EPI_RELU", "EPI_RES", "EPI_RES_UP2", "EPI_OUT_F32", "EPI_SHUFFLE2", "EPI_DCN_COORDS", "EPI_HEAD_DOT", "EPI_GELU", "db_maps", "dcn_coords", "IGEMM_CONV", "IGEMM_STEM", "IGEMM_DCN",
+    "EPI_RELU", "EPI_RES", "EPI_RES_UP2", "EPI_OUT_F32", "EPI_SHUFFLE2", "EPI_DCN_COORDS", "EPI_HEAD_DOT", "EPI_GELU", "EPI_CHAIN", "db_maps", "dcn_coords", "IGEMM_CONV", "IGEMM_STEM", "IGEMM_DCN",
 ]
 
 
@@ -128,10 +128,13 @@ class Igemm:
                  y: torch.Tensor, *, batch: int, in_h: int, in_w: int, in_c: int, out_c: int, ksize: int,
                  stride: int, flags: int = 0, residual: Optional[torch.Tensor] = None,
                  offsets: Optional[torch.Tensor] = None, out_ld: Optional[int] = None, res_ld: int = 0,
-                 shuf_c: int = 0, block_n: int = 0, x_ld: int = 0, stride_w: int = 0, name: str = ""):
+                 shuf_c: int = 0, block_n: int = 0, x_ld: int = 0, stride_w: int = 0, name: str = "",
+                 chain: Optional[tuple] = None):
+        """`chain` = (w2, scale2, shift2, y2, relu2): EPI_CHAIN, the next block's 1x1 conv folded into this launch."""
         lib = _lib.load()
         self.name = name
         self._keep = (x, w, scale, shift, y, residual, offsets)
+        self._chain = chain
         n_pad = w.shape[0]
         assert scale.numel() == n_pad and shift.numel() == n_pad, "scale/shift must be padded to n_pad"
         assert w.dtype == torch.bfloat16 and w.is_contiguous()
@@ -143,11 +146,19 @@ class Igemm:
             stride_w=stride_w,
             x=_lib.ptr(x), w=_lib.ptr(w), scale=_lib.ptr(scale), shift=_lib.ptr(shift),
             residual=_lib.ptr(residual), y=_lib.ptr(y), offsets=_lib.ptr(offsets))
+        if chain is not None:
+            w2, s2, t2, y2, relu2 = chain
+            assert w2.dtype == torch.bfloat16 and w2.is_contiguous() and w2.shape[1] == out_c
+            d.flags |= EPI_CHAIN
+            d.chain_w, d.chain_scale, d.chain_shift, d.chain_y = _lib.ptr(w2), _lib.ptr(s2), _lib.ptr(t2), _lib.ptr(y2)
+            d.chain_n, d.chain_ld, d.chain_relu = w2.shape[0], y2.shape[-1], int(bool(relu2))
         h = C.c_void_p()
         _lib.check(lib.b200_igemm_create(C.byref(d), C.byref(h)), f"igemm_create({name})")
         self._h = h
         self._lib = lib
         self.flops = 2.0 * batch * (in_h // stride) * (in_w // (stride_w or stride)) * out_c * w.shape[1]
+        if chain is not None:
+            self.flops += 2.0 * batch * (in_h // stride) * (in_w // (stride_w or stride)) * chain[0].shape[0] * chain[0].shape[1]
 
     def info(self) -> dict:
         vals = [C.c_int32() for _ in range(7)]
