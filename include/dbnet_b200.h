@@ -69,7 +69,7 @@ enum {
                                   y = the normal output (bf16, 256 channels, with RES + RELU as flagged); every staged 64-channel
                                   chunk of y is also the A operand of y2[pixel][chain_n] += chunk x chain_w^T, and after the tile's
                                   last chunk y2 = relu?(y2 * chain_scale + chain_shift) is stored as bf16: the block output is never
-                                  re-read.  CONV mode, 1x1, out_c == n_pad == 256, chain_n == 64, residual required.          */
+                                  re-read.  CONV mode, 1x1, out_c == n_pad == 256, chain_n 64 or 128, residual required.       */
     B200_EPI_DCN_COORDS = 32  /* offset_mask_conv only (out_c = 32): instead of the raw 27 channels, store
                                  the b200_dcn_coord records of the 9 taps, y = [pixel][9] records, so
                                  the DCN producers do no coordinate arithmetic (dcn.py:44-46 fused)    */
@@ -117,7 +117,7 @@ typedef struct b200_igemm_desc {
     const float* chain_scale; /* [chain_n] */
     const float* chain_shift; /* [chain_n] */
     void*        chain_y;     /* second output, NHWC bf16, chain_ld elements per pixel               */
-    int32_t      chain_n;     /* 64                                                                  */
+    int32_t      chain_n;     /* 64 or 128                                                           */
     int32_t      chain_ld;
     int32_t      chain_relu;  /* ReLU on the second output                                           */
     int32_t      chain_reserved;

@@ -523,7 +523,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
             if constexpr (kEpi == 4) {
                 for (int a = 0; a < 2; ++a) {
                     mbar_init(&sm.b_full[a], 1);   // d2_full: the chained GEMM's accumulator of tile parity a is complete
-                    mbar_init(&sm.b_empty[a], 4);  // d2_empty: the four warps of the group that drained it
+                    mbar_init(&sm.b_empty[a], 4 * (p.chain_n >> 6));  // d2_empty: four warps per 64-column tail chunk
                 }
             }
             mbar_init(sm.b_ready, 1);
@@ -837,7 +837,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
             // Chain: a tile is 4 main chunks (residual prefetched, stored to y, multiplied by warp 3) + 1 tail chunk (the
             // chained GEMM's 64 columns: no residual, stored to the second output).  A main chunk's buffer is recycled when
             // BOTH its store has read it and its UMMAs have completed (chain_done = slot_free barrier).
-            const int B = p.epi_bufs, NC = p.n_pad >> 6;
+            const int B = p.epi_bufs, NC = p.n_pad >> 6, NT = p.chain_n >> 6;  // main / tail chunks per tile
             int ld_u = u_first, ld_chunk = 0;
             auto issue_load = [&](int slot) {
                 if (ld_u >= num_units) return;
@@ -851,7 +851,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
                     mbar_arrive(&sm.res_full[slot]);  // tail chunk: nothing to load, the buffer is simply free
                 }
                 __syncwarp();
-                if (++ld_chunk == NC + 1) { ld_chunk = 0; ld_u += u_stride; }
+                if (++ld_chunk == NC + NT) { ld_chunk = 0; ld_u += u_stride; }
             };
             for (int i = 0; i < B; ++i) issue_load(i);
             int g = 0, slot = 0, rslot = 0;
@@ -859,11 +859,11 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
             bool prev_main = false;
             for (int u = u_first; u < num_units; u += u_stride) {
                 const TileCoord t = decode_tile(p, unit_tile(u));
-                for (int c = 0; c <= NC; ++c, ++g) {
+                for (int c = 0; c < NC + NT; ++c, ++g) {
                     mbar_wait(&sm.out_ready[slot], par);
                     if (elect_one()) {
                         if (c < NC) tma_store_4d(&tm.out[0], sm.epi + slot * kABytes, c * 64, t.x0, t.y0, t.n);
-                        else tma_store_4d(&tm.out[1], sm.epi + slot * kABytes, 0, t.x0, t.y0, t.n);
+                        else tma_store_4d(&tm.out[1], sm.epi + slot * kABytes, (c - NC) * 64, t.x0, t.y0, t.n);
                         bulk_commit();
                         if (g >= 1) bulk_wait_read1();
                     }
@@ -958,7 +958,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
         }
         if constexpr (kEpi == 4) {
             // chain: y2[128 x chain_n] += staged chunk [128 x 64] x W2[chain_n x 64]^T for the tile's main chunks, in order
-            const int B = p.epi_bufs, NC = p.n_pad >> 6;
+            const int B = p.epi_bufs, NC = p.n_pad >> 6, NT = p.chain_n >> 6;
             const uint32_t idesc2 = umma_idesc_bf16(static_cast<uint32_t>(p.chain_n));
             const uint32_t a2 = smem_u32(sm.epi), w2 = smem_u32(sm.epi) - static_cast<uint32_t>(p.chain_bytes);
             mbar_wait(sm.b_ready, 0);
@@ -982,7 +982,8 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
                     __syncwarp();
                     if (++slot == B) { slot = 0; par ^= 1; }
                 }
-                if (++slot == B) { slot = 0; par ^= 1; }  // the tile's tail chunk is not multiplied
+                for (int j = 0; j < NT; ++j)  // the tile's tail chunks are not multiplied
+                    if (++slot == B) { slot = 0; par ^= 1; }
             }
         }
         // weight producer of the share mode:
@@ -1174,8 +1175,9 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
                 else mbar_arrive(&sm.tempty[as]);
             }
             if constexpr (kEpi == 4) {
-                // tail chunk of the tile: the chained GEMM's chain_n (= 64) columns, BN + ReLU, bf16, staged for the DMA warp
-                if (eg < GA) {
+                // tail chunks of the tile: the chained GEMM's chain_n columns (64 each), BN + ReLU, bf16, staged for the DMA warp
+                if (eg < GA)
+                for (int tj = 0; tj < (p.chain_n >> 6); ++tj) {
                     const int my_slot = slot;
                     const uint32_t my_par = par;
                     const bool is_mine = (owner == eg);
@@ -1187,8 +1189,9 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
                         mbar_wait(&sm.res_full[my_slot], my_par);           // the buffer is free (plain arrival of the DMA warp)
                         mbar_wait(&sm.b_full[it & 1], (it >> 1) & 1);       // d2_full
                         tc_fence_after();
-                        const uint32_t t2 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + 256u + static_cast<uint32_t>((it & 1) * p.chain_n);
-                        const uint32_t ss2 = ss_s0 + static_cast<uint32_t>(p.n_pad) * 4;
+                        const uint32_t t2 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + 256u +
+                                            static_cast<uint32_t>((it & 1) * p.chain_n + tj * 64);
+                        const uint32_t ss2 = ss_s0 + static_cast<uint32_t>(p.n_pad + tj * 64) * 4;
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             uint32_t v[32];
@@ -1515,11 +1518,11 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
          (d->flags & (B200_EPI_RELU | B200_EPI_RES_UP2 | B200_EPI_OUT_F32 | B200_EPI_SHUFFLE2 | B200_EPI_DCN_COORDS | B200_EPI_HEAD_DOT))))
         return set_error("igemm: GELU is for plain bf16 conv outputs with out_c a multiple of 64 (optionally + RES)");
     if (d->flags & B200_EPI_CHAIN) {
-        if (d->mode != B200_IGEMM_CONV || d->ksize != 1 || d->stride != 1 || d->out_c != 256 || d->n_pad != 256 || d->chain_n != 64 ||
+        if (d->mode != B200_IGEMM_CONV || d->ksize != 1 || d->stride != 1 || d->out_c != 256 || d->n_pad != 256 || (d->chain_n != 64 && d->chain_n != 128) ||
             !(d->flags & B200_EPI_RES) || !d->chain_w || !d->chain_scale || !d->chain_shift || !d->chain_y || (d->chain_ld % 8) ||
             d->chain_ld < d->chain_n || d->in_c > 256 ||
             (d->flags & (B200_EPI_RES_UP2 | B200_EPI_OUT_F32 | B200_EPI_SHUFFLE2 | B200_EPI_DCN_COORDS | B200_EPI_HEAD_DOT | B200_EPI_GELU)))
-            return set_error("igemm: CHAIN is for a 1x1 stride-1 conv with out_c == n_pad == 256, in_c <= 256, a residual and chain_n == 64");
+            return set_error("igemm: CHAIN is for a 1x1 stride-1 conv with out_c == n_pad == 256, in_c <= 256, a residual and chain_n 64 or 128");
         if ((reinterpret_cast<uintptr_t>(d->chain_w) | reinterpret_cast<uintptr_t>(d->chain_y) | reinterpret_cast<uintptr_t>(d->chain_scale) |
              reinterpret_cast<uintptr_t>(d->chain_shift)) & 15)
             return set_error("igemm: chain pointers must be 16-byte aligned");

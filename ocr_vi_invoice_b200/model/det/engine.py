@@ -183,11 +183,12 @@ class Plan:
                     idn = x
                 y = bf(b, ho, wo, cout)
                 chain = None
-                if use_chain and cout == 256 and bi + 1 < nblocks:
-                    # layer1: the next block's conv1 (256 -> 64) + bn1 + ReLU rides on this launch's staged output chunks
-                    # (B200_EPI_CHAIN): the 256-channel block output is written once and not read back by a conv1 launch
-                    w2, s2, t2_ = P[f"layer{li}.{bi + 1}.conv1"]
-                    chained_t1 = bf(b, ho, wo, width)
+                if use_chain and cout == 256:
+                    # layer1: the next block's conv1 (256 -> 64, or layer2.0's 256 -> 128) + bn1 + ReLU rides on this launch's
+                    # staged output chunks (B200_EPI_CHAIN): the 256-channel block output is not read back by a conv1 launch
+                    nxt = f"layer{li}.{bi + 1}.conv1" if bi + 1 < nblocks else f"layer{li + 1}.0.conv1"
+                    w2, s2, t2_ = P[nxt]
+                    chained_t1 = bf(b, ho, wo, w2.shape[0])
                     chain = (w2, s2, t2_, chained_t1, True)
                 igemm(p + ".conv3", ops.IGEMM_CONV, t2, p + ".conv3", y, in_h=ho, in_w=wo, in_c=width, out_c=cout,
                       ksize=1, stride=1, flags=ops.EPI_RES | ops.EPI_RELU, residual=idn, res_ld=cout, chain=chain)

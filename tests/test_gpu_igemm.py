@@ -178,8 +178,9 @@ def test_convT_igemm(shape):
     close(nchw(y), ref)
 
 
+@pytest.mark.parametrize("n2", [64, 128])
 @pytest.mark.parametrize("shape", [(1, 16, 24), (2, 40, 56), (16, 128, 128)], ids=lambda c: "b%d_%dx%d" % c)
-def test_chained_second_gemm(shape):
+def test_chained_second_gemm(shape, n2):
     """B200_EPI_CHAIN: conv3 (64 -> 256) + residual + ReLU of one Bottleneck with the next block's conv1 (256 -> 64) + BN + ReLU
     chained onto its staged output chunks -- y as usual, y2 == the 1x1 conv applied to the bf16 y the launch stored."""
     from ocr_vi_invoice_b200 import ops
@@ -190,14 +191,14 @@ def test_chained_second_gemm(shape):
     x = torch.randn(b, 64, h, w, device=dev, generator=g)
     r = torch.randn(b, 256, h, w, device=dev, generator=g)
     wt = torch.randn(256, 64, 1, 1, device=dev, generator=g) / 8
-    w2 = torch.randn(64, 256, 1, 1, device=dev, generator=g) / 16
+    w2 = torch.randn(n2, 256, 1, 1, device=dev, generator=g) / 16
     sc, sh = torch.rand(256, device=dev, generator=g) + 0.5, torch.randn(256, device=dev, generator=g) * 0.1
-    s2, t2 = torch.rand(64, device=dev, generator=g) + 0.5, torch.randn(64, device=dev, generator=g) * 0.1
+    s2, t2 = torch.rand(n2, device=dev, generator=g) + 0.5, torch.randn(n2, device=dev, generator=g) * 0.1
     y = torch.full((b, h, w, 256), float("nan"), device=dev, dtype=torch.bfloat16)
-    y2 = torch.full((b, h, w, 64), float("nan"), device=dev, dtype=torch.bfloat16)
+    y2 = torch.full((b, h, w, n2), float("nan"), device=dev, dtype=torch.bfloat16)
     op = ops.Igemm(ops.IGEMM_CONV, nhwc(x), ops.pack_conv_weight(wt, 256), sc, sh, y, batch=b, in_h=h, in_w=w, in_c=64, out_c=256,
                    ksize=1, stride=1, flags=ops.EPI_RELU | ops.EPI_RES, residual=nhwc(r), res_ld=256,
-                   chain=(ops.pack_conv_weight(w2, 64), s2, t2, y2, True), name="chain")
+                   chain=(ops.pack_conv_weight(w2, n2), s2, t2, y2, True), name="chain")
     op()
     op()
     torch.cuda.synchronize()

@@ -29,6 +29,21 @@ def conv(name, b, h, w, ci, co, k, s, flags=0, res=False, pair_ok=True):
     return name, op, y
 
 
+def chained(name, b, hw, n2):
+    dev = "cuda"
+    x = torch.randn(b, hw, hw, 64, device=dev).to(torch.bfloat16)
+    wt = (torch.randn(256, 64, device=dev) / 8).to(torch.bfloat16)
+    w2 = (torch.randn(n2, 256, device=dev) / 16).to(torch.bfloat16)
+    sc, sh = torch.rand(256, device=dev) + 0.5, torch.randn(256, device=dev) * 0.1
+    s2, t2 = torch.rand(n2, device=dev) + 0.5, torch.randn(n2, device=dev) * 0.1
+    r = torch.randn(b, hw, hw, 256, device=dev).to(torch.bfloat16)
+    y = torch.empty(b, hw, hw, 256, device=dev, dtype=torch.bfloat16)
+    y2 = torch.empty(b, hw, hw, n2, device=dev, dtype=torch.bfloat16)
+    op = ops.Igemm(ops.IGEMM_CONV, x, wt, sc, sh, y, batch=b, in_h=hw, in_w=hw, in_c=64, out_c=256, ksize=1, stride=1,
+                   flags=ops.EPI_RELU | ops.EPI_RES, residual=r, res_ld=256, chain=(w2, s2, t2, y2, True), name=name)
+    return name, op, y2
+
+
 def dcn(name, b, hw, c, s):
     dev = "cuda"
     x = torch.randn(b, hw, hw, c, device=dev).to(torch.bfloat16)
@@ -105,7 +120,7 @@ def main():
     def maybe(fn, *a_):
         try:
             return [fn(*a_)]
-        except AttributeError:  # an older build of the package without this operator
+        except (AttributeError, TypeError):  # an older build of the package without this operator
             return []
     items = [
         conv("layer1.conv3 64->256 res", b, 256, 256, 64, 256, 1, 1, ops.EPI_RELU, res=True),
@@ -122,6 +137,8 @@ def main():
         head_tail("head tail", b, 256),
         *maybe(asf, "asf tensor-core", b, 256),
         conv("layer2.conv3 128->512 res", b, 128, 128, 128, 512, 1, 1, ops.EPI_RELU, res=True),
+        *maybe(chained, "chained conv3 -> conv1 (64)", b, 256, 64),
+        *maybe(chained, "chained conv3 -> conv1 (128)", b, 256, 128),
         conv("layer2.conv1 512->128", b, 128, 128, 512, 128, 1, 1, ops.EPI_RELU),
     ]
     torch.cuda.synchronize()
