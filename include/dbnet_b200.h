@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define B200_ABI_VERSION 1
+#define B200_ABI_VERSION 2
 
 /* ---- status ------------------------------------------------------------------------------- */
 int         b200_abi_version(void);

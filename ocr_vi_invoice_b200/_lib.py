@@ -116,7 +116,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.b200_abi_version() != 1:
+    if lib.b200_abi_version() != 2:
         raise B200Error("libdbnet_b200.so ABI version mismatch")
     _lib = lib
     return lib
