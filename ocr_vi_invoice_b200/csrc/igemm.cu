@@ -638,7 +638,13 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
                 for (int c0 = 0; c0 < p.in_c; c0 += kBlockK) {
                     for (int kx = 0; kx < 3; ++kx) {
                         B200_TIMED_WAIT(0, mbar_wait(&sm.a_empty[s], ph ^ 1));
-                        if (elect_one()) {
+                        if constexpr (kPair) {  // both CTAs' boxes land on rank 0's barrier
+                            if (elect_one()) {
+                                if (cta_rank == 0) mbar_arrive_expect_tx(&sm.a_full[s], 2 * tx_bytes);
+                                tma_load_4d_2sm(sm.a + s * p.a_bytes, &tm.a[0], mapa_u32(smem_u32(&sm.a_full[s]), 0), c0,
+                                                t.x0 + kx - 1, t.y0 - 1, t.n);
+                            }
+                        } else if (elect_one()) {
                             mbar_arrive_expect_tx(&sm.a_full[s], tx_bytes);
                             if (!(p.dbg & 2))
                                 tma_load_4d(sm.a + s * p.a_bytes, &tm.a[0], &sm.a_full[s], c0, t.x0 + kx - 1, t.y0 - 1, t.n);
@@ -728,6 +734,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
             // weight k-blocks between the sub-tiles of a stage: ring stage = 3 consecutive k-blocks; resident 3x3 weights are
             // (chunk, ky, kx) so ky steps by 3; the stem's four window rows are consecutive
             const uint32_t wstep = (b_ring || akb == 4) ? be : 3 * be;
+            const uint32_t idesc2 = umma_idesc_bf16_2sm(static_cast<uint32_t>(p.block_n)); (void)idesc2;
             int bs = 0;
             uint32_t bph = 0;
             for (int u = u_first; u < num_units; u += u_stride, ++it) {
@@ -746,7 +753,18 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
 #ifdef B200_PROF
                     const long long ti0 = clock64();
 #endif
-                    if (elect_one()) {
+                    if constexpr (kPair) {
+                        if (elect_one()) {  // 256 pixels x block_n per instruction: both CTAs' boxes and weight halves
+#pragma unroll
+                            for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+                                for (int k = 0; k < kBlockK / 16; ++k)
+                                    umma_bf16_2sm(d_tmem, da + ky * sh + 2 * k, db + ky * wstep + 2 * k, idesc2, (ai | ky | k) ? 1u : 0u);
+                            }
+                            umma_commit_2sm(&sm.a_empty[s]);
+                            umma_commit_2sm(&sm.b_empty[bs]);
+                        }
+                    } else if (elect_one()) {
                         if (!(p.dbg & 1)) {
 #pragma unroll
                             for (int ky = 0; ky < 3; ++ky) {
@@ -771,7 +789,10 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
                     if (b_ring && ++bs == bst) { bs = 0; bph ^= 1; }
                     if (++kx == 3) { kx = 0; wbase += 7; } else { ++wbase; }
                 }
-                if (elect_one()) umma_commit(&sm.tfull[acc]);
+                if (elect_one()) {
+                    if constexpr (kPair) umma_commit_2sm(&sm.tfull[acc]);
+                    else umma_commit(&sm.tfull[acc]);
+                }
                 __syncwarp();
             }
         } else {
@@ -988,7 +1009,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
         }
         // weight producer of the share mode:
         // One stage = the three weight k-blocks (ky = 0..2) of one (chunk, kx); the matrix itself stays (chunk, ky, kx).
-        if constexpr (kShare) if (!p.b_resident) {
+        if constexpr (kShare) if (!p.b_resident && warp == 3) {  // (rank 1 of a pair: its idle warp 1 lands in this branch too)
             int s = 0;
             uint32_t ph = 0;
             const int bst = p.b_stages;
@@ -998,7 +1019,16 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
                 for (int kb9 = 0; kb9 < p.k_blocks; kb9 += 9) {
                     for (int kx = 0; kx < 3; ++kx) {
                         B200_TIMED_WAIT(1, mbar_wait(&sm.b_empty[s], ph ^ 1));
-                        if (elect_one()) {
+                        if constexpr (kPair) {  // each CTA stages its half of the weight rows, rank 0's barrier counts both
+                            if (elect_one()) {
+                                if (cta_rank == 0) mbar_arrive_expect_tx(&sm.b_full[s], 2 * 3 * b_bytes);
+                                const uint32_t bar0 = mapa_u32(smem_u32(&sm.b_full[s]), 0);
+#pragma unroll
+                                for (int ky = 0; ky < 3; ++ky)
+                                    tma_load_2d_2sm(sm.b + (s * 3 + ky) * b_bytes, &tm.b, bar0, (kb9 + ky * 3 + kx) * kBlockK,
+                                                    n0 + static_cast<int>(cta_rank) * p.b_rows);
+                            }
+                        } else if (elect_one()) {
                             mbar_arrive_expect_tx(&sm.b_full[s], 3 * b_bytes);
 #pragma unroll
                             for (int ky = 0; ky < 3; ++ky)
@@ -1669,7 +1699,10 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     // 0.275), and K = 1024..2048 1x1 convs do not move.  Hence: at least 16 k-blocks per tile.
     int pair_min_kb = 16;
     if (const char* e = getenv("B200_PAIR_MIN_KB")) pair_min_kb = atoi(e);
-    bool pair = (d->mode == B200_IGEMM_CONV && !fat && !p.b_resident && p.epi_tma && block_n >= 128 && px_tiles >= 2 &&
+    // Share-mode layers (3x3 stride 1, N = 128) pair as well: the DB head's 256 -> 128 conv pulled 816 KB per tile through the
+    // L2 fabric (weights 576 KB of it) at the ~13 TB/s the fabric gives when every SM pulls; the pair halves the weight part.
+    bool pair = (d->mode == B200_IGEMM_CONV && (!fat || (share && !(d->flags & B200_EPI_RES_UP2) && !getenv("B200_NO_PAIR_SHARE"))) &&
+                 !p.b_resident && p.epi_tma && block_n >= 128 && px_tiles >= 2 &&
                  !(d->flags & (B200_EPI_GELU | B200_EPI_HEAD_DOT | B200_EPI_CHAIN)) && p.k_blocks >= pair_min_kb);
     if (const char* e = getenv("B200_PAIR")) pair = pair && atoi(e) != 0;
     op->pair = pair ? 1 : 0;
@@ -1913,6 +1946,8 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
         e = cudaFuncSetAttribute(igemm_kernel<0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(igemm_kernel<0, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(igemm_kernel<2, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) {
         delete op;
         return set_error("igemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -1950,7 +1985,9 @@ extern "C" int b200_igemm_launch(const b200_igemm* op, void* stream) {
     cfg.attrs = attr;
     cfg.numAttrs = nattr;
     cudaError_t e;
-    if (op->pair && (op->p.flags & B200_EPI_RES_UP2))
+    if (op->pair && op->p.a_kb > 1)
+        e = cudaLaunchKernelEx(&cfg, igemm_kernel<2, 0, true>, op->tm, op->p, NoConsts{});
+    else if (op->pair && (op->p.flags & B200_EPI_RES_UP2))
         e = cudaLaunchKernelEx(&cfg, igemm_kernel<0, 1, true>, op->tm, op->p, NoConsts{});
     else if (op->pair)
         e = cudaLaunchKernelEx(&cfg, igemm_kernel<0, 0, true>, op->tm, op->p, NoConsts{});

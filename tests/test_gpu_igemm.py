@@ -62,6 +62,8 @@ CONV_CASES = [
     (2, 5, 200, 256, 256, 3, 1, ""),            # ragged second tile, 4 channel chunks
     (1, 9, 256, 128, 27, 3, 1, "f32"),          # 128x1 tiles with the direct fp32 epilogue
     (1, 4, 130, 256, 128, 3, 1, "res+relu"),    # 128x1 tiles + residual
+    (2, 40, 56, 256, 128, 3, 1, "relu"),        # share mode on a CTA pair (DB head 256 -> 128), ragged right edge
+    (3, 24, 24, 128, 128, 3, 1, "res+relu"),    # the same with a residual and an odd tile count
 ]
 
 

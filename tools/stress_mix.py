@@ -129,6 +129,7 @@ def main():
         conv("layer1.down 64->256", b, 256, 256, 64, 256, 1, 1, 0),
         conv("smooth1 3x3 256->256 (pair)", b, 128, 128, 256, 256, 3, 1, ops.EPI_RELU),
         conv("layer3.conv1 1024->256 (pair)", b, 64, 64, 1024, 256, 1, 1, ops.EPI_RELU),
+        conv("head.0 3x3 256->128 (pair + share)", b, 128, 128, 256, 128, 3, 1, ops.EPI_RELU),
         *maybe(dcn, "dcn c3", b, 128, 128, 1),
         *maybe(dcn, "dcn c4", b, 64, 256, 1),
         dcn_v1("dcn v1 c5 (N=512)", b, 32, 512, 1),
