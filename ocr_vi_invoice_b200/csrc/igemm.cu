@@ -1614,7 +1614,16 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     // ("share mode"): tall tiles (8 rows x 16 pixels) make that 2.4x less L2->SM traffic and a third of the barrier
     // round trips (a hand-shake costs ~380 cycles whatever it carries, a 128 x N x 64 MMA block only 2*N).
     // Only narrow GEMMs (N <= 128) take it: at N = 256 a k-block is 512 MMA cycles and hides everything already.
-    const bool share = (d->mode == B200_IGEMM_CONV && d->ksize == 3 && d->stride == 1 && block_n <= 128 &&
+    // ... except N = 256 layers that will run on a CTA pair (K >= 16 k-blocks, see `pair` below): what bounds those is the L2 ->
+    // SM fabric (~13 TB/s when every SM pulls; 3x3 256 -> 256 at 256^2 pulled 12.5), and the shared box cuts the activation
+    // part from 9 to 3.75 tiles per chunk: 0.772 -> 0.739 ms.
+    const bool share = (d->mode == B200_IGEMM_CONV && d->ksize == 3 && d->stride == 1 &&
+                        (block_n <= 128 ||
+                         (!getenv("B200_NO_SHARE_N256") && block_n == 256 && d->in_c >= 128 && (d->out_c % 64) == 0 &&
+                          d->batch * d->in_h * d->in_w > kBlockM /* at least two pixel tiles */ && !getenv("B200_PAIR_MIN_KB") &&
+                          (!getenv("B200_PAIR") || atoi(getenv("B200_PAIR")) != 0) &&
+                          !(d->flags & (B200_EPI_GELU | B200_EPI_HEAD_DOT | B200_EPI_CHAIN | B200_EPI_RES_UP2 | B200_EPI_OUT_F32 |
+                                        B200_EPI_DCN_COORDS | B200_EPI_SHUFFLE2)))) &&
                         !getenv("B200_NO_SHARE"));
     // RES_UP2 reads a half-resolution residual box: the tile needs at least two rows
     // The stem (4x4 window over the space-to-depth buffer) works the same way: the four window rows of a tile are
@@ -1705,6 +1714,10 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
                  !p.b_resident && p.epi_tma && block_n >= 128 && px_tiles >= 2 &&
                  !(d->flags & (B200_EPI_GELU | B200_EPI_HEAD_DOT | B200_EPI_CHAIN)) && p.k_blocks >= pair_min_kb);
     if (const char* e = getenv("B200_PAIR")) pair = pair && atoi(e) != 0;
+    if (share && block_n > 128 && !pair) {
+        delete op;
+        return set_error("igemm: internal: an N = 256 share-mode plan must run on a CTA pair");
+    }
     op->pair = pair ? 1 : 0;
     p.b_rows = pair ? block_n / 2 : block_n;
     p.num_units = pair ? ((px_tiles + 1) / 2) * p.num_n_blocks : p.num_tiles;

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from ocr_vi_invoice_b200 import ops
 
-def run(name, b, h, w, ci, co, k, s, flags, res=False, shuf=0, iters=20):
+def run(name, b, h, w, ci, co, k, s, flags, res=False, shuf=0, iters=20, block_n=0):
     dev = "cuda"
     x = torch.randn(b, h, w, ci, device=dev).to(torch.bfloat16)
     n_pad = ops.choose_n_pad(co)
@@ -17,7 +17,7 @@ def run(name, b, h, w, ci, co, k, s, flags, res=False, shuf=0, iters=20):
         y = torch.empty(b, oh, ow, co, device=dev, dtype=torch.bfloat16)
     r = torch.randn(b, oh, ow, co, device=dev).to(torch.bfloat16) if res else None
     op = ops.Igemm(ops.IGEMM_CONV, x, wt, sc, sh, y, batch=b, in_h=h, in_w=w, in_c=ci, out_c=co, ksize=k, stride=s,
-                   flags=flags | (ops.EPI_RES if res else 0), residual=r, res_ld=co if res else 0, shuf_c=shuf, name=name)
+                   flags=flags | (ops.EPI_RES if res else 0), residual=r, res_ld=co if res else 0, shuf_c=shuf, block_n=block_n, name=name)
     for _ in range(3):
         op()
     torch.cuda.synchronize()
@@ -99,6 +99,14 @@ if __name__ == "__main__" and os.environ.get("EPI_SET") == "offset":
     run_offset("layer2 offset s2", 16, 256, 256, 128, 2)
     run_offset("layer3 offset s1", 16, 64, 64, 256, 1)
     run_offset("layer4 offset s1", 16, 32, 32, 512, 1)
+    sys.exit(0)
+if __name__ == "__main__" and os.environ.get("EPI_SET") == "conv3":
+    for bn in (256, 128):
+        run(f"layer2.conv3 128->512 res bn{bn}", 16, 128, 128, 128, 512, 1, 1, ops.EPI_RELU, res=True, block_n=bn)
+        run(f"layer3.conv3 256->1024 res bn{bn}", 16, 64, 64, 256, 1024, 1, 1, ops.EPI_RELU, res=True, block_n=bn)
+        run(f"layer3.conv3 no-res bn{bn}", 16, 64, 64, 256, 1024, 1, 1, ops.EPI_RELU, block_n=bn)
+        run(f"layer4.conv3 512->2048 res bn{bn}", 16, 32, 32, 512, 2048, 1, 1, ops.EPI_RELU, res=True, block_n=bn)
+        run(f"layer4.conv3 no-res bn{bn}", 16, 32, 32, 512, 2048, 1, 1, ops.EPI_RELU, block_n=bn)
     sys.exit(0)
 if __name__ == "__main__" and os.environ.get("EPI_SET") == "head":
     run_head_dot()
