@@ -69,6 +69,7 @@ struct IgemmParams {
     int ss_shared;         // (always 1) one copy of the layer's whole scale / shift vectors per CTA
     int res_bytes;         // bytes of one residual box (16 KB, or 4 KB for the half-resolution RES_UP2 box)
     int b_resident;        // the whole weight matrix stays in shared memory for the CTA's lifetime (small N x K)
+    int mma_group;         // share mode: the MMA warp issues the three kernel-column stages of a chunk as one group (small N)
     int dbg;               // development probes (B200_DEBUG): 1 = no MMA issue, 2 = no A loads, 4 = no epilogue math
     const __nv_bfloat16* x;
     const float* scale;
@@ -153,7 +154,7 @@ __device__ unsigned long long g_prof[16];
         if (p.dbg & 16) {                                                               \
             const long long t_ = clock64();                                             \
             stmt;                                                                       \
-            if (blockIdx.x == 0 && lane == 0) g_prof[slot] += clock64() - t_;           \
+            if (blockIdx.x == 0 && lane == 0) atomicAdd(&g_prof[slot], (unsigned long long)(clock64() - t_)); /* RED: no stall */ \
         } else {                                                                        \
             stmt;                                                                       \
         }                                                                               \
@@ -744,6 +745,60 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.block_n);
                 int wbase = 0, kx = 0;  // resident weights: k-block of (chunk, ky = 0, kx)
+                if (p.mma_group) {
+                    // 3x3: the three kernel columns of a 64-channel chunk = three consecutive stages are issued as ONE group of
+                    // 36 instructions.  What precedes the first UTCHMMA of a group (waits, election, stage bases through
+                    // R2UR: ~55 instructions of one warp) leaves the tensor pipe idle once its short queue has drained --
+                    // ~480 cycles per 12 instructions of ~57 cycles at N = 32 when every stage was a group of its own; the
+                    // descriptor arithmetic of the other 35 instructions sits between instructions the pipe is executing.
+                    // N <= 64 only (host: mma_group): the group waits for three stages at once, which needs a deep ring, and
+                    // at N >= 128 the queue already covers the gap (grouping cost the N = 256 pair layers 17 %).
+                    for (int c = 0; c < a_per_tile; c += 3) {
+                        int sj[3], bj[3];
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            sj[j] = s;
+                            bj[j] = bs;
+                            B200_TIMED_WAIT(3, mbar_wait(&sm.a_full[s], ph));
+                            if (b_ring) B200_TIMED_WAIT(4, mbar_wait(&sm.b_full[bs], bph));
+                            if (++s == stages) { s = 0; ph ^= 1; }
+                            if (b_ring && ++bs == bst) { bs = 0; bph ^= 1; }
+                        }
+                        tc_fence_after();
+#ifdef B200_PROF
+                        const long long ti0 = clock64();
+#endif
+                        if (elect_one()) {
+#pragma unroll
+                            for (int j = 0; j < 3; ++j) {
+                                const uint64_t da = umma_desc_sw128(a0 + sj[j] * p.a_bytes);
+                                const uint64_t db = umma_desc_sw128(b0 + (b_ring ? bj[j] * 3 : wbase + j) * b_bytes);
+#pragma unroll
+                                for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+                                    for (int k = 0; k < kBlockK / 16; ++k) {
+                                        if constexpr (kPair)
+                                            umma_bf16_2sm(d_tmem, da + ky * sh + 2 * k, db + ky * wstep + 2 * k, idesc2, (c | j | ky | k) ? 1u : 0u);
+                                        else
+                                            umma_bf16(d_tmem, da + ky * sh + 2 * k, db + ky * wstep + 2 * k, idesc, (c | j | ky | k) ? 1u : 0u);
+                                    }
+                                }
+                                if constexpr (kPair) {
+                                    umma_commit_2sm(&sm.a_empty[sj[j]]);
+                                    umma_commit_2sm(&sm.b_empty[bj[j]]);
+                                } else {
+                                    umma_commit(&sm.a_empty[sj[j]]);
+                                    if (b_ring) umma_commit(&sm.b_empty[bj[j]]);
+                                }
+                            }
+                        }
+                        __syncwarp();
+#ifdef B200_PROF
+                        if ((p.dbg & 16) && blockIdx.x == 0 && lane == 0) atomicAdd(&g_prof[10], (unsigned long long)(clock64() - ti0));
+#endif
+                        wbase += 9;
+                    }
+                } else
                 for (int ai = 0; ai < a_per_tile; ++ai) {
                     B200_TIMED_WAIT(3, mbar_wait(&sm.a_full[s], ph));
                     if (b_ring) B200_TIMED_WAIT(4, mbar_wait(&sm.b_full[bs], bph));
@@ -783,7 +838,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
                     }
                     __syncwarp();
 #ifdef B200_PROF
-                    if ((p.dbg & 16) && blockIdx.x == 0 && lane == 0) g_prof[10] += clock64() - ti0;
+                    if ((p.dbg & 16) && blockIdx.x == 0 && lane == 0) atomicAdd(&g_prof[10], (unsigned long long)(clock64() - ti0));
 #endif
                     if (++s == stages) { s = 0; ph ^= 1; }
                     if (b_ring && ++bs == bst) { bs = 0; bph ^= 1; }
@@ -1396,7 +1451,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
     tc_fence_before();
     __syncthreads();
 #ifdef B200_PROF
-    if ((p.dbg & 16) && blockIdx.x == 0 && threadIdx.x == 0) g_prof[9] += clock64() - prof_t0;
+    if ((p.dbg & 16) && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_prof[9], (unsigned long long)(clock64() - prof_t0));
 #endif
     if constexpr (kPair) cluster_sync_all();  // neither CTA leaves (or frees TMEM) while the pair's MMAs / multicasts may still touch it
     if (warp == 1) {
@@ -1826,6 +1881,7 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     }
     p.a_stages = a_st;
     p.b_stages = b_st;
+    p.mma_group = (share && !pair && block_n <= 64 && a_st >= 5 && (p.b_resident || b_st >= 5) && !getenv("B200_NO_MMA_GROUP")) ? 1 : 0;
     p.b_kb = b_kb;
     p.epi_bufs = bufs;
     p.epi_active = ga;
