@@ -1,4 +1,3 @@
-export B200_DEBUG=16
-EPI_SET=offset timeout 120 python tools/epi_bench.py 2>&1 | grep -v "^dcn2"
-EPI_SET=conv2 timeout 120 python tools/epi_bench.py 2>&1 | grep -v "^dcn2"
-EPI_SET=conv3 timeout 120 python tools/epi_bench.py 2>&1 | grep -v "^dcn2" | head -10
+export B200_DEBUG=16 B200_VERBOSE=1
+EPI_SET=stem timeout 120 python tools/epi_bench.py 2>&1 | grep -v "^dcn2"
+EPI_SET=offset timeout 120 python tools/epi_bench.py 2>&1 | grep -v "^dcn2\|plan" | head -4

@@ -108,6 +108,41 @@ if __name__ == "__main__" and os.environ.get("EPI_SET") == "conv3":
         run(f"layer4.conv3 512->2048 res bn{bn}", 16, 32, 32, 512, 2048, 1, 1, ops.EPI_RELU, res=True, block_n=bn)
         run(f"layer4.conv3 no-res bn{bn}", 16, 32, 32, 512, 2048, 1, 1, ops.EPI_RELU, block_n=bn)
     sys.exit(0)
+def run_stem(iters=20):
+    dev = "cuda"
+    b, h, w = 16, 1024, 1024
+    img = torch.randn(b, 3, h, w, device=dev)
+    wt = torch.randn(64, 3, 7, 7, device=dev) / 147 ** 0.5
+    packed = torch.empty(b, h // 2 + 3, w // 2 + 3, 16, device=dev, dtype=torch.bfloat16)
+    ops.stem_pack(img, packed)
+    y = torch.empty(b, h // 2, w // 2, 64, device=dev, dtype=torch.bfloat16)
+    op = ops.Igemm(ops.IGEMM_STEM, packed, ops.pack_stem_weight(wt, 64), torch.ones(64, device=dev), torch.zeros(64, device=dev), y,
+                   batch=b, in_h=h, in_w=w, in_c=3, out_c=64, ksize=7, stride=2, flags=ops.EPI_RELU, name="stem")
+    for _ in range(3):
+        op()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        op()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    if int(os.environ.get("B200_DEBUG", "0")) & 16:
+        import ctypes as C
+        from ocr_vi_invoice_b200 import _lib
+        buf = (C.c_ulonglong * 16)()
+        _lib.load().b200_igemm_debug_counters(buf)
+        op(); torch.cuda.synchronize()
+        _lib.load().b200_igemm_debug_counters(buf)
+        names = ["A.empty", "B.empty", "mma.tempty", "mma.a_full", "mma.b_full", "dma.out_ready", "dma.wait_read", "epi.tfull", "epi.slot", "total", "mma.issue"]
+        print("   " + "  ".join(f"{n}={buf[i]}" for i, n in enumerate(names)))
+    print(f"stem 7x7 s2 3->64 @1024      {ms:7.3f} ms  {op.flops / ms / 1e9:8.1f} TF/s  {op.info()}", flush=True)
+
+
+if __name__ == "__main__" and os.environ.get("EPI_SET") == "stem":
+    run_stem()
+    sys.exit(0)
 if __name__ == "__main__" and os.environ.get("EPI_SET") == "head":
     run_head_dot()
     sys.exit(0)
