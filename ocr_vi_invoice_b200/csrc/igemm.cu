@@ -137,8 +137,8 @@ __device__ __forceinline__ SmemLayout carve(uint8_t* raw, const IgemmParams& p) 
     s.b_full = s.a_empty + kMaxStages;
     s.b_empty = s.b_full + kMaxStages;
     s.tfull = s.b_empty + kMaxStages;
-    s.tempty = s.tfull + 2;
-    s.res_full = s.tempty + 2;
+    s.tempty = s.tfull + 4;
+    s.res_full = s.tempty + 4;
     s.slot_free = s.res_full + kMaxEpiBufs;
     s.out_ready = s.slot_free + kMaxEpiBufs;
     s.b_ready = s.out_ready + kMaxEpiBufs;
@@ -517,7 +517,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
                     mbar_init(&sm.b_empty[s], 1);
                 }
             }
-            for (int a = 0; a < 2; ++a) {
+            for (int a = 0; a < 4; ++a) {  // (share mode at N <= 64 runs four accumulators)
                 mbar_init(&sm.tfull[a], 1);
                 mbar_init(&sm.tempty[a], (kPair ? 2 : 1) * 4 * G);  // pair: the epilogue warps of BOTH CTAs release rank 0's barrier
             }
@@ -738,10 +738,56 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
             const uint32_t idesc2 = umma_idesc_bf16_2sm(static_cast<uint32_t>(p.block_n)); (void)idesc2;
             int bs = 0;
             uint32_t bph = 0;
+            const int amask = p.nacc - 1, ashift = (p.nacc == 4) ? 2 : 1;  // share mode: 2 or 4 accumulators
+            if (p.mma_group == 2) {
+                // One stage per tile (stem: 16 instructions; 3x3 64 -> 64 would be three): TWO tiles per issue group, each into
+                // its own accumulator (four in flight), for the same reason the kernel columns of a chunk are grouped below --
+                // the stem's MMA warp spent ~1000 cycles per tile outside instruction issue against ~1040 inside.
+                for (int u = u_first; u < num_units; u += 2 * u_stride, it += 2) {
+                    const bool two = (u + u_stride < num_units);
+                    int sj[2];
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        sj[j] = s;
+                        if (j == 0 || two) {
+                            B200_TIMED_WAIT(2, mbar_wait(&sm.tempty[(it + j) & amask], (((it + j) >> ashift) & 1) ^ 1));
+                            B200_TIMED_WAIT(3, mbar_wait(&sm.a_full[s], ph));
+                            if (++s == stages) { s = 0; ph ^= 1; }
+                        }
+                    }
+                    tc_fence_after();
+#ifdef B200_PROF
+                    const long long ti0 = clock64();
+#endif
+                    if (elect_one()) {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            if (j == 0 || two) {
+                                const int acc = (it + j) & amask;
+                                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.block_n);
+                                const uint64_t da = umma_desc_sw128(a0 + sj[j] * p.a_bytes);
+                                const uint64_t db = umma_desc_sw128(b0);
+#pragma unroll
+                                for (int ky = 0; ky < 4; ++ky) {
+#pragma unroll
+                                    for (int k = 0; k < kBlockK / 16; ++k)
+                                        umma_bf16(d_tmem, da + ky * sh + 2 * k, db + ky * wstep + 2 * k, idesc, (ky | k) ? 1u : 0u);
+                                }
+                                umma_commit(&sm.a_empty[sj[j]]);
+                                umma_commit(&sm.tfull[acc]);
+                            }
+                        }
+                    }
+                    __syncwarp();
+#ifdef B200_PROF
+                    if ((p.dbg & 16) && blockIdx.x == 0 && lane == 0) atomicAdd(&g_prof[10], (unsigned long long)(clock64() - ti0));
+#endif
+                }
+            } else
             for (int u = u_first; u < num_units; u += u_stride, ++it) {
                 const int tile = unit_tile(u); (void)tile;
-                const int acc = it & 1;
-                B200_TIMED_WAIT(2, mbar_wait(&sm.tempty[acc], ((it >> 1) & 1) ^ 1));
+                const int acc = it & amask;
+                B200_TIMED_WAIT(2, mbar_wait(&sm.tempty[acc], ((it >> ashift) & 1) ^ 1));
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.block_n);
                 int wbase = 0, kx = 0;  // resident weights: k-block of (chunk, ky = 0, kx)
@@ -1160,8 +1206,9 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
         for (int u = u_first; u < num_units; u += u_stride, ++it) {
                 const int tile = unit_tile(u); (void)tile;
             const TileCoord t = decode_tile(p, tile);
-            const int as = (kEpi == 4) ? 0 : ((!kGather || p.nacc == 2) ? (it & 1) : 0);
-            const uint32_t aph = (kEpi == 4) ? (it & 1) : ((!kGather || p.nacc == 2) ? ((it >> 1) & 1) : (it & 1));
+            const int as = (kEpi == 4) ? 0 : (kShare ? (it & (p.nacc - 1)) : ((!kGather || p.nacc == 2) ? (it & 1) : 0));
+            const uint32_t aph = (kEpi == 4) ? (it & 1)
+                                 : (kShare ? ((it >> (p.nacc == 4 ? 2 : 1)) & 1) : ((!kGather || p.nacc == 2) ? ((it >> 1) & 1) : (it & 1)));
             const int oy = t.y0 + ty, ox = t.x0 + tx;
             const bool valid = (oy < p.out_h) && (ox < p.out_w);
             B200_TIMED_WAIT(7, mbar_wait(&sm.tfull[as], aph));
@@ -1882,6 +1929,12 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     p.a_stages = a_st;
     p.b_stages = b_st;
     p.mma_group = (share && !pair && block_n <= 64 && a_st >= 5 && (p.b_resident || b_st >= 5) && !getenv("B200_NO_MMA_GROUP")) ? 1 : 0;
+    // share-mode layers with N <= 64 keep four accumulators in flight (N x 4 <= 256 TMEM columns); the stem (one stage = one
+    // tile) issues two tiles per group
+    if (fat && !pair && block_n <= 64 && !(d->flags & (B200_EPI_HEAD_DOT | B200_EPI_CHAIN)) && !getenv("B200_NACC2")) {
+        p.nacc = 4;
+        if (stem_share && p.b_resident && a_st >= 4 && !getenv("B200_NO_MMA_GROUP")) p.mma_group = 2;
+    }
     p.b_kb = b_kb;
     p.epi_bufs = bufs;
     p.epi_active = ga;
