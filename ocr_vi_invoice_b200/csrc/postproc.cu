@@ -65,45 +65,68 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
     }
 }
 
-// One warp = 4 consecutive words (4 loads in flight per lane).  Writes the foreground bitmask and, for foreground
-// pixels only, L[p] = index of the first pixel of p's run inside its word.
-__global__ void pp_init_kernel(const PP p) {
+// One warp = one image row.  Writes the foreground bitmask and, for foreground pixels only, L[p] = index of the first pixel
+// of p's horizontal run -- the WHOLE run, across word boundaries: the start of the run that enters a word from the left is
+// found by a scan over the row's word masks (a word of 32 foreground pixels is transparent, any other word either ends the
+// run or starts a new one behind its highest background pixel).  The merge kernel then only links runs of adjacent rows;
+// linking the words of a run one by one built chains as long as the run (a page-wide component: 32 unions per row, each
+// walking the chain of the ones before it).
+__global__ void __launch_bounds__(256) pp_init_kernel(const PP p) {
     const int lane = threadIdx.x & 31;
-    // all indices fit 32 bits (batch*h*w < 2^31 is checked by the host): no 64-bit divisions in the loops
-    const uint32_t nwords = static_cast<uint32_t>(p.batch) * p.h * p.wpr;
-    const uint32_t nquads = (nwords + 3) >> 2;
-    for (uint32_t wq = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wq < nquads; wq += (gridDim.x * blockDim.x) >> 5) {
-        float v[4];
-        uint32_t g[4];
-        bool in[4];
+    const uint32_t nrows = static_cast<uint32_t>(p.batch) * p.h;
+    const uint32_t below = (1u << lane) - 1u;
+    for (uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < nrows; row += (gridDim.x * blockDim.x) >> 5) {
+        const float* pr = p.prob + static_cast<size_t>(row) * p.w;
+        const uint32_t g0 = row * p.w;
+        int carry = -1;  // x of the first pixel of the run that holds the last pixel of the previous 32-word segment, or -1
+        for (int w0 = 0; w0 < p.wpr; w0 += 32) {
+            const int nw = min(32, p.wpr - w0);
+            // masks of the segment's words: lane j keeps word w0 + j
+            uint32_t mymask = 0;
+            for (int j0 = 0; j0 < nw; j0 += 8) {
+                float v[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t wd = wq * 4 + j;
-            const uint32_t row = wd / p.wpr;  // n*h + y
-            const int wx = static_cast<int>(wd - row * p.wpr);
-            const int x = wx * 32 + lane;
-            in[j] = (wd < nwords) && (x < p.w);
-            g[j] = row * p.w + x;
-            v[j] = in[j] ? __ldg(p.prob + g[j]) : 0.0f;
-        }
+                for (int i = 0; i < 8; ++i) {
+                    const int x = (w0 + j0 + i) * 32 + lane;
+                    v[i] = (j0 + i < nw && x < p.w) ? __ldg(pr + x) : -1.0f;
+                }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t wd = wq * 4 + j;
-            const bool fg = in[j] && (v[j] > p.thresh);
-            const uint32_t m = __ballot_sync(0xffffffffu, fg);
-            if (wd < nwords && lane == 0) p.mask[wd] = m;
-            if (fg) {
-                // zeros strictly below this lane; the run starts right above the highest of them
-                const uint32_t z = ~m & ((1u << lane) - 1u);
-                const int start = z ? (32 - __clz(z)) : 0;
-                p.L[g[j]] = static_cast<int>(g[j]) - (lane - start);
+                for (int i = 0; i < 8; ++i) {
+                    const int x = (w0 + j0 + i) * 32 + lane;
+                    const uint32_t m = __ballot_sync(0xffffffffu, (j0 + i < nw) && (x < p.w) && (v[i] > p.thresh));
+                    if (lane == j0 + i) mymask = m;
+                }
             }
+            if (lane < nw) p.mask[row * p.wpr + w0 + lane] = mymask;
+            // out = x of the first pixel of the run that holds the LAST pixel of this lane's word, -1 if that pixel is background
+            const bool full = (mymask == 0xffffffffu);
+            int out = -1;
+            if (!full && (mymask >> 31)) out = (w0 + lane) * 32 + (32 - __clz(~mymask));
+            const uint32_t nonfull = __ballot_sync(0xffffffffu, !full);
+            const uint32_t nb = nonfull & below;          // words of this segment before mine that are not all foreground
+            const int r = nb ? (31 - __clz(nb)) : 0;      // the nearest of them
+            const int o = __shfl_sync(0xffffffffu, out, r);
+            if (full) out = nb ? ((o >= 0) ? o : (w0 + r + 1) * 32) : ((carry >= 0) ? carry : w0 * 32);
+            int in = __shfl_up_sync(0xffffffffu, out, 1);  // run entering my word from the left (first pixel's x), or -1
+            if (lane == 0) in = carry;
+            for (int j = 0; j < nw; ++j) {
+                const uint32_t m = __shfl_sync(0xffffffffu, mymask, j);
+                const int inj = __shfl_sync(0xffffffffu, in, j);
+                if ((m >> lane) & 1u) {
+                    // background pixels strictly below this lane; the run starts right above the highest of them
+                    const uint32_t z = ~m & below;
+                    const int x0 = (w0 + j) * 32;
+                    const int start = z ? (x0 + 32 - __clz(z)) : ((inj >= 0) ? inj : x0);
+                    p.L[g0 + x0 + lane] = static_cast<int>(g0) + start;
+                }
+            }
+            carry = __shfl_sync(0xffffffffu, out, nw - 1);
         }
     }
 }
 
-// Merge runs across word boundaries and with the row above (8-connectivity).  Which unions are needed is decided
-// from six bitmask words per warp, skipping the ones a horizontally adjacent pixel is guaranteed to perform.
+// Merge runs with the row above (8-connectivity; a horizontal run is one set since pp_init).  Which unions are needed is
+// decided from six bitmask words per warp, skipping the ones a horizontally adjacent pixel is guaranteed to perform.
 __global__ void pp_merge_kernel(const PP p) {
     const int lane = threadIdx.x & 31;
     const uint32_t nwords = static_cast<uint32_t>(p.batch) * p.h * p.wpr;
@@ -120,13 +143,11 @@ __global__ void pp_merge_kernel(const PP p) {
         const uint32_t left = (m << 1) | (ml >> 31);    // bit i: pixel i-1 of this row is foreground
         const uint32_t right = (m >> 1) | (mr << 31);   // bit i: pixel i+1
         const uint32_t upl = (u << 1) | (ul >> 31), upr = (u >> 1) | (ur << 31);
-        const uint32_t do_word = m & 1u & (ml >> 31);            // run continues from the previous word
         const uint32_t do_up = m & u & ~(left & upl);            // the left pair has not linked these two runs yet
         const uint32_t do_ul = m & ~u & upl & ~left;
         const uint32_t do_ur = m & ~u & upr & ~right;
         const uint32_t g = row * p.w + wx * 32 + lane;
         const uint32_t bit = 1u << lane;
-        if (do_word & bit) uf_union(p.L, static_cast<int>(g), static_cast<int>(g - 1));
         if (do_up & bit) uf_union(p.L, static_cast<int>(g), static_cast<int>(g - p.w));
         if (do_ul & bit) uf_union(p.L, static_cast<int>(g), static_cast<int>(g - p.w - 1));
         if (do_ur & bit) uf_union(p.L, static_cast<int>(g), static_cast<int>(g - p.w + 1));
@@ -417,9 +438,10 @@ extern "C" int b200_postproc(const float* prob, int32_t* labels, b200_box* boxes
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int64_t nwords = static_cast<int64_t>(batch) * wimg;
     const int cap = 148 * 8;  // 8 resident 256-thread blocks per SM
-    const int qblocks = static_cast<int>(((nwords + 31) / 32 < cap) ? (nwords + 31) / 32 : cap);
     const int wblocks = static_cast<int>(((nwords + 7) / 8 < cap) ? (nwords + 7) / 8 : cap);
-    pp_init_kernel<<<qblocks, 256, 0, st>>>(p);
+    const int64_t nrows = static_cast<int64_t>(batch) * h;
+    const int rblocks = static_cast<int>(((nrows + 7) / 8 < cap) ? (nrows + 7) / 8 : cap);
+    pp_init_kernel<<<rblocks, 256, 0, st>>>(p);
     pp_merge_kernel<<<wblocks, 256, 0, st>>>(p);
     pp_flatten_count_kernel<<<batch * p.nchunks, 256, 0, st>>>(p);
     pp_scan_kernel<<<batch, 256, 0, st>>>(p);

@@ -143,6 +143,13 @@ def run_stem(iters=20):
 if __name__ == "__main__" and os.environ.get("EPI_SET") == "stem":
     run_stem()
     sys.exit(0)
+if __name__ == "__main__" and os.environ.get("EPI_SET") == "conv1":
+    run("layer3.conv1 1024->256 64x64", 16, 64, 64, 1024, 256, 1, 1, ops.EPI_RELU)
+    run("layer4.conv1 2048->512 32x32", 16, 32, 32, 2048, 512, 1, 1, ops.EPI_RELU)
+    run("layer2.conv1 512->128 128x128", 16, 128, 128, 512, 128, 1, 1, ops.EPI_RELU)
+    run("layer3.down 512->1024 s2", 16, 128, 128, 512, 1024, 1, 2, 0)
+    run("lat1 512->256 128x128", 16, 128, 128, 512, 256, 1, 1, 0)
+    sys.exit(0)
 if __name__ == "__main__" and os.environ.get("EPI_SET") == "head":
     run_head_dot()
     sys.exit(0)
