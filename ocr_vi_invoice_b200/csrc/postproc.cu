@@ -44,10 +44,22 @@ __device__ __forceinline__ int uf_find(const int* L, int a) {
 }
 // find with path compression: re-point the start at the root it found (any ancestor is a valid parent, and parents
 // only ever decrease, so a racing writer can at worst store another valid ancestor)
+// Path halving on the way up: every visited node is re-pointed at its grandparent.  Only a ROOT's entry is ever the
+// target of a union's atomicMin and a node that has a parent never becomes a root again (parents have smaller indices), so a
+// plain store of an ancestor into a non-root's entry cannot lose a link.  (Without it a page-high component is a linked list
+// of row heads when the rows are merged concurrently, and one find is a thousand dependent L2 round trips.)
 __device__ __forceinline__ int uf_find_compress(int* L, int a) {
-    const int r = uf_find(L, a);
-    if (r != a && L[a] > r) L[a] = r;
-    return r;
+    const int start = a;
+    int p = L[a];
+    while (p != a) {
+        const int gp = L[p];
+        if (gp == p) { a = p; break; }
+        L[a] = gp;
+        a = gp;
+        p = L[a];
+    }
+    if (a != start && L[start] > a) L[start] = a;
+    return a;
 }
 __device__ __forceinline__ void uf_union(int* L, int a, int b) {
     while (true) {
@@ -127,30 +139,47 @@ __global__ void __launch_bounds__(256) pp_init_kernel(const PP p) {
 
 // Merge runs with the row above (8-connectivity; a horizontal run is one set since pp_init).  Which unions are needed is
 // decided from six bitmask words per warp, skipping the ones a horizontally adjacent pixel is guaranteed to perform.
-__global__ void pp_merge_kernel(const PP p) {
+// One warp walks a 32-pixel column of kMergeRows rows DOWNWARDS: when row y is linked, row y-1 of the same strip already hangs
+// under the strip's top, so a find is a hop or two.  (Rows linked concurrently each grab their still-unlinked upper
+// neighbour and a tall component becomes a linked list of row heads; the first find over it was hundreds of dependent L2
+// round trips -- a 170 us tail on a page-sized component.)  Lists now form only across strips (h / 32 entries).
+constexpr int kMergeRows = 32;
+__global__ void __launch_bounds__(256) pp_merge_kernel(const PP p) {
     const int lane = threadIdx.x & 31;
-    const uint32_t nwords = static_cast<uint32_t>(p.batch) * p.h * p.wpr;
-    for (uint32_t wd = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wd < nwords; wd += (gridDim.x * blockDim.x) >> 5) {
-        const uint32_t m = p.mask[wd];
-        if (m == 0) continue;
-        const uint32_t row = wd / p.wpr;
-        const int wx = static_cast<int>(wd - row * p.wpr);
-        const int y = static_cast<int>(row % p.h);
-        const bool has_l = wx > 0, has_r = wx + 1 < p.wpr, has_u = y > 0;
-        const uint32_t ml = has_l ? p.mask[wd - 1] : 0u, mr = has_r ? p.mask[wd + 1] : 0u;
-        const uint32_t u = has_u ? p.mask[wd - p.wpr] : 0u;
-        const uint32_t ul = (has_u && has_l) ? p.mask[wd - p.wpr - 1] : 0u, ur = (has_u && has_r) ? p.mask[wd - p.wpr + 1] : 0u;
-        const uint32_t left = (m << 1) | (ml >> 31);    // bit i: pixel i-1 of this row is foreground
-        const uint32_t right = (m >> 1) | (mr << 31);   // bit i: pixel i+1
-        const uint32_t upl = (u << 1) | (ul >> 31), upr = (u >> 1) | (ur << 31);
-        const uint32_t do_up = m & u & ~(left & upl);            // the left pair has not linked these two runs yet
-        const uint32_t do_ul = m & ~u & upl & ~left;
-        const uint32_t do_ur = m & ~u & upr & ~right;
-        const uint32_t g = row * p.w + wx * 32 + lane;
-        const uint32_t bit = 1u << lane;
-        if (do_up & bit) uf_union(p.L, static_cast<int>(g), static_cast<int>(g - p.w));
-        if (do_ul & bit) uf_union(p.L, static_cast<int>(g), static_cast<int>(g - p.w - 1));
-        if (do_ur & bit) uf_union(p.L, static_cast<int>(g), static_cast<int>(g - p.w + 1));
+    const uint32_t bit = 1u << lane;
+    const uint32_t strips = static_cast<uint32_t>((p.h + kMergeRows - 1) / kMergeRows);
+    const uint32_t items = static_cast<uint32_t>(p.batch) * strips * p.wpr;
+    for (uint32_t it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < items; it += (gridDim.x * blockDim.x) >> 5) {
+        const uint32_t t = it / p.wpr;
+        const int wx = static_cast<int>(it - t * p.wpr);
+        const uint32_t n = t / strips;
+        const int y0 = static_cast<int>(t - n * strips) * kMergeRows;
+        const int y1 = min(y0 + kMergeRows, p.h);
+        const bool has_l = wx > 0, has_r = wx + 1 < p.wpr;
+        uint32_t wd = (n * p.h + y0) * p.wpr + wx;
+        uint32_t g = (n * p.h + y0) * p.w + wx * 32 + lane;
+        uint32_t u = 0, ul = 0, ur = 0;  // masks of the row above
+        if (y0 > 0) {
+            u = p.mask[wd - p.wpr];
+            ul = has_l ? p.mask[wd - p.wpr - 1] : 0u;
+            ur = has_r ? p.mask[wd - p.wpr + 1] : 0u;
+        }
+        for (int y = y0; y < y1; ++y, wd += p.wpr, g += p.w) {
+            const uint32_t m = p.mask[wd];
+            const uint32_t ml = has_l ? p.mask[wd - 1] : 0u, mr = has_r ? p.mask[wd + 1] : 0u;
+            if (m) {
+                const uint32_t left = (m << 1) | (ml >> 31);    // bit i: pixel i-1 of this row is foreground
+                const uint32_t right = (m >> 1) | (mr << 31);   // bit i: pixel i+1
+                const uint32_t upl = (u << 1) | (ul >> 31), upr = (u >> 1) | (ur << 31);
+                const uint32_t do_up = m & u & ~(left & upl);   // the left pair has not linked these two runs yet
+                const uint32_t do_ul = m & ~u & upl & ~left;
+                const uint32_t do_ur = m & ~u & upr & ~right;
+                if (do_up & bit) uf_union(p.L, static_cast<int>(g), static_cast<int>(g - p.w));
+                if (do_ul & bit) uf_union(p.L, static_cast<int>(g), static_cast<int>(g - p.w - 1));
+                if (do_ur & bit) uf_union(p.L, static_cast<int>(g), static_cast<int>(g - p.w + 1));
+            }
+            u = m; ul = ml; ur = mr;
+        }
     }
 }
 
@@ -271,6 +300,11 @@ __global__ void __launch_bounds__(256) pp_stats_kernel(const PP p) {
     const uint32_t per_block = (nwords + gridDim.x - 1) / gridDim.x;
     const uint32_t w_begin = blockIdx.x * per_block;
     const uint32_t w_end = (w_begin + per_block < nwords) ? w_begin + per_block : nwords;
+    // runs of the block's cached component are summed in registers first (every lane its own run heads) and reach shared
+    // memory once per warp: on a page-sized component the eight warps of a block were serialising six same-address
+    // shared-memory atomics per word
+    int a_minx = 0x7fffffff, a_miny = 0x7fffffff, a_maxx = -1, a_maxy = -1, a_npix = 0;
+    unsigned long long a_qsum = 0ull;
     for (uint32_t wd = w_begin + warp; wd < w_end; wd += 8) {
         const uint32_t m = p.mask[wd];
         if (m == 0 && !p.labels) continue;
@@ -286,8 +320,11 @@ __global__ void __launch_bounds__(256) pp_stats_kernel(const PP p) {
         const int n = static_cast<int>(row / p.h);
         int lab = 0;
         uint32_t q = 0;
-        if ((m >> lane) & 1u) {
-            lab = p.R[p.L[g]];
+        const bool fg = (m >> lane) & 1u;
+        const bool run_head = fg && (lane == 0 || !((m >> (lane - 1)) & 1u));
+        if (fg) {
+            // the label costs two dependent loads: every pixel needs it for the label map, the statistics only at run heads
+            if (p.labels || run_head) lab = p.R[p.L[g]];
             q = __float2uint_rn(p.prob[g] * 16777216.0f);
         }
         if (p.labels && x < p.w) p.labels[g] = lab;
@@ -298,18 +335,18 @@ __global__ void __launch_bounds__(256) pp_stats_kernel(const PP p) {
             const uint32_t t = __shfl_down_sync(0xffffffffu, q, o);
             if (lane + o < end) q += t;
         }
-        const bool head = (lab != 0) && (lane == 0 || !((m >> (lane - 1)) & 1u));
+        const bool head = run_head && (lab != 0);
         if (head && lab <= p.maxc) {
             const int key = n * p.maxc + (lab - 1);
             int cur = s_key;
             if (cur == -1) cur = atomicCAS(&s_key, -1, key), cur = (cur == -1) ? key : cur;
             if (cur == key) {
-                atomicMin(&s_minx, x);
-                atomicMax(&s_maxx, x + (end - lane) - 1);
-                atomicMin(&s_miny, y);
-                atomicMax(&s_maxy, y);
-                atomicAdd(&s_npix, end - lane);
-                atomicAdd(&s_qsum, static_cast<unsigned long long>(q));
+                a_minx = min(a_minx, x);
+                a_maxx = max(a_maxx, x + (end - lane) - 1);
+                a_miny = min(a_miny, y);
+                a_maxy = max(a_maxy, y);
+                a_npix += end - lane;
+                a_qsum += static_cast<unsigned long long>(q);
             } else {
                 CompRec* r = p.rec + key;
                 atomicMin(&r->minx, x);
@@ -320,6 +357,21 @@ __global__ void __launch_bounds__(256) pp_stats_kernel(const PP p) {
                 atomicAdd(&r->qsum, static_cast<unsigned long long>(q));
             }
         }
+    }
+    a_minx = __reduce_min_sync(0xffffffffu, a_minx);
+    a_miny = __reduce_min_sync(0xffffffffu, a_miny);
+    a_maxx = __reduce_max_sync(0xffffffffu, a_maxx);
+    a_maxy = __reduce_max_sync(0xffffffffu, a_maxy);
+    a_npix = __reduce_add_sync(0xffffffffu, a_npix);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a_qsum += __shfl_down_sync(0xffffffffu, a_qsum, o);
+    if (lane == 0 && a_npix > 0) {
+        atomicMin(&s_minx, a_minx);
+        atomicMax(&s_maxx, a_maxx);
+        atomicMin(&s_miny, a_miny);
+        atomicMax(&s_maxy, a_maxy);
+        atomicAdd(&s_npix, a_npix);
+        atomicAdd(&s_qsum, a_qsum);
     }
     __syncthreads();
     if (threadIdx.x == 0 && s_key >= 0) {
@@ -442,7 +494,9 @@ extern "C" int b200_postproc(const float* prob, int32_t* labels, b200_box* boxes
     const int64_t nrows = static_cast<int64_t>(batch) * h;
     const int rblocks = static_cast<int>(((nrows + 7) / 8 < cap) ? (nrows + 7) / 8 : cap);
     pp_init_kernel<<<rblocks, 256, 0, st>>>(p);
-    pp_merge_kernel<<<wblocks, 256, 0, st>>>(p);
+    const int64_t mitems = static_cast<int64_t>(batch) * ((h + kMergeRows - 1) / kMergeRows) * p.wpr;
+    const int mblocks = static_cast<int>(((mitems + 7) / 8 < cap) ? (mitems + 7) / 8 : cap);
+    pp_merge_kernel<<<mblocks, 256, 0, st>>>(p);
     pp_flatten_count_kernel<<<batch * p.nchunks, 256, 0, st>>>(p);
     pp_scan_kernel<<<batch, 256, 0, st>>>(p);
     pp_rank_kernel<<<batch * p.nchunks, 256, 0, st>>>(p);
