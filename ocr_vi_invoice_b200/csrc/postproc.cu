@@ -193,14 +193,19 @@ __global__ void __launch_bounds__(256) pp_flatten_count_kernel(const PP p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wimg = p.h * p.wpr;
     int cnt = 0;
-    for (int i = warp; i < kChunkWords; i += 8) {
+    // (row, word-in-row) of this warp's words advance by additions: the kernels of this file are bound by instruction issue,
+    // and a division by a run-time divisor is ~25 of them
+    const int wl0 = ck * kChunkWords + warp;
+    int fy = wl0 / p.wpr, fx = wl0 - fy * p.wpr;
+    for (int i = warp; i < kChunkWords; i += 8, fx += 8) {
         const int wl = ck * kChunkWords + i;
         if (wl >= wimg) break;
+        while (fx >= p.wpr) { fx -= p.wpr; ++fy; }
         const uint32_t wd = static_cast<uint32_t>(n) * wimg + wl;
         const uint32_t m = p.mask[wd];
         uint32_t rm = 0;
         if (m) {
-            const uint32_t g = (wd / p.wpr) * p.w + (wl % p.wpr) * 32 + lane;
+            const uint32_t g = (static_cast<uint32_t>(n) * p.h + fy) * p.w + fx * 32 + lane;
             bool root = false;
             if ((m >> lane) & 1u) {
                 const int r = uf_find(p.L, static_cast<int>(g));
@@ -305,19 +310,25 @@ __global__ void __launch_bounds__(256) pp_stats_kernel(const PP p) {
     // shared-memory atomics per word
     int a_minx = 0x7fffffff, a_miny = 0x7fffffff, a_maxx = -1, a_maxy = -1, a_npix = 0;
     unsigned long long a_qsum = 0ull;
+    uint32_t row = (w_begin + warp) / p.wpr;
+    int wx = static_cast<int>(w_begin + warp - row * p.wpr) - 8;
+    int n = static_cast<int>(row / p.h);
+    int y = static_cast<int>(row - static_cast<uint32_t>(n) * p.h);
     for (uint32_t wd = w_begin + warp; wd < w_end; wd += 8) {
+        wx += 8;  // (row, word-in-row, image) by additions, see pp_flatten_count_kernel
+        while (wx >= p.wpr) {
+            wx -= p.wpr;
+            ++row;
+            if (++y == p.h) { y = 0; ++n; }
+        }
         const uint32_t m = p.mask[wd];
         if (m == 0 && !p.labels) continue;
-        const uint32_t row = wd / p.wpr;
-        const int wx = static_cast<int>(wd - row * p.wpr);
         const int x = wx * 32 + lane;
         const uint32_t g = row * p.w + x;
         if (m == 0) {
             if (x < p.w) p.labels[g] = 0;
             continue;
         }
-        const int y = static_cast<int>(row % p.h);
-        const int n = static_cast<int>(row / p.h);
         int lab = 0;
         uint32_t q = 0;
         const bool fg = (m >> lane) & 1u;
