@@ -11,13 +11,16 @@ namespace b200 {
 // channel (dy*2+dx)*3 + c holds img[c][2*br+dy][2*bc+dx] of block (br, bc) = (row-2, col-2); 12..15 = 0.
 // With this layout the 7x7 s2 p3 stem conv (torchvision resnet.py:197) is a 4x4 s1 conv whose A rows are
 // contiguous 128-byte runs (4 blocks x 16 channels).
+// Idx: uint32_t whenever the packed pixel count fits (a 64-bit division by a run-time divisor is ~100 instructions, and the
+// flat index is split by three of them)
+template <typename Idx>
 __global__ void stem_pack_kernel(const float* __restrict__ img, uint4* __restrict__ out, int batch, int h, int w) {
     const int ph = h / 2 + 3, pw = w / 2 + 3;
-    const int64_t total = static_cast<int64_t>(batch) * ph * pw;
-    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const Idx total = static_cast<Idx>(batch) * ph * pw;
+    for (Idx i = blockIdx.x * static_cast<Idx>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<Idx>(gridDim.x) * blockDim.x) {
         const int px = static_cast<int>(i % pw);
-        int64_t r = i / pw;
+        Idx r = i / pw;
         const int py = static_cast<int>(r % ph);
         const int n = static_cast<int>(r / ph);
         const int br = py - 2, bc = px - 2;
@@ -52,15 +55,16 @@ __global__ void stem_pack_kernel(const float* __restrict__ img, uint4* __restric
 
 // Same packing straight from the decoded image: uint8 HWC RGB -> (v / 255 - mean) / std (the reference's host-side
 // normalisation, src/pipeline/pipeline2.py:312-314) -> bf16 space-to-depth.  4x less H2D traffic than fp32 NCHW.
+template <typename Idx>
 __global__ void stem_pack_u8_kernel(const uint8_t* __restrict__ img, uint4* __restrict__ out, int batch, int h, int w,
                                     float m0, float m1, float m2, float i0, float i1, float i2) {
     const int ph = h / 2 + 3, pw = w / 2 + 3;
-    const int64_t total = static_cast<int64_t>(batch) * ph * pw;
+    const Idx total = static_cast<Idx>(batch) * ph * pw;
     const float mean[3] = {m0, m1, m2}, inv[3] = {i0, i1, i2};
-    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    for (Idx i = blockIdx.x * static_cast<Idx>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<Idx>(gridDim.x) * blockDim.x) {
         const int px = static_cast<int>(i % pw);
-        int64_t r = i / pw;
+        Idx r = i / pw;
         const int py = static_cast<int>(r % ph);
         const int n = static_cast<int>(r / ph);
         const int br = py - 2, bc = px - 2;
@@ -565,8 +569,12 @@ extern "C" int b200_stem_pack(const float* img, void* packed, int batch, int h, 
     if (!img || !packed) return set_error("b200_stem_pack: null pointer");
     if (batch <= 0 || h <= 0 || w <= 0 || (h & 1) || (w & 1)) return set_error("b200_stem_pack: H and W must be even");
     const int64_t total = static_cast<int64_t>(batch) * (h / 2 + 3) * (w / 2 + 3);
-    stem_pack_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        img, reinterpret_cast<uint4*>(packed), batch, h, w);
+    if (total < (int64_t(1) << 30))
+        stem_pack_kernel<uint32_t><<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+            img, reinterpret_cast<uint4*>(packed), batch, h, w);
+    else
+        stem_pack_kernel<int64_t><<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+            img, reinterpret_cast<uint4*>(packed), batch, h, w);
     return check_cuda(cudaGetLastError(), "b200_stem_pack launch");
 }
 
@@ -576,9 +584,14 @@ extern "C" int b200_stem_pack_u8(const void* img_hwc, void* packed, int batch, i
     if (batch <= 0 || h <= 0 || w <= 0 || (h & 1) || (w & 1)) return set_error("b200_stem_pack_u8: H and W must be even");
     if (std3[0] == 0.0f || std3[1] == 0.0f || std3[2] == 0.0f) return set_error("b200_stem_pack_u8: zero std");
     const int64_t total = static_cast<int64_t>(batch) * (h / 2 + 3) * (w / 2 + 3);
-    stem_pack_u8_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const uint8_t*>(img_hwc), reinterpret_cast<uint4*>(packed), batch, h, w, mean3[0], mean3[1], mean3[2],
-        1.0f / std3[0], 1.0f / std3[1], 1.0f / std3[2]);
+    if (total < (int64_t(1) << 30))
+        stem_pack_u8_kernel<uint32_t><<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+            reinterpret_cast<const uint8_t*>(img_hwc), reinterpret_cast<uint4*>(packed), batch, h, w, mean3[0], mean3[1],
+            mean3[2], 1.0f / std3[0], 1.0f / std3[1], 1.0f / std3[2]);
+    else
+        stem_pack_u8_kernel<int64_t><<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+            reinterpret_cast<const uint8_t*>(img_hwc), reinterpret_cast<uint4*>(packed), batch, h, w, mean3[0], mean3[1],
+            mean3[2], 1.0f / std3[0], 1.0f / std3[1], 1.0f / std3[2]);
     return check_cuda(cudaGetLastError(), "b200_stem_pack_u8 launch");
 }
 
