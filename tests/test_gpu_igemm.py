@@ -155,6 +155,20 @@ def test_stem_igemm(shape):
     assert torch.equal(nchw(yp), refp)
 
 
+@pytest.mark.parametrize("case", [(2, 20, 36, 8), (1, 34, 70, 32), (3, 12, 18, 128), (1, 64, 66, 64), (1, 8, 10, 24)])
+def test_maxpool_channel_counts(case):
+    """The strip kernel's block shapes (256 / (C / 8) output columns per block) and the flat-index fallback (C / 8 = 3)."""
+    from ocr_vi_invoice_b200 import ops
+    _setup()
+    b, h, w, c = case
+    g = torch.Generator(device="cuda").manual_seed(c)
+    x = torch.randn(b, h, w, c, device="cuda", generator=g).to(torch.bfloat16)
+    y = torch.full((b, h // 2, w // 2, c), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.maxpool3x3s2(x, y, b, h, w, c)
+    torch.cuda.synchronize()
+    assert torch.equal(nchw(y), F.max_pool2d(nchw(x), 3, 2, 1))
+
+
 @pytest.mark.parametrize("shape", [(1, 16, 16), (2, 24, 40)])
 def test_convT_igemm(shape):
     from ocr_vi_invoice_b200 import ops

@@ -79,6 +79,21 @@ def test_edge_cases_bit_exact():
     _assert_same(dots, max_candidates=37, min_area=4)
 
 
+def test_rows_wider_than_32_words():
+    """Rows of more than 1024 pixels: the row scan of pp_init carries a run from one 32-word segment into the next."""
+    rng = np.random.default_rng(5)
+    wide = np.zeros((40, 2200), np.float32)
+    wide[3, :] = 0.9                       # one run across the whole row (two segment boundaries)
+    wide[6, 1000:1060] = 0.9               # crosses x = 1024 inside partly filled words
+    wide[9, 992:1088] = 0.9                # whole words on both sides of the boundary
+    wide[12, 1024:2048] = 0.9              # a run that is exactly one segment
+    wide[15, 0:1024] = 0.9; wide[15, 1025:2200] = 0.9   # ends at a boundary, next run starts one pixel later
+    wide[18:22, 2040:2060] = 0.9           # block across x = 2048
+    wide[24:, :] = (rng.random((16, 2200)) > 0.35) * 0.9   # dense noise, long ragged runs
+    _assert_same(wide, min_area=1, box_thresh=0.5)
+    _assert_same(np.full((33, 1100), 0.9, np.float32))      # one component, 35 words per row, 2 strips
+
+
 def test_full_size_properties():
     """1024x1024, batch 4 (BASELINE config-2 map size): oracle parity + size-independent properties."""
     from oracle import postproc_oracle as ppo
