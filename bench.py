@@ -645,12 +645,29 @@ def main():
         balance = pk["tf_sustained"] * 1e12 / (pk["hbm_gbs"] * 1e9)
         hb = [(n, ms, lb[n]) for n, kind, ms, fl in launches if kind in ("conv", "stem") and n in lb and fl / lb[n] < balance]
         hbm_line = None
+        # HBM writes alone top out well below the copy rate (tools/bw_probe.py: ~3.9 vs 6.4 TB/s): measured live with a fill of
+        # 537 MB, and used for a second, direction-aware bound per launch: max(bytes / copy peak, bytes written / write peak)
+        wbuf = torch.empty(268435456, dtype=torch.bfloat16, device=dev)
+        for _ in range(3):
+            wbuf.zero_()
+        ev[0].record()
+        for _ in range(10):
+            wbuf.zero_()
+        ev[1].record()
+        torch.cuda.synchronize()
+        write_gbs = wbuf.numel() * 2 / (ev[0].elapsed_time(ev[1]) / 10 * 1e-3) / 1e9
+        del wbuf
+        lw = model._get_plan(x_dev).launch_write_bytes()
         if hb:
             hb_ms, hb_bytes = sum(h[1] for h in hb), sum(h[2] for h in hb)
+            bound_ms = sum(max(h[2] / (pk["hbm_gbs"] * 1e9), lw.get(h[0], 0.0) / (write_gbs * 1e9)) * 1e3 for h in hb)
             hbm_line = {"launches": len(hb), "bound": "hbm", "achieved": round(hb_bytes / (hb_ms * 1e-3) / 1e9, 1),
                         "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": round(hb_bytes / (hb_ms * 1e-3) / 1e9 / pk["hbm_gbs"], 4),
                         "share_of_step": round(hb_ms / tot_ms, 4), "algorithmic_bytes_per_step": int(hb_bytes),
-                        "what": "TMA-fed conv launches with FLOP/byte below the machine balance (1x1 convs, stem, ConvT)"}
+                        "write_peak": round(write_gbs, 1), "frac_directional": round(bound_ms / hb_ms, 4),
+                        "what": "TMA-fed conv launches with FLOP/byte below the machine balance (1x1 convs, stem, ConvT); "
+                                "frac_directional = sum over launches of max(bytes / copy peak, bytes written / write-only peak "
+                                "measured live with a 537 MB fill) / their time"}
         shares = {k: round(v["ms"] / tot_ms, 4) for k, v in by_kind.items()}
         if args.dump_launches:
             with open(args.dump_launches, "w") as f:

@@ -106,6 +106,7 @@ class Plan:
         self.step_flops: Dict[str, float] = {}
         self.step_kind: Dict[str, str] = {}
         self.step_bytes: Dict[str, float] = {}  # algorithmic HBM bytes: every operand read once, every output written once
+        self.step_write_bytes: Dict[str, float] = {}  # the written part of step_bytes (HBM writes top out below the copy rate)
         b = batch
         bf = lambda *s: torch.empty(*s, device=dev, dtype=torch.bfloat16)
         P = W.P
@@ -127,8 +128,10 @@ class Plan:
             in_px = b * in_h * in_w if ksize > 1 or stride == 1 else b * oh * ow  # a strided 1x1 reads only its pixels
             res_bytes = (2 * b * oh * ow * out_c if flags & ops.EPI_RES else 0) + (2 * b * oh * ow * out_c // 4 if flags & ops.EPI_RES_UP2 else 0)
             self.step_bytes[name] = float(in_px * in_c * 2 + out_bytes + res_bytes + w.numel() * 2)
+            self.step_write_bytes[name] = float(out_bytes)
             if chain is not None:
                 self.step_bytes[name] += float(chain[3].numel() * 2 + chain[0].numel() * 2)
+                self.step_write_bytes[name] += float(chain[3].numel() * 2)
             self.flops += op.flops
             self.n_igemm += 1
             return op
@@ -327,6 +330,10 @@ class Plan:
     def launch_bytes(self) -> Dict[str, float]:
         """Algorithmic HBM bytes per igemm launch (for the bandwidth side of the roofline)."""
         return dict(self.step_bytes)
+
+    def launch_write_bytes(self) -> Dict[str, float]:
+        """The bytes of launch_bytes() that are written."""
+        return dict(self.step_write_bytes)
 
     def tap(self, name: str) -> torch.Tensor:
         """NCHW fp32 copy of a recorded stage tensor (tests only)."""
