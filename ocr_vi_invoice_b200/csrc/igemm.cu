@@ -448,7 +448,7 @@ __device__ __forceinline__ void gelu_as2(float& x0, float& x1) {
 // (B200_EPI_GELU, the recogniser's Linear / conv + GELU layers); 4 = a second 1x1 GEMM chained onto the staged output chunks
 // (B200_EPI_CHAIN: conv3 + residual + ReLU of one Bottleneck and conv1 + BN + ReLU of the next in one launch).  Own
 // instantiations: the common epilogue must not pay registers (spills) for the rare ones.
-// kPair: cta_group::2 -- the two CTAs of a cluster run one 256-pixel x block_n UMMA per K step (variant 0 only): each stages
+// kPair: cta_group::2 -- the two CTAs of a cluster run one 256-pixel x block_n UMMA per K step (variants 0 and 2): each stages
 // its own 128-pixel A tile and HALF of the weight rows, rank 0 issues the MMAs and multicasts the commits, each CTA's
 // epilogue drains its own TMEM.  Per k-block an SM pulls A + B/2 instead of A + B through the L2 fabric, which is what the
 // weight-heavy small-spatial layers (layer3 / layer4 1x1 convs, the top of the neck) are bound by (~42 B/clk per SM).
