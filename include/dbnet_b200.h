@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define B200_ABI_VERSION 2
+#define B200_ABI_VERSION 3
 
 /* ---- status ------------------------------------------------------------------------------- */
 int         b200_abi_version(void);
@@ -69,7 +69,7 @@ enum {
                                   y = the normal output (bf16, 256 channels, with RES + RELU as flagged); every staged 64-channel
                                   chunk of y is also the A operand of y2[pixel][chain_n] += chunk x chain_w^T, and after the tile's
                                   last chunk y2 = relu?(y2 * chain_scale + chain_shift) is stored as bf16: the block output is never
-                                  re-read.  CONV mode, 1x1, out_c == n_pad == 256, chain_n 64 or 128, residual required.       */
+                                  re-read.  CONV mode, 1x1, out_c == n_pad == 256, chain_n 64 or 128 (residual optional).    */
     B200_EPI_DCN_COORDS = 32  /* offset_mask_conv only (out_c = 32): instead of the raw 27 channels, store
                                  the b200_dcn_coord records of the 9 taps, y = [pixel][9] records, so
                                  the DCN producers do no coordinate arithmetic (dcn.py:44-46 fused)    */
@@ -121,6 +121,16 @@ typedef struct b200_igemm_desc {
     int32_t      chain_ld;
     int32_t      chain_relu;  /* ReLU on the second output                                           */
     int32_t      chain_reserved;
+    /* Second K segment (NULL / 0 = none): a 1x1 stride-1 CONV whose K dimension continues over a second NHWC tensor,
+       y = epi([x | x2] . w^T) with w = [n_pad][in_c + in_c2].  A Bottleneck's first block uses it to run the projection
+       shortcut INSIDE conv3 (torchvision resnet.py:155-161: out = bn3(conv3(t)) + downsample(x) is one GEMM over [t | x]
+       once the BN scales are folded into the weights), instead of writing the projection and reading it back as a
+       residual.  x2 is sampled at (stride2 * oy, stride2 * ox).                                                         */
+    const void*  x2;          /* NHWC bf16, spatial size (in_h * stride2, in_w * stride2)             */
+    int32_t      in_c2;       /* channels of x2, multiple of 64                                       */
+    int32_t      x2_ld;       /* elements between consecutive pixels of x2; 0 = in_c2                 */
+    int32_t      stride2;     /* 1 or 2                                                               */
+    int32_t      x2_reserved;
 } b200_igemm_desc;
 
 typedef struct b200_igemm b200_igemm; /* opaque: TMA descriptors + launch geometry */

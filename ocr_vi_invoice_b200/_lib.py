@@ -30,6 +30,7 @@ class IgemmDesc(C.Structure):
         ("residual", C.c_void_p), ("y", C.c_void_p), ("offsets", C.c_void_p),
         ("chain_w", C.c_void_p), ("chain_scale", C.c_void_p), ("chain_shift", C.c_void_p), ("chain_y", C.c_void_p),
         ("chain_n", C.c_int32), ("chain_ld", C.c_int32), ("chain_relu", C.c_int32), ("chain_reserved", C.c_int32),
+        ("x2", C.c_void_p), ("in_c2", C.c_int32), ("x2_ld", C.c_int32), ("stride2", C.c_int32), ("x2_reserved", C.c_int32),
     ]
 
 
@@ -116,7 +117,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.b200_abi_version() != 2:
+    if lib.b200_abi_version() != 3:
         raise B200Error("libdbnet_b200.so ABI version mismatch")
     _lib = lib
     return lib

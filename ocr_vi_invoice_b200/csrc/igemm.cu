@@ -69,6 +69,7 @@ struct IgemmParams {
     int ss_shared;         // (always 1) one copy of the layer's whole scale / shift vectors per CTA
     int res_bytes;         // bytes of one residual box (16 KB, or 4 KB for the half-resolution RES_UP2 box)
     int b_resident;        // the whole weight matrix stays in shared memory for the CTA's lifetime (small N x K)
+    int kb_split;          // second K segment (x2): k-blocks >= kb_split come from tensor map a[1]; 0 = none
     int mma_group;         // share mode: the MMA warp issues the three kernel-column stages of a chunk as one group (small N)
     int dbg;               // development probes (B200_DEBUG): 1 = no MMA issue, 2 = no A loads, 4 = no epilogue math
     const __nv_bfloat16* x;
@@ -490,6 +491,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
         tma_prefetch_desc(&tm.b);
         if (!kGather) {
             tma_prefetch_desc(&tm.a[0]);
+            if (p.kb_split) tma_prefetch_desc(&tm.a[1]);
             if (p.stride == 2 && p.ksize == 3) {
                 tma_prefetch_desc(&tm.a[1]);
                 if (p.stride_w == 2) {
@@ -687,19 +689,24 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
                             }
                         }
                     }
+                    int ca = c0;  // channel offset inside the source tensor of this k-block
+                    if (!kGather && p.kb_split && kb >= p.kb_split) {  // second K segment: the other tensor (map a[1])
+                        view = 1;
+                        ca = c0 - p.kb_split * kBlockK;
+                    }
                     B200_TIMED_WAIT(0, mbar_wait(&sm.a_empty[s], ph ^ 1));
                     if constexpr (kPair) {
                         if (elect_one()) {
                             if (cta_rank == 0) mbar_arrive_expect_tx(&sm.a_full[s], tx_bytes);
                             const uint32_t bar0 = mapa_u32(smem_u32(&sm.a_full[s]), 0);
-                            tma_load_4d_2sm(sm.a + s * kABytes, &tm.a[view], bar0, c0, ax, ay, t.n);
+                            tma_load_4d_2sm(sm.a + s * kABytes, &tm.a[view], bar0, ca, ax, ay, t.n);
                             tma_load_2d_2sm(sm.b + s * b_bytes, &tm.b, bar0, kb * kBlockK,
                                             t.nb * p.block_n + static_cast<int>(cta_rank) * p.b_rows);
                         }
                     } else if (elect_one()) {
                         mbar_arrive_expect_tx(&sm.a_full[s], tx_bytes);
                         if (!kGather && !(p.dbg & 2))
-                            tma_load_4d(sm.a + s * kABytes, &tm.a[view], &sm.a_full[s], c0, ax, ay, t.n);
+                            tma_load_4d(sm.a + s * kABytes, &tm.a[view], &sm.a_full[s], ca, ax, ay, t.n);
                         if (!p.b_resident) {
                             tma_load_2d(sm.b + s * b_bytes, &tm.b, &sm.a_full[s], kb * kBlockK, t.nb * p.block_n);
                             if (kGather && p.block_n > 256)  // a weight box holds at most 256 rows
@@ -963,13 +970,13 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
             int ld_u = u_first, ld_chunk = 0;
             auto issue_load = [&](int slot) {
                 if (ld_u >= num_units) return;
-                if (ld_chunk < NC) {
+                if (ld_chunk < NC && p.res_tma) {
                     const TileCoord t = decode_tile(p, unit_tile(ld_u));
                     if (elect_one()) {
                         mbar_arrive_expect_tx(&sm.res_full[slot], p.res_bytes);
                         tma_load_4d(sm.epi + slot * kABytes, &tm.res, &sm.res_full[slot], ld_chunk * 64, t.x0, t.y0, t.n);
                     }
-                } else if (elect_one()) {
+                } else if (elect_one()) {  // (also the main chunks of a chain without residual)
                     mbar_arrive(&sm.res_full[slot]);  // tail chunk: nothing to load, the buffer is simply free
                 }
                 __syncwarp();
@@ -1239,7 +1246,7 @@ igemm_kernel(const __grid_constant__ TmapPack tm, const IgemmParams p, const __g
                     const uint32_t buf = smem_u32(sm.epi) + static_cast<uint32_t>(my_slot) * kABytes;
                     const uint32_t mine = buf + static_cast<uint32_t>(row) * 128;
                     const uint32_t rsd = buf + static_cast<uint32_t>(rrow) * 128;
-                    B200_TIMED_WAIT(8, if (p.res_tma) mbar_wait(&sm.res_full[my_slot], my_par); else mbar_wait(&sm.slot_free[my_slot], my_par ^ 1));
+                    B200_TIMED_WAIT(8, if (p.res_tma || kEpi == 4) mbar_wait(&sm.res_full[my_slot], my_par); else mbar_wait(&sm.slot_free[my_slot], my_par ^ 1));
                     uint4 rup[kUp2 ? 8 : 1];
                     if constexpr (up2) {  // the 4 KB half-resolution box is shared by four pixels: read it before anyone overwrites
 #pragma unroll
@@ -1640,6 +1647,13 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     const int x_ld = d->x_ld ? d->x_ld : d->in_c;
     if (d->mode != B200_IGEMM_STEM && (x_ld < d->in_c || (x_ld % 8))) return set_error("igemm: bad x_ld");
     if (d->mode == B200_IGEMM_DCN && !d->offsets) return set_error("igemm: DCN needs offsets");
+    if (d->x2) {
+        const int x2_ld = d->x2_ld ? d->x2_ld : d->in_c2;
+        if (d->mode != B200_IGEMM_CONV || d->ksize != 1 || d->stride != 1 || d->in_c2 <= 0 || (d->in_c2 % 64) != 0 ||
+            (d->stride2 != 1 && d->stride2 != 2) || x2_ld < d->in_c2 || (x2_ld % 8) || (reinterpret_cast<uintptr_t>(d->x2) & 15) ||
+            (d->flags & (B200_EPI_GELU | B200_EPI_HEAD_DOT | B200_EPI_DCN_COORDS)))
+            return set_error("igemm: a second K segment (x2) is for 1x1 stride-1 CONV launches, in_c2 a multiple of 64, stride2 1 or 2");
+    }
     if ((d->flags & (B200_EPI_RES | B200_EPI_RES_UP2)) && !d->residual) return set_error("igemm: residual missing");
     if ((d->flags & B200_EPI_HEAD_DOT) &&
         (!(d->flags & B200_EPI_SHUFFLE2) || d->shuf_c != 64 || d->out_c != 256 || d->mode != B200_IGEMM_CONV || !d->offsets ||
@@ -1651,10 +1665,10 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
         return set_error("igemm: GELU is for plain bf16 conv outputs with out_c a multiple of 64 (optionally + RES)");
     if (d->flags & B200_EPI_CHAIN) {
         if (d->mode != B200_IGEMM_CONV || d->ksize != 1 || d->stride != 1 || d->out_c != 256 || d->n_pad != 256 || (d->chain_n != 64 && d->chain_n != 128) ||
-            !(d->flags & B200_EPI_RES) || !d->chain_w || !d->chain_scale || !d->chain_shift || !d->chain_y || (d->chain_ld % 8) ||
-            d->chain_ld < d->chain_n || d->in_c > 256 ||
+            !d->chain_w || !d->chain_scale || !d->chain_shift || !d->chain_y || (d->chain_ld % 8) ||
+            d->chain_ld < d->chain_n || d->in_c + (d->x2 ? d->in_c2 : 0) > 256 ||
             (d->flags & (B200_EPI_RES_UP2 | B200_EPI_OUT_F32 | B200_EPI_SHUFFLE2 | B200_EPI_DCN_COORDS | B200_EPI_HEAD_DOT | B200_EPI_GELU)))
-            return set_error("igemm: CHAIN is for a 1x1 stride-1 conv with out_c == n_pad == 256, in_c <= 256, a residual and chain_n 64 or 128");
+            return set_error("igemm: CHAIN is for a 1x1 stride-1 conv with out_c == n_pad == 256, in_c <= 256 and chain_n 64 or 128");
         if ((reinterpret_cast<uintptr_t>(d->chain_w) | reinterpret_cast<uintptr_t>(d->chain_y) | reinterpret_cast<uintptr_t>(d->chain_scale) |
              reinterpret_cast<uintptr_t>(d->chain_shift)) & 15)
             return set_error("igemm: chain pointers must be 16-byte aligned");
@@ -1747,7 +1761,8 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     p.tiles_y = (p.out_h + p.tile_h - 1) / p.tile_h;
     p.num_n_blocks = d->n_pad / block_n;
     p.num_tiles = p.batch * p.tiles_x * p.tiles_y * p.num_n_blocks;
-    p.cchunks = (d->mode == B200_IGEMM_STEM) ? 1 : d->in_c / kBlockK;
+    p.cchunks = (d->mode == B200_IGEMM_STEM) ? 1 : (d->in_c + (d->x2 ? d->in_c2 : 0)) / kBlockK;
+    p.kb_split = d->x2 ? d->in_c / kBlockK : 0;
     p.k_blocks = taps * p.cchunks;
     p.out_ld = d->out_ld;
     p.res_ld = d->res_ld;
@@ -1825,9 +1840,9 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     p.num_units = pair ? ((px_tiles + 1) / 2) * p.num_n_blocks : p.num_tiles;
     if (pair) b_bytes = p.b_rows * 128;
     p.ss_shared = 1;
-    if ((d->flags & B200_EPI_CHAIN) && (!p.b_resident || !p.res_tma)) {
+    if ((d->flags & B200_EPI_CHAIN) && !p.b_resident) {
         delete op;
-        return set_error("igemm: CHAIN needs resident weights and the TMA residual path");
+        return set_error("igemm: CHAIN needs resident weights");
     }
     const int fixed = 1024 /*alignment*/ + 1024 /*barriers*/ + 8 * p.ss_half /*scale+shift*/ +
                       (p.b_resident ? p.k_blocks * b_bytes : 0) + p.chain_bytes;
@@ -1993,6 +2008,11 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
         if (d->stride == 1) {
             err |= encode_nhwc(&op->tm.a[0], d->x, C, W, H, d->batch, LD, 1, 1, W, H * W, p.tile_w,
                                share ? p.tile_h + 2 : p.tile_h, "activations");
+            if (!err && d->x2) {  // second K segment: x2 sampled at (stride2 * oy, stride2 * ox)
+                const uint64_t s2 = d->stride2, LD2 = d->x2_ld ? d->x2_ld : d->in_c2;
+                err |= encode_nhwc(&op->tm.a[1], d->x2, d->in_c2, W, H, d->batch, LD2, s2, s2, W * s2, H * s2 * W * s2, p.tile_w,
+                                   p.tile_h, "second K segment");
+            }
         } else if (stride_w == 1) {
             // stride (2, 1): two row-parity views, full width
             for (int v = 0; v < 2 && !err; ++v) {

@@ -61,6 +61,15 @@ class PreparedWeights:
                 conv_bn(p + ".conv3", blk.conv3.weight, blk.bn3)
                 if blk.downsample is not None:
                     conv_bn(p + ".down", blk.downsample[0].weight, blk.downsample[1])
+                    # The projection shortcut inside conv3 (resnet.py:155-161): bn3(conv3(t)) + bn_d(conv_d(x)) is ONE GEMM over
+                    # K = [t | x] once both BN scales are folded into the weights (fp32, before the bf16 rounding); the
+                    # shifts add up.  The launch reads x as a second K segment (b200_igemm_desc.x2).
+                    s3, t3 = _bn_fold(blk.bn3)
+                    sd, td = _bn_fold(blk.downsample[1])
+                    w3 = ops.pack_conv_weight(to(blk.conv3.weight) * to(s3).view(-1, 1, 1, 1))
+                    wd = ops.pack_conv_weight(to(blk.downsample[0].weight) * to(sd).view(-1, 1, 1, 1), w3.shape[0])
+                    wf = torch.cat([w3, wd], dim=1).contiguous()
+                    P[p + ".conv3d"] = (wf, torch.ones(wf.shape[0], device=device), ops.pad_vec(to(t3) + to(td), wf.shape[0]))
         nk = model.neck
         for i in range(4):
             lc = nk.lateral_convs[i]
@@ -112,11 +121,11 @@ class Plan:
         P = W.P
 
         def igemm(name, mode, x, key, y, *, in_h, in_w, in_c, out_c, ksize, stride, flags=0, residual=None, res_ld=0,
-                  offsets=None, shuf_c=0, out_ld=None, x_ld=0, chain=None):
+                  offsets=None, shuf_c=0, out_ld=None, x_ld=0, chain=None, x2=None, in_c2=0, stride2=1):
             w, s, t = P[key]
             op = ops.Igemm(mode, x, w, s, t, y, batch=b, in_h=in_h, in_w=in_w, in_c=in_c, out_c=out_c, ksize=ksize,
                            stride=stride, flags=flags, residual=residual, res_ld=res_ld, offsets=offsets, shuf_c=shuf_c,
-                           out_ld=out_ld, x_ld=x_ld, name=name, chain=chain)
+                           out_ld=out_ld, x_ld=x_ld, name=name, chain=chain, x2=x2, in_c2=in_c2, stride2=stride2)
             self.steps.append(op)
             self.names.append(name)
             self.step_flops[name] = op.flops
@@ -128,6 +137,8 @@ class Plan:
             in_px = b * in_h * in_w if ksize > 1 or stride == 1 else b * oh * ow  # a strided 1x1 reads only its pixels
             res_bytes = (2 * b * oh * ow * out_c if flags & ops.EPI_RES else 0) + (2 * b * oh * ow * out_c // 4 if flags & ops.EPI_RES_UP2 else 0)
             self.step_bytes[name] = float(in_px * in_c * 2 + out_bytes + res_bytes + w.numel() * 2)
+            if x2 is not None:
+                self.step_bytes[name] += float(b * oh * ow * in_c2 * 2)  # the second K segment reads only the pixels it samples
             self.step_write_bytes[name] = float(out_bytes)
             if chain is not None:
                 self.step_bytes[name] += float(chain[3].numel() * 2 + chain[0].numel() * 2)
@@ -154,6 +165,7 @@ class Plan:
         feats = []
         import os
         use_chain = not os.environ.get("B200_NO_CHAIN")
+        use_fused_down = not os.environ.get("B200_NO_FUSED_DOWN")
         chained_t1 = None  # conv1 output of this block, already produced by the previous block's conv3 launch
         for li, nblocks, width in LAYER_CFG:
             cout = width * 4
@@ -178,7 +190,10 @@ class Plan:
                 else:
                     igemm(p + ".conv2", ops.IGEMM_CONV, t1, p + ".conv2", t2, in_h=h, in_w=w, in_c=width, out_c=width,
                           ksize=3, stride=stride, flags=ops.EPI_RELU)
-                if bi == 0:
+                fused_down = (bi == 0 and use_fused_down)
+                if fused_down:
+                    idn = None  # the projection shortcut runs inside conv3 (second K segment)
+                elif bi == 0:
                     idn = bf(b, ho, wo, cout)
                     igemm(p + ".down", ops.IGEMM_CONV, x, p + ".down", idn, in_h=h, in_w=w, in_c=cin, out_c=cout,
                           ksize=1, stride=stride)
@@ -193,8 +208,12 @@ class Plan:
                     w2, s2, t2_ = P[nxt]
                     chained_t1 = bf(b, ho, wo, w2.shape[0])
                     chain = (w2, s2, t2_, chained_t1, True)
-                igemm(p + ".conv3", ops.IGEMM_CONV, t2, p + ".conv3", y, in_h=ho, in_w=wo, in_c=width, out_c=cout,
-                      ksize=1, stride=1, flags=ops.EPI_RES | ops.EPI_RELU, residual=idn, res_ld=cout, chain=chain)
+                if fused_down:
+                    igemm(p + ".conv3", ops.IGEMM_CONV, t2, p + ".conv3d", y, in_h=ho, in_w=wo, in_c=width, out_c=cout,
+                          ksize=1, stride=1, flags=ops.EPI_RELU, chain=chain, x2=x, in_c2=cin, stride2=stride)
+                else:
+                    igemm(p + ".conv3", ops.IGEMM_CONV, t2, p + ".conv3", y, in_h=ho, in_w=wo, in_c=width, out_c=cout,
+                          ksize=1, stride=1, flags=ops.EPI_RES | ops.EPI_RELU, residual=idn, res_ld=cout, chain=chain)
                 if keep_taps and W.dcn and li >= 2:
                     self.taps[f"backbone.model.{p}.bn2"] = (t2, width)
                 x, cin, h, w = y, cout, ho, wo

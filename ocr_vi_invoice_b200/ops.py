@@ -129,11 +129,12 @@ class Igemm:
                  stride: int, flags: int = 0, residual: Optional[torch.Tensor] = None,
                  offsets: Optional[torch.Tensor] = None, out_ld: Optional[int] = None, res_ld: int = 0,
                  shuf_c: int = 0, block_n: int = 0, x_ld: int = 0, stride_w: int = 0, name: str = "",
-                 chain: Optional[tuple] = None):
-        """`chain` = (w2, scale2, shift2, y2, relu2): EPI_CHAIN, the next block's 1x1 conv folded into this launch."""
+                 chain: Optional[tuple] = None, x2: Optional[torch.Tensor] = None, in_c2: int = 0, stride2: int = 1):
+        """`chain` = (w2, scale2, shift2, y2, relu2): EPI_CHAIN, the next block's 1x1 conv folded into this launch.
+        `x2` / `in_c2` / `stride2`: second K segment of a 1x1 conv (w = [n_pad][in_c + in_c2]), see dbnet_b200.h."""
         lib = _lib.load()
         self.name = name
-        self._keep = (x, w, scale, shift, y, residual, offsets)
+        self._keep = (x, w, scale, shift, y, residual, offsets, x2)
         self._chain = chain
         n_pad = w.shape[0]
         assert scale.numel() == n_pad and shift.numel() == n_pad, "scale/shift must be padded to n_pad"
@@ -146,6 +147,8 @@ class Igemm:
             stride_w=stride_w,
             x=_lib.ptr(x), w=_lib.ptr(w), scale=_lib.ptr(scale), shift=_lib.ptr(shift),
             residual=_lib.ptr(residual), y=_lib.ptr(y), offsets=_lib.ptr(offsets))
+        if x2 is not None:
+            d.x2, d.in_c2, d.x2_ld, d.stride2 = _lib.ptr(x2), in_c2, x2.shape[-1], stride2
         if chain is not None:
             w2, s2, t2, y2, relu2 = chain
             assert w2.dtype == torch.bfloat16 and w2.is_contiguous() and w2.shape[1] == out_c

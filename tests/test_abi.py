@@ -31,7 +31,7 @@ def test_header_symbols_exported(lib):
 
 
 def test_status_calls_work_without_gpu(lib):
-    assert lib.b200_abi_version() == 2
+    assert lib.b200_abi_version() == 3
     assert lib.b200_postproc_workspace_bytes(1, 64, 64, 100) > 2 * 64 * 64 * 4
     assert lib.b200_postproc_workspace_bytes(0, 64, 64, 100) == -1
     # argument validation happens before any CUDA call and reports through b200_last_error
@@ -44,7 +44,7 @@ def test_box_record_layout():
     from ocr_vi_invoice_b200 import _lib, postprocess
     assert ctypes.sizeof(_lib.Box) == 48 == postprocess._BOX_DTYPE.itemsize
     assert _lib.Box.qsum.offset == 40 == postprocess._BOX_DTYPE.fields["qsum"][1]
-    assert ctypes.sizeof(_lib.IgemmDesc) == 16 * 4 + 11 * 8 + 4 * 4  # ABI 2: chain_* fields appended
+    assert ctypes.sizeof(_lib.IgemmDesc) == 16 * 4 + 12 * 8 + 8 * 4  # ABI 2: chain_* fields appended; ABI 3: the second K segment (x2)
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

@@ -231,6 +231,52 @@ def test_chained_second_gemm(shape, n2):
     assert torch.equal(y0, y)
 
 
+SEG2_CASES = [
+    # (batch, H, W, C1, C2, Cout, stride2, chain_n or 0)
+    (2, 24, 40, 64, 64, 256, 1, 0),      # layer1.0: conv3 over [t | x]
+    (2, 24, 40, 64, 64, 256, 1, 64),     # ... with the next conv1 chained on (no residual on this path)
+    (1, 20, 36, 128, 256, 512, 2, 0),    # layer2.0: projection input at stride 2, two n-blocks
+    (2, 16, 16, 256, 512, 1024, 2, 0),   # layer3.0
+    (1, 12, 20, 512, 1024, 2048, 2, 0),  # layer4.0: 24 k-blocks, CTA pair
+    (16, 32, 32, 512, 1024, 2048, 2, 0),
+]
+
+
+@pytest.mark.parametrize("case", SEG2_CASES, ids=lambda c: "b%d_%dx%d_c%d+%d_o%d_s%d_ch%d" % c)
+def test_second_k_segment(case):
+    """b200_igemm_desc.x2: y = relu([x | x2 at stride2] . w^T + shift) -- a Bottleneck's projection shortcut inside conv3."""
+    from ocr_vi_invoice_b200 import ops
+    _setup()
+    b, h, w, c1, c2, co, s2, n2 = case
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(c1 + c2 + h)
+    x = torch.randn(b, c1, h, w, device=dev, generator=g)
+    x2 = torch.randn(b, c2, h * s2, w * s2, device=dev, generator=g)
+    w1 = torch.randn(co, c1, 1, 1, device=dev, generator=g) / (c1 + c2) ** 0.5
+    w2 = torch.randn(co, c2, 1, 1, device=dev, generator=g) / (c1 + c2) ** 0.5
+    sc, sh = torch.rand(co, device=dev, generator=g) + 0.5, torch.randn(co, device=dev, generator=g) * 0.1
+    wp = torch.cat([ops.pack_conv_weight(w1, co), ops.pack_conv_weight(w2, co)], dim=1).contiguous()
+    y = torch.full((b, h, w, co), float("nan"), device=dev, dtype=torch.bfloat16)
+    chain, y2 = None, None
+    if n2:
+        wc = torch.randn(n2, co, 1, 1, device=dev, generator=g) / co ** 0.5
+        sc2, sh2 = torch.rand(n2, device=dev, generator=g) + 0.5, torch.randn(n2, device=dev, generator=g) * 0.1
+        y2 = torch.full((b, h, w, n2), float("nan"), device=dev, dtype=torch.bfloat16)
+        chain = (ops.pack_conv_weight(wc, n2), sc2, sh2, y2, True)
+    op = ops.Igemm(ops.IGEMM_CONV, nhwc(x), wp, sc, sh, y, batch=b, in_h=h, in_w=w, in_c=c1, out_c=co, ksize=1, stride=1,
+                   flags=ops.EPI_RELU, x2=nhwc(x2), in_c2=c2, stride2=s2, chain=chain, name=str(case))
+    op()
+    op()
+    torch.cuda.synchronize()
+    bfr = lambda t: t.to(torch.bfloat16).float()
+    ref = F.conv2d(bfr(x), bfr(w1)) + F.conv2d(bfr(x2), bfr(w2), stride=s2)
+    ref = (ref * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)).relu()
+    close(nchw(y), ref)
+    if n2:
+        ref2 = (F.conv2d(nchw(y), bfr(wc)) * sc2.view(1, -1, 1, 1) + sh2.view(1, -1, 1, 1)).relu()
+        close(nchw(y2), ref2)
+
+
 DCN_CASES = [
     # (batch, Hin, Win, C, Cout, stride, offset sigma)
     (1, 16, 16, 64, 64, 1, 0.0),
