@@ -1822,8 +1822,10 @@ extern "C" int b200_igemm_create(const b200_igemm_desc* d, b200_igemm** out) {
     // Measured per layer (batch 16 @1024^2, pair on vs off): 3x3 256->256 at 256^2 0.851 -> 0.769 ms (1.6 PFLOP/s: the SS
     // operand reads, A + B per instruction, drop from 12 to 8 KB), 128^2 0.209 -> 0.189, lat3 (K = 2048) 0.030 -> 0.027;
     // but short-K layers lose to the cross-CTA hand-shakes per tile (conv3 with K = 256: 0.072 -> 0.079, lat0 0.239 ->
-    // 0.275), and K = 1024..2048 1x1 convs do not move.  Hence: at least 16 k-blocks per tile.
-    int pair_min_kb = 16;
+    // 0.275, K = 512 layers 0.065 -> 0.072), and K = 1024..2048 1x1 convs do not move.  Hence: at least 12 k-blocks per tile
+    // (12 = the 256 + 512 -> 1024 conv3 that carries its projection shortcut as second K segment: 0.096 -> 0.087 ms; without
+    // the pair it pulled 94 B/clk per SM through the L2 fabric).
+    int pair_min_kb = 12;
     if (const char* e = getenv("B200_PAIR_MIN_KB")) pair_min_kb = atoi(e);
     // Share-mode layers (3x3 stride 1, N = 128) pair as well: the DB head's 256 -> 128 conv pulled 816 KB per tile through the
     // L2 fabric (weights 576 KB of it) at the ~13 TB/s the fabric gives when every SM pulls; the pair halves the weight part.
