@@ -68,6 +68,28 @@ def test_pack_conv_weight_is_chunk_then_tap_major():
     torch.testing.assert_close(p[2, (1 * 9 + 4) * 64 + 7], w[2, 71, 1, 1].to(torch.bfloat16).float())
 
 
+def test_projection_shortcut_folds_into_conv3(model):
+    """engine.PreparedWeights: [t | x] . [s3 W3 | sd Wd]^T + (t3 + td) == bn3(conv3(t)) + bn_d(conv_d(x)) (resnet.py:155-161)."""
+    from ocr_vi_invoice_b200.model.det.engine import PreparedWeights
+    sd = make_state_dict(11)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    W = PreparedWeights(model, torch.device("cpu"))
+    for li, stride in ((1, 1), (2, 2)):
+        blk = model.backbone.model.__getattr__(f"layer{li}")[0]
+        wf, scale, shift = W.P[f"layer{li}.0.conv3d"]
+        c1, c2 = blk.conv3.weight.shape[1], blk.downsample[0].weight.shape[1]
+        assert wf.shape == (blk.conv3.weight.shape[0], c1 + c2) and (scale == 1).all()
+        t = torch.randn(2, c1, 6, 5)
+        x = torch.randn(2, c2, 6 * stride, 5 * stride)
+        with torch.no_grad():
+            ref = blk.bn3(blk.conv3(t)) + blk.downsample(x)
+        k = torch.cat([t, x[:, :, ::stride, ::stride]], dim=1)              # the GEMM's K axis: conv3 input, then the block input
+        got = torch.einsum("nkhw,ok->nohw", k, wf.float()) + shift.view(1, -1, 1, 1)
+        err = (got - ref).abs().max().item()
+        assert err < 0.03 * ref.abs().max().item() + 1e-3, (li, err)         # bf16 weights vs fp32 modules
+
+
 def test_pack_stem_weight_equals_conv7x7():
     """The space-to-depth re-layout reproduces conv 7x7 s2 p3 exactly (fp32 emulation of pack + GEMM)."""
     g = torch.Generator().manual_seed(0)
