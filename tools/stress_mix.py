@@ -44,6 +44,24 @@ def chained(name, b, hw, n2):
     return name, op, y2
 
 
+def projected(name, b, hw, c1, c2, co, s2, n2=0):
+    """conv3 with the projection shortcut as second K segment (x2), optionally with the next conv1 chained on (no residual)."""
+    dev = "cuda"
+    x = torch.randn(b, hw, hw, c1, device=dev).to(torch.bfloat16)
+    x2 = torch.randn(b, hw * s2, hw * s2, c2, device=dev).to(torch.bfloat16)
+    wt = (torch.randn(co, c1 + c2, device=dev) / (c1 + c2) ** 0.5).to(torch.bfloat16)
+    sc, sh = torch.ones(co, device=dev), torch.randn(co, device=dev) * 0.1
+    y = torch.empty(b, hw, hw, co, device=dev, dtype=torch.bfloat16)
+    chain, out = None, y
+    if n2:
+        wc = (torch.randn(n2, co, device=dev) / co ** 0.5).to(torch.bfloat16)
+        y2 = torch.empty(b, hw, hw, n2, device=dev, dtype=torch.bfloat16)
+        chain, out = (wc, torch.rand(n2, device=dev) + 0.5, torch.randn(n2, device=dev) * 0.1, y2, True), y2
+    op = ops.Igemm(ops.IGEMM_CONV, x, wt, sc, sh, y, batch=b, in_h=hw, in_w=hw, in_c=c1, out_c=co, ksize=1, stride=1,
+                   flags=ops.EPI_RELU, x2=x2, in_c2=c2, stride2=s2, chain=chain, name=name)
+    return name, op, out
+
+
 def dcn(name, b, hw, c, s):
     dev = "cuda"
     x = torch.randn(b, hw, hw, c, device=dev).to(torch.bfloat16)
@@ -141,6 +159,8 @@ def main():
         *maybe(chained, "chained conv3 -> conv1 (64)", b, 256, 64),
         *maybe(chained, "chained conv3 -> conv1 (128)", b, 256, 128),
         conv("layer2.conv1 512->128", b, 128, 128, 512, 128, 1, 1, ops.EPI_RELU),
+        *maybe(projected, "projection in conv3, layer1.0 (chained)", b, 256, 64, 64, 256, 1, 64),
+        *maybe(projected, "projection in conv3, layer3.0 (pair)", b, 64, 256, 512, 1024, 2),
     ]
     torch.cuda.synchronize()
     ref = {}
